@@ -1,0 +1,199 @@
+/*
+ * scatt.h - C ABI of libscatt.so, the sm_100a kernels behind scattennet_b200.
+ *
+ * The reference (tinh2044/SCAttenNet) has no FFI / plugin interface: its
+ * boundary is the Python nn.Module surface.  This header
+ * is the "thin C-ABI extension" the host-side PyTorch modules call through
+ * ctypes; every entry point names the reference code it replaces
+ * (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, scratch); the library
+ *     never allocates, never synchronises, never touches the default stream:
+ *     work is enqueued on `stream` (a cudaStream_t passed as void*), so calls
+ *     are capturable into CUDA graphs;
+ *   - return value: 0 on success, a negative SCATT_ERR_* code otherwise;
+ *     scatt_last_error() returns a thread-local message for the last failure;
+ *   - re-entrant across host threads and streams; no global mutable state
+ *     besides per-kernel attribute initialisation (idempotent);
+ *   - sm_100a only.  There is no CPU fallback: on a machine without a B200
+ *     the compute entry points return SCATT_ERR_CUDA.
+ *
+ * "Split planes": activations and weights that feed a tensor-core GEMM are
+ * stored as 16-bit hi/lo planes, `planes[0] = rn16(x)`, `planes[1] =
+ * rn16(x - planes[0])`, laid out [2][rows][cols] row-major (fp16 or bf16, see
+ * scatt_plane_fmt).  A GEMM with `terms` = 1 uses hi*hi only, 2 adds lo*hi
+ * (activation low part), 3 adds hi*lo as well (fp32-grade products).
+ */
+#ifndef SCATT_H_
+#define SCATT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCATT_ABI_VERSION 1
+#define SCATT_MAX_GROUP 4 /* problems per grouped launch (the 3 anatomical streams + spare) */
+
+enum scatt_error {
+  SCATT_OK = 0,
+  SCATT_ERR_INVALID = -1,     /* bad argument (shape, alignment, enum) */
+  SCATT_ERR_UNSUPPORTED = -2, /* valid request this build does not implement */
+  SCATT_ERR_CUDA = -3,        /* CUDA runtime / driver error (message has the string) */
+  SCATT_ERR_KERNEL = -4       /* a kernel reported a device-side failure (pipeline time-out) */
+};
+
+enum scatt_engine {
+  SCATT_ENGINE_SIMT = 0,   /* fp32 FMA on CUDA cores: exact-order reference engine, fp32 tier */
+  SCATT_ENGINE_TCGEN05 = 1 /* TMA -> smem -> tcgen05.mma (TMEM accumulators), split-plane operands */
+};
+
+enum scatt_plane_fmt { SCATT_PLANE_F16 = 0, SCATT_PLANE_BF16 = 1 };
+
+enum scatt_act { SCATT_ACT_NONE = 0, SCATT_ACT_GELU = 1 /* exact erf */, SCATT_ACT_RELU = 2 };
+
+enum scatt_residual_mode { SCATT_RES_NONE = 0, SCATT_RES_BEFORE_LN = 1, SCATT_RES_AFTER_LN = 2 };
+
+enum scatt_attention_kind { SCATT_ATTN_SELF = 0, SCATT_ATTN_CAUSAL = 1, SCATT_ATTN_CROSS = 2 };
+
+/* ------------------------------------------------------------------ misc */
+
+int scatt_abi_version(void);
+const char* scatt_version(void);
+const char* scatt_last_error(void);
+/* Number of kernels this library has launched from the calling process (all
+ * threads); bench.py's `gpu_launches` is the difference across the timed region. */
+uint64_t scatt_launch_count(void);
+/* 0 if the current device is sm_100 and the kernels are loadable. */
+int scatt_device_check(void);
+
+/* ------------------------------------------------------------------ split planes */
+
+/* planes[0..1][rows][cols] <- split(scale * x[rows][ldx]); used to pack weights
+ * once (scale = 0.5 folds the `key_value_states / 2` of CrossAttention,
+ * model/attention.py:103, into W_v exactly) and to import fp32 activations. */
+int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale,
+                       void* planes, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ K1: front end */
+
+/* One anatomical stream of the fused front end.  Replaces, in one pass over
+ * keypoints[B,T,K,2]: the region gather `keypoints[:, :, idx, :]`
+ * (model/__init__.py:133-142), the x / y split (model/keypoint_module.py:23-24),
+ * CoordinateMapping (model/layers.py:118-123), LearningPositionEmbedding
+ * (model/layers.py:20-30, table row t+2) and first_self_norm /
+ * first_causal_norm (model/keypoint_module.py:155-162).
+ * Branch 0 is the "self" branch, branch 1 the "causal" branch; `coord[br]`
+ * says which coordinate (0 = x, 1 = y) feeds it (cfg self_attn_x). */
+typedef struct scatt_frontend_stream {
+  const int32_t* joint_idx; /* [n_joints] indices into K */
+  int32_t n_joints;         /* <= 32 */
+  int32_t coord[2];
+  const float* map_w[2];    /* [D, n_joints] mapping weight of the coordinate feeding branch br */
+  const float* map_b[2];    /* [D] */
+  const float* pos[2];      /* [max_pos + 2, D] position tables (self, causal) */
+  const float* ln_g[2];     /* [D] */
+  const float* ln_b[2];     /* [D] */
+  float* out[2];            /* [B*T, D] fp32, may be NULL */
+  void* out_planes[2];      /* [2][B*T][D] split planes, may be NULL */
+  float* gathered;          /* optional [B,T,n_joints,2] exact copy of the gathered region, may be NULL */
+} scatt_frontend_stream;
+
+int scatt_frontend(const float* keypoints, int B, int T, int K, int D, const scatt_frontend_stream* streams_host,
+                   int n_streams, int max_pos, int plane_fmt, void* stream);
+
+/* x[B,T,D] + table[t+2] -> LayerNorm -> out (+ planes).  The same two steps
+ * for callers that enter below KeypointModule (SeparativeCoordinateAttention /
+ * Encoder called directly: model/keypoint_module.py:155-162, model/encoder.py:80-82). */
+int scatt_posembed_layernorm(const float* x, const float* table, const float* ln_g, const float* ln_b, float* out,
+                             void* out_planes, int B, int T, int D, int max_pos, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ K2: linear + epilogue */
+
+typedef struct scatt_epilogue {
+  int32_t act_pre;       /* scatt_act applied to (acc + bias) * colscale */
+  int32_t residual_mode; /* scatt_residual_mode */
+  int32_t layer_norm;    /* 1: LayerNorm over the N outputs of a row (eps, affine) */
+  int32_t act_post;      /* scatt_act applied last */
+  float clamp;           /* > 0: clamp to [-clamp, clamp] (RecognitionHead, model/__init__.py:56-60) */
+  int32_t scale_cols;    /* columns [0, scale_cols) are multiplied by `scale` after the bias ... */
+  float scale;           /* ... (q = (x Wq + bq) * head_dim^-0.5, model/attention.py:49) */
+  float ln_eps;          /* 1e-5 */
+} scatt_epilogue;
+
+/* One problem of a grouped launch: y = epilogue(x W^T + bias).
+ * Replaces nn.Linear call sites of the path with their trailing elementwise /
+ * LayerNorm ops fused: q/k/v/out projections (model/attention.py:49-51,74),
+ * FeedForward (model/layers.py:103-108), residual + LayerNorm
+ * (model/keypoint_module.py:62-72,98-107), ResidualBlock linears + LayerNorm +
+ * ReLU (model/residual.py:25-38), CoordinatesFusion / InvertedResidual linears
+ * (model/fusion.py:37-53,67-78), RecognitionHead classifiers + clamp
+ * (model/__init__.py:49-60). */
+typedef struct scatt_linear_problem {
+  const float* x;        /* SIMT engine: [M, K] fp32, row stride ldx */
+  const void* x_planes;  /* TCGEN05 engine: [2][M][K] split planes (contiguous) */
+  const float* w;        /* SIMT engine: [N, K] fp32 contiguous (nn.Linear.weight) */
+  const void* w_planes;  /* TCGEN05 engine: [2][N][K] split planes */
+  const float* bias;     /* [N] or NULL */
+  const float* residual; /* [M, N] fp32 (row stride ldres) or NULL */
+  const float* ln_g;     /* [N] */
+  const float* ln_b;     /* [N] */
+  float* y;              /* [M, N] fp32, row stride ldy; may be NULL if y_planes is given and no LayerNorm scratch is needed */
+  void* y_planes;        /* [2][M][N] split planes or NULL */
+} scatt_linear_problem;
+
+int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx,
+                 int64_t ldres, int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms,
+                 void* stream);
+
+/* Row-wise tail on an fp32 [M, N] matrix: optional LayerNorm, residual after,
+ * activation, clamp, split-plane export.  In-place (y == z) is allowed. */
+int scatt_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* residual, int64_t ldres,
+                  const float* ln_g, const float* ln_b, const scatt_epilogue* epilogue_host, float* y, int64_t ldy,
+                  void* y_planes, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ K3: stream attention */
+
+/* softmax(q k^T + mask) v per head for one stream; q is already scaled.
+ * Replaces the score / mask / softmax / PV block of SelfAttention,
+ * CrossAttention and SelfCausalAttention (model/attention.py:53-73,105-125,
+ * 155-179) and the mask builders (model/utils.py:3-28) without materialising
+ * scores or masks.  Mask semantics: `key_mask` ([B,Tk] uint8, 1 = valid) gives
+ * a padded key the logit finfo(float32).min exactly like the additive mask of
+ * the reference (so a row whose permitted keys are all padded is uniform over
+ * them); `additive` ([B,1,Tq,Tk] fp32) is the generic low-level-interface
+ * mask and is added verbatim; causal rows see keys j <= i only. */
+typedef struct scatt_attention_problem {
+  const float* q; /* [B*Tq, H*hd] fp32, row stride ldq */
+  const float* k; /* [B*Tk, H*hd] row stride ldk */
+  const float* v; /* [B*Tk, H*hd] row stride ldv */
+  const uint8_t* key_mask;
+  const float* additive;
+  float* out;       /* [B*Tq, H*hd] fp32 contiguous or NULL */
+  void* out_planes; /* [2][B*Tq][H*hd] or NULL */
+} scatt_attention_problem;
+
+int scatt_attention(const scatt_attention_problem* problems_host, int group, int B, int Tq, int Tk, int H, int hd,
+                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ K5: fusion attention */
+
+/* out[b] = softmax(q[b] k[b]^T) v[b], single head of width D, no mask, no
+ * scaling (model/fusion.py:46-49: q = right_out, k = left_out, v = body_out). */
+int scatt_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out,
+                           void* out_planes, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ K4: temporal pooling */
+
+/* MaxPool1d(2,2) over time of x[B,T,C] -> y[B,floor(T/2),C] (model/residual.py:40-43),
+ * with optional split-plane export of the pooled rows. */
+int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_planes, int plane_fmt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCATT_H_ */

@@ -1,0 +1,81 @@
+"""Build ``libscatt.so`` in-tree with nvcc for sm_100a (no torch dependency).
+
+``python -m scattennet_b200.build`` or ``scattennet_b200.build.build()``.
+nvcc cross-compiles without a GPU; the ``.so`` is git-ignored but travels to
+the GPU box with the repo snapshot.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libscatt.so")
+OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
+SOURCES = ["api.cu", "rowwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "scatt.h")]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libscatt.so cannot be built (there is no CPU fallback)")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, name), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(ARCH + FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    stamp = OUT + ".digest"
+    return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == _digest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a and link ``libscatt.so``; returns its path."""
+    if not force and is_current():
+        return OUT
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+        with open(obj + ".ptxas.log", "w") as fh:
+            fh.write(res.stderr)
+        if verbose:
+            sys.stderr.write(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        objs = list(pool.map(compile_one, SOURCES))
+    link = [nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
+    res = subprocess.run(link, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(OUT + ".digest", "w") as fh:
+        fh.write(_digest())
+    return OUT
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(path)

@@ -1,0 +1,112 @@
+// extern "C" surface of libscatt.so (see include/scatt.h).  Argument checking
+// and engine selection only; kernels live in the other translation units.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace scatt {
+
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+thread_local char t_error[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace scatt
+
+using namespace scatt;
+
+namespace {
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool fmt_ok(int fmt) { return fmt == SCATT_PLANE_F16 || fmt == SCATT_PLANE_BF16; }
+}  // namespace
+
+extern "C" {
+
+int scatt_abi_version(void) { return SCATT_ABI_VERSION; }
+
+const char* scatt_version(void) { return "scatt-b200 0.1 (sm_100a; tcgen05+TMA linear engine, fp32 SIMT engine)"; }
+
+const char* scatt_last_error(void) { return t_error; }
+
+uint64_t scatt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int scatt_device_check(void) {
+  int dev = 0;
+  SCATT_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SCATT_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libscatt is built for sm_100a only", dev, prop.major, prop.minor);
+    return SCATT_ERR_UNSUPPORTED;
+  }
+  return SCATT_OK;
+}
+
+int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,
+                       void* stream) {
+  SCATT_REQUIRE(x && planes && fmt_ok(plane_fmt), "split_planes: null pointer or bad plane format");
+  return launch_split_planes(x, rows, cols, ldx, scale, planes, plane_fmt, as_stream(stream));
+}
+
+int scatt_frontend(const float* keypoints, int B, int T, int K, int D, const scatt_frontend_stream* streams_host,
+                   int n_streams, int max_pos, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(keypoints && streams_host && fmt_ok(plane_fmt), "frontend: null pointer or bad plane format");
+  SCATT_REQUIRE(B >= 0 && T >= 0 && K >= 1, "frontend: bad shape");
+  return launch_frontend(keypoints, B, T, K, D, streams_host, n_streams, max_pos, plane_fmt, as_stream(stream));
+}
+
+int scatt_posembed_layernorm(const float* x, const float* table, const float* ln_g, const float* ln_b, float* out,
+                             void* out_planes, int B, int T, int D, int max_pos, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(x && table && ln_g && ln_b && (out || out_planes) && fmt_ok(plane_fmt), "posembed_layernorm: bad argument");
+  SCATT_REQUIRE(T <= max_pos, "posembed_layernorm: T=%d exceeds max_position_embeddings=%d", T, max_pos);
+  return launch_posembed_ln(x, table, ln_g, ln_b, out, out_planes, B, T, D, plane_fmt, as_stream(stream));
+}
+
+int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
+                 int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms, void* stream) {
+  SCATT_REQUIRE(problems_host && epilogue_host && fmt_ok(plane_fmt), "linear: null pointer or bad plane format");
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "linear: group must be 1..%d", SCATT_MAX_GROUP);
+  SCATT_REQUIRE(M >= 0 && N >= 1 && K >= 1, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  if (engine == SCATT_ENGINE_SIMT)
+    return launch_linear_simt(problems_host, group, M, N, K, ldx, ldres, ldy, *epilogue_host, plane_fmt, as_stream(stream));
+  if (engine == SCATT_ENGINE_TCGEN05)
+    return launch_linear_tc(problems_host, group, M, N, K, ldres, ldy, *epilogue_host, plane_fmt, terms, as_stream(stream));
+  set_error("linear: unknown engine %d", engine);
+  return SCATT_ERR_INVALID;
+}
+
+int scatt_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* residual, int64_t ldres, const float* ln_g,
+                  const float* ln_b, const scatt_epilogue* epilogue_host, float* y, int64_t ldy, void* y_planes,
+                  int plane_fmt, void* stream) {
+  SCATT_REQUIRE(z && epilogue_host && (y || y_planes) && fmt_ok(plane_fmt), "rowwise: bad argument");
+  return launch_rowwise(z, M, N, ldz, residual, ldres, ln_g, ln_b, *epilogue_host, y, ldy, y_planes, plane_fmt,
+                        as_stream(stream));
+}
+
+int scatt_attention(const scatt_attention_problem* problems_host, int group, int B, int Tq, int Tk, int H, int hd,
+                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(problems_host && fmt_ok(plane_fmt), "attention: null pointer or bad plane format");
+  SCATT_REQUIRE(kind >= SCATT_ATTN_SELF && kind <= SCATT_ATTN_CROSS, "attention: bad kind %d", kind);
+  return launch_attention(problems_host, group, B, Tq, Tk, H, hd, ldq, ldk, ldv, kind, plane_fmt, as_stream(stream));
+}
+
+int scatt_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* out_planes,
+                           int plane_fmt, void* stream) {
+  SCATT_REQUIRE(q && k && v && (out || out_planes) && fmt_ok(plane_fmt), "fusion_attention: bad argument");
+  return launch_fusion_attention(q, k, v, B, T, D, out, out_planes, plane_fmt, as_stream(stream));
+}
+
+int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_planes, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(x && (y || y_planes) && fmt_ok(plane_fmt), "pool_pairs: bad argument");
+  return launch_pool_pairs(x, B, T, C, y, y_planes, plane_fmt, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Shared host/device helpers for libscatt.so (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/scatt.h"
+
+namespace scatt {
+
+// ---------------------------------------------------------------- host-side error plumbing
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return SCATT_ERR_CUDA;
+}
+
+#define SCATT_CUDA(expr)                                     \
+  do {                                                       \
+    cudaError_t e__ = (expr);                                \
+    if (e__ != cudaSuccess) return ::scatt::cuda_fail(e__, #expr); \
+  } while (0)
+
+#define SCATT_REQUIRE(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      ::scatt::set_error(__VA_ARGS__);      \
+      return SCATT_ERR_INVALID;             \
+    }                                       \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-config errors.
+inline int after_launch(const char* name) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("launch of %s failed: %s", name, cudaGetErrorString(e));
+    return SCATT_ERR_CUDA;
+  }
+  return SCATT_OK;
+}
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == SCATT_ACT_GELU) return gelu_erf(x);
+  if (act == SCATT_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 16-bit hi/lo split of an fp32 value. Returned as raw 16-bit patterns.
+template <int FMT>
+__device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
+  if (FMT == SCATT_PLANE_F16) {
+    __half h = __float2half_rn(x);
+    __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  }
+}
+
+__device__ __forceinline__ void split16_rt(float x, int fmt, uint16_t& hi, uint16_t& lo) {
+  if (fmt == SCATT_PLANE_F16) split16<SCATT_PLANE_F16>(x, hi, lo);
+  else split16<SCATT_PLANE_BF16>(x, hi, lo);
+}
+
+// Store 4 consecutive fp32 values as split planes (8-byte stores).
+__device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t plane_stride, int64_t off, float4 v, int fmt) {
+  uint16_t h[4], l[4];
+  split16_rt(v.x, fmt, h[0], l[0]);
+  split16_rt(v.y, fmt, h[1], l[1]);
+  split16_rt(v.z, fmt, h[2], l[2]);
+  split16_rt(v.w, fmt, h[3], l[3]);
+  uint2 ph, pl;
+  ph.x = h[0] | (uint32_t(h[1]) << 16);
+  ph.y = h[2] | (uint32_t(h[3]) << 16);
+  pl.x = l[0] | (uint32_t(l[1]) << 16);
+  pl.y = l[2] | (uint32_t(l[3]) << 16);
+  *reinterpret_cast<uint2*>(planes + off) = ph;
+  *reinterpret_cast<uint2*>(planes + plane_stride + off) = pl;
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- launchers implemented in the .cu files
+int launch_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int fmt,
+                        cudaStream_t s);
+int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_frontend_stream* streams, int n, int max_pos,
+                    int fmt, cudaStream_t s);
+int launch_posembed_ln(const float* x, const float* table, const float* g, const float* b, float* out, void* planes,
+                       int B, int T, int D, int fmt, cudaStream_t s);
+int launch_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* residual, int64_t ldres, const float* g,
+                   const float* b, const scatt_epilogue& ep, float* y, int64_t ldy, void* planes, int fmt,
+                   cudaStream_t s);
+int launch_pool_pairs(const float* x, int B, int T, int C, float* y, void* planes, int fmt, cudaStream_t s);
+int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
+                       int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s);
+int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
+                     const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s);
+int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int64_t ldq,
+                     int64_t ldk, int64_t ldv, int kind, int fmt, cudaStream_t s);
+int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
+                            int fmt, cudaStream_t s);
+
+}  // namespace scatt

@@ -1,0 +1,293 @@
+"""Host-side glue between the PyTorch modules and the C ABI of ``libscatt.so``.
+
+Everything here is plumbing: tensors are allocated by torch (so CUDA-graph
+capture and the caching allocator work), their raw device pointers are handed
+to the kernels on torch's current stream.  No arithmetic is done in torch.
+
+An activation travelling between kernels is an :class:`Act`: an optional fp32
+``[rows, cols]`` matrix (residual stream, attention operands, final outputs)
+and optional 16-bit hi/lo split planes ``[2, rows, cols]`` (tensor-core GEMM
+operands).  Grouped calls take one entry per anatomical stream and become one
+kernel launch (``grid.z`` = stream).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+# ----------------------------------------------------------------------------- precision
+
+
+@dataclass(frozen=True)
+class Precision:
+    """How contractions are evaluated.
+
+    ``fp32``    fp32 FMA on the CUDA cores (exact-order engine, fp32 tier).
+    ``fp16xN``  tcgen05 tensor cores on fp16 hi/lo split planes, N in 1..3
+                product terms, fp32 accumulation in TMEM.  ``fp16x3`` has
+                fp32-grade products (max-abs ~1e-5 vs the fp32 reference on the
+                C1 parity run); ``fp16x1`` is the plain 16-bit product (~7e-3).
+    ``bf16xN``  same with bf16 planes (wider range, 3 fewer mantissa bits).
+    """
+
+    name: str
+    engine: int
+    plane_fmt: int
+    terms: int
+
+    @property
+    def uses_planes(self) -> bool:
+        return self.engine == L.ENGINE_TCGEN05
+
+    @property
+    def plane_dtype(self):
+        return torch.float16 if self.plane_fmt == L.PLANE_F16 else torch.bfloat16
+
+
+PRECISIONS = {
+    "fp32": Precision("fp32", L.ENGINE_SIMT, L.PLANE_F16, 0),
+    **{f"fp16x{n}": Precision(f"fp16x{n}", L.ENGINE_TCGEN05, L.PLANE_F16, n) for n in (1, 2, 3)},
+    **{f"bf16x{n}": Precision(f"bf16x{n}", L.ENGINE_TCGEN05, L.PLANE_BF16, n) for n in (1, 2, 3)},
+}
+_default_precision = "fp16x3"
+
+
+def set_default_precision(name: str) -> None:
+    global _default_precision
+    if name not in PRECISIONS:
+        raise KeyError(f"unknown precision {name!r}; have {sorted(PRECISIONS)}")
+    _default_precision = name
+
+
+def get_precision(name: Optional[str] = None) -> Precision:
+    return PRECISIONS[name or _default_precision]
+
+
+# ----------------------------------------------------------------------------- helpers
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    """The product path has no CPU fallback: fail loudly on host tensors."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "scattennet_b200 runs on a CUDA device (sm_100a) only; got a CPU tensor and there is no CPU fallback"
+            )
+        dev = t.device
+    return dev
+
+
+def as_f32_2d(x: torch.Tensor) -> torch.Tensor:
+    x = x.reshape(-1, x.shape[-1])
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.contiguous()
+
+
+class Act:
+    """fp32 matrix and / or split planes of the same ``[rows, cols]`` activation."""
+
+    __slots__ = ("f32", "planes", "rows", "cols")
+
+    def __init__(self, f32: Optional[torch.Tensor] = None, planes: Optional[torch.Tensor] = None):
+        ref = f32 if f32 is not None else planes
+        self.f32, self.planes = f32, planes
+        self.rows, self.cols = (ref.shape[-2], ref.shape[-1])
+
+    @staticmethod
+    def from_f32(x: torch.Tensor) -> "Act":
+        return Act(as_f32_2d(x))
+
+    def with_planes(self, prec: Precision) -> "Act":
+        if prec.uses_planes and self.planes is None:
+            self.planes = split_planes(self.f32, prec)
+        return self
+
+
+def split_planes(x: torch.Tensor, prec: Precision, scale: float = 1.0) -> torch.Tensor:
+    rows, cols = x.shape
+    planes = torch.empty(2, rows, cols, dtype=prec.plane_dtype, device=x.device)
+    L.check(L.load().scatt_split_planes(x.data_ptr(), rows, cols, x.stride(0), scale, planes.data_ptr(), prec.plane_fmt,
+                                        _stream()), "scatt_split_planes")
+    return planes
+
+
+# ----------------------------------------------------------------------------- packed weights
+
+
+class PackedLinear:
+    """Row-concatenation of one or more ``nn.Linear`` (weight ``[N_i, K]``),
+    each optionally scaled by an exact power of two, kept as fp32 for the SIMT
+    engine and as split planes for the tcgen05 engine."""
+
+    def __init__(self, linears: Sequence[torch.nn.Linear], scales: Optional[Sequence[float]], key):
+        scales = list(scales) if scales is not None else [1.0] * len(linears)
+        with torch.no_grad():
+            ws = [l.weight.detach().float() * s if s != 1.0 else l.weight.detach().float() for l, s in zip(linears, scales)]
+            self.w32 = (torch.cat(ws, 0) if len(ws) > 1 else ws[0]).contiguous()
+            if all(l.bias is not None for l in linears):
+                bs = [l.bias.detach().float() for l in linears]
+                self.b32 = (torch.cat(bs, 0) if len(bs) > 1 else bs[0]).contiguous()
+            else:
+                self.b32 = None
+        self.N, self.K = self.w32.shape
+        self.key = key
+        self._planes = {}
+
+    def planes(self, prec: Precision) -> torch.Tensor:
+        p = self._planes.get(prec.plane_fmt)
+        if p is None:
+            p = split_planes(self.w32, prec)
+            self._planes[prec.plane_fmt] = p
+        return p
+
+
+def pack_of(owner: torch.nn.Module, tag: str, linears: Sequence[torch.nn.Linear], scales=None) -> PackedLinear:
+    """Cached :class:`PackedLinear` of ``linears``; rebuilt when a parameter was
+    moved or modified in place (``load_state_dict`` bumps ``_version``)."""
+    key = tuple(
+        (l.weight.data_ptr(), l.weight._version, 0 if l.bias is None else l.bias.data_ptr(), 0 if l.bias is None else l.bias._version)
+        for l in linears
+    )
+    cache = owner.__dict__.setdefault("_scatt_packs", {})
+    ent = cache.get(tag)
+    if ent is None or ent.key != key:
+        ent = PackedLinear(linears, scales, key)
+        cache[tag] = ent
+    return ent
+
+
+# ----------------------------------------------------------------------------- ops
+
+
+def make_epilogue(act_pre=L.ACT_NONE, residual_mode=L.RES_NONE, layer_norm=False, act_post=L.ACT_NONE, clamp=0.0,
+                  scale_cols=0, scale=1.0, ln_eps=1e-5) -> L.Epilogue:
+    return L.Epilogue(act_pre, residual_mode, 1 if layer_norm else 0, act_post, clamp, scale_cols, scale, ln_eps)
+
+
+def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep: L.Epilogue,
+           residuals: Optional[Sequence[torch.Tensor]] = None, lns: Optional[Sequence[torch.nn.LayerNorm]] = None,
+           out_f32: bool = True, out_planes: bool = True) -> List[Act]:
+    """Grouped ``y_g = epilogue(x_g W_g^T + b_g)`` - one launch for all ``g``."""
+    G = len(xs)
+    M, K, N = xs[0].rows, xs[0].cols, packs[0].N
+    dev = (xs[0].f32 if xs[0].f32 is not None else xs[0].planes).device
+    want_planes = out_planes and prec.uses_planes
+    need_f32 = out_f32 or not want_planes or (ep.layer_norm and (not prec.uses_planes or N != 256))
+    probs = (L.LinearProblem * G)()
+    outs: List[Act] = []
+    keep = []
+    for g in range(G):
+        x, pk = xs[g], packs[g]
+        if pk.K != K or pk.N != N or x.rows != M:
+            raise ValueError("grouped linear: all problems must share M, N, K")
+        y = torch.empty(M, N, dtype=torch.float32, device=dev) if need_f32 else None
+        yp = torch.empty(2, M, N, dtype=prec.plane_dtype, device=dev) if want_planes else None
+        p = probs[g]
+        if prec.uses_planes:
+            x.with_planes(prec)
+            p.x_planes, p.w_planes = x.planes.data_ptr(), pk.planes(prec).data_ptr()
+        else:
+            p.x, p.w = x.f32.data_ptr(), pk.w32.data_ptr()
+        p.bias = _ptr(pk.b32)
+        if residuals is not None:
+            p.residual = residuals[g].data_ptr()
+        if lns is not None:
+            p.ln_g, p.ln_b = lns[g].weight.data_ptr(), lns[g].bias.data_ptr()
+        p.y, p.y_planes = _ptr(y), _ptr(yp)
+        outs.append(Act(y, yp))
+        keep.append((x, pk))
+    ldx = xs[0].f32.stride(0) if xs[0].f32 is not None else K
+    ldres = residuals[0].stride(0) if residuals is not None else N
+    L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
+                                  max(prec.terms, 1), _stream()), "scatt_linear")
+    return outs
+
+
+def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: int, kind: int,
+                     key_mask: Optional[torch.Tensor] = None, additive: Optional[torch.Tensor] = None) -> List[Act]:
+    """Grouped flash-style attention; ``qs/ks/vs`` are fp32 2-D views (row stride = leading dim)."""
+    G = len(qs)
+    D = qs[0].shape[1]
+    dev = qs[0].device
+    probs = (L.AttentionProblem * G)()
+    outs = []
+    for g in range(G):
+        o = torch.empty(B * Tq, D, dtype=torch.float32, device=dev) if not prec.uses_planes else None
+        op = torch.empty(2, B * Tq, D, dtype=prec.plane_dtype, device=dev) if prec.uses_planes else None
+        p = probs[g]
+        p.q, p.k, p.v = qs[g].data_ptr(), ks[g].data_ptr(), vs[g].data_ptr()
+        p.key_mask, p.additive = _ptr(key_mask), _ptr(additive)
+        p.out, p.out_planes = _ptr(o), _ptr(op)
+        outs.append(Act(o, op))
+    L.check(L.load().scatt_attention(probs, G, B, Tq, Tk, H, D // H, qs[0].stride(0), ks[0].stride(0), vs[0].stride(0), kind,
+                                     prec.plane_fmt, _stream()), "scatt_attention")
+    return outs
+
+
+def fusion_attention(prec: Precision, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, T: int) -> Act:
+    D = q.shape[1]
+    o = torch.empty(B * T, D, dtype=torch.float32, device=q.device) if not prec.uses_planes else None
+    op = torch.empty(2, B * T, D, dtype=prec.plane_dtype, device=q.device) if prec.uses_planes else None
+    L.check(L.load().scatt_fusion_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), B, T, D, _ptr(o), _ptr(op),
+                                            prec.plane_fmt, _stream()), "scatt_fusion_attention")
+    return Act(o, op)
+
+
+def pool_pairs(prec: Precision, x: torch.Tensor, B: int, T: int) -> Act:
+    Cc = x.shape[1]
+    if T < 2:
+        # MaxPool1d(2, 2) on a single frame: the reference raises (model/residual.py:42)
+        raise RuntimeError("max_pool1d() Invalid computed output size: 0")
+    y = torch.empty(B * (T // 2), Cc, dtype=torch.float32, device=x.device)
+    yp = torch.empty(2, B * (T // 2), Cc, dtype=prec.plane_dtype, device=x.device) if prec.uses_planes else None
+    L.check(L.load().scatt_pool_pairs(x.data_ptr(), B, T, Cc, y.data_ptr(), _ptr(yp), prec.plane_fmt, _stream()),
+            "scatt_pool_pairs")
+    return Act(y, yp)
+
+
+def posembed_layernorm(prec: Precision, x: torch.Tensor, table: torch.Tensor, ln: torch.nn.LayerNorm, B: int, T: int) -> Act:
+    D = x.shape[-1]
+    max_pos = table.shape[0] - 2
+    if T > max_pos:
+        raise IndexError("index out of range in self")  # what nn.Embedding raises in the reference (model/layers.py:28)
+    x2 = as_f32_2d(x)
+    out = torch.empty(B * T, D, dtype=torch.float32, device=x.device)
+    planes = torch.empty(2, B * T, D, dtype=prec.plane_dtype, device=x.device) if prec.uses_planes else None
+    L.check(L.load().scatt_posembed_layernorm(x2.data_ptr(), table.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(),
+                                              out.data_ptr(), _ptr(planes), B, T, D, max_pos, prec.plane_fmt, _stream()),
+            "scatt_posembed_layernorm")
+    return Act(out, planes)
+
+
+def rowwise(prec: Precision, z: torch.Tensor, ep: L.Epilogue, ln: Optional[torch.nn.LayerNorm] = None,
+            residual: Optional[torch.Tensor] = None) -> Act:
+    M, N = z.shape
+    y = torch.empty(M, N, dtype=torch.float32, device=z.device)
+    yp = torch.empty(2, M, N, dtype=prec.plane_dtype, device=z.device) if prec.uses_planes else None
+    L.check(L.load().scatt_rowwise(z.data_ptr(), M, N, z.stride(0), _ptr(residual), N if residual is None else residual.stride(0),
+                                   _ptr(ln.weight) if ln is not None else None, _ptr(ln.bias) if ln is not None else None,
+                                   C.byref(ep), y.data_ptr(), N, _ptr(yp), prec.plane_fmt, _stream()), "scatt_rowwise")
+    return Act(y, yp)
+
+
+def key_mask_u8(mask: torch.Tensor) -> torch.Tensor:
+    """``[B, T]`` 0/1 mask of any integer / bool / float dtype -> uint8 (1 = valid key)."""
+    return (mask != 0).to(torch.uint8).contiguous()

@@ -1,0 +1,263 @@
+"""``KeypointModule``, ``CoordinateAttention``, ``CoordinatesMerge`` and
+``SeparativeCoordinateAttention`` with the interface of the reference
+``model/keypoint_module.py``.
+
+Data flow of one stream (reference ``:22-31,153-198``):
+
+    keypoints[B,T,K_s,2] --K1 front end--> self / causal embeddings (LN'd)
+    4 x self layer      : QKV GEMM -> attention -> out_proj+res+LN -> fc1+GELU -> fc2+res+LN
+    1 x cross K/V GEMM  : K,V of all 4 merge layers from the final self map (N = 4*2*D)
+    4 x (causal layer   : QKV GEMM -> causal attention -> out_proj+res+LN
+         merge layer    : Q GEMM -> cross attention -> out_proj+res+LN -> fc1+GELU -> fc2+res+LN)
+    residual network    : see residual.py
+
+Every function here takes *lists* (one entry per anatomical stream with equal
+shapes); the three streams of the model run as grouped launches.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib as L
+from . import functional as F_
+from .attention import CrossAttention, SelfAttention, SelfCausalAttention, attention_core
+from .functional import Act, Precision
+from .layers import CoordinateMapping, FeedForward, LearningPositionEmbedding
+from .residual import ResidualNetwork, residual_network_forward
+from .utils import create_attention_mask, create_causal_attention_mask  # noqa: F401  (interface parity)
+
+
+def _inference_only(mod: nn.Module, p: float):
+    if mod.training and p > 0:
+        raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward (dropout > 0 in training mode)")
+
+
+def _additive(mask: Optional[torch.Tensor], b: int, tq: int, tk: int) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    return mask.to(torch.float32).expand(b, 1, tq, tk).contiguous()
+
+
+class CoordinateAttention(nn.Module):
+    def __init__(self, cfg, attn_type="self_attn"):
+        super().__init__()
+        self.attn_type = attn_type
+        if attn_type == "self_attn":
+            self.attn = SelfAttention(d_model=cfg["d_model"], num_heads=cfg["attention_heads"], dropout=cfg["attention_dropout"])
+            self.mlp = FeedForward(cfg["d_model"], cfg["ff_dim"], cfg["dropout"])
+            self.last_layer_norm = nn.LayerNorm(cfg["d_model"])
+        elif attn_type == "causal_attn":
+            self.attn = SelfCausalAttention(d_model=cfg["d_model"], num_heads=cfg["attention_heads"], dropout=cfg["attention_dropout"])
+            self.mlp = nn.Identity()
+            self.last_layer_norm = nn.Identity()
+        else:
+            raise ValueError(f"Invalid attention type: {attn_type}")
+        self.attn_layer_norm = nn.LayerNorm(cfg["d_model"])
+        self.dropout = cfg["dropout"]
+        self.activation_fn = nn.GELU()
+        self.precision: Optional[str] = None
+
+    def forward(self, coord_embed, attention_mask=None):
+        _inference_only(self, self.dropout)
+        F_.require_cuda(coord_embed, attention_mask)
+        prec = F_.get_precision(self.precision)
+        b, t, _ = coord_embed.shape
+        out = coordinate_attention_forward(prec, [self], [Act.from_f32(coord_embed)], b, t, None,
+                                           _additive(attention_mask, b, t, t))
+        return out[0].f32.view_as(coord_embed).to(coord_embed.dtype)
+
+
+def _attn_out_ln(prec, attns, ctx, norms, residuals: List[Act]) -> List[Act]:
+    return F_.linear(prec, ctx, [F_.pack_of(a, "out", [a.out_proj]) for a in attns],
+                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[r.f32 for r in residuals],
+                     lns=norms)
+
+
+def _ffn_ln(prec, mlps: Sequence[FeedForward], norms, h: List[Act]) -> List[Act]:
+    f = F_.linear(prec, h, [F_.pack_of(m, "fc1", [m.fc1]) for m in mlps], F_.make_epilogue(act_pre=L.ACT_GELU),
+                  out_f32=not prec.uses_planes)
+    return F_.linear(prec, f, [F_.pack_of(m, "fc2", [m.fc2]) for m in mlps],
+                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[x.f32 for x in h], lns=norms)
+
+
+def coordinate_attention_forward(prec: Precision, mods: Sequence[CoordinateAttention], xs: List[Act], B: int, T: int,
+                                 key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None) -> List[Act]:
+    """reference ``model/keypoint_module.py:61-80`` for a group of streams."""
+    kind = L.ATTN_SELF if mods[0].attn_type == "self_attn" else L.ATTN_CAUSAL
+    ctx = attention_core(prec, [m.attn for m in mods], xs, None, B, T, T, kind, key_mask, additive)
+    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], xs)
+    if mods[0].attn_type == "self_attn":
+        h = _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h)
+    return h
+
+
+class CoordinatesMerge(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.attn = CrossAttention(d_model=cfg["d_model"], num_heads=cfg["attention_heads"], dropout=cfg["attention_dropout"])
+        self.mlp = FeedForward(cfg["d_model"], cfg["ff_dim"], cfg["dropout"])
+        self.attn_layer_norm = nn.LayerNorm(cfg["d_model"])
+        self.last_layer_norm = nn.LayerNorm(cfg["d_model"])
+        self.dropout = cfg["dropout"]
+        self.precision: Optional[str] = None
+
+    def forward(self, y_embed, x_embed, cross_attn_mask=None):
+        _inference_only(self, self.dropout)
+        F_.require_cuda(y_embed, x_embed, cross_attn_mask)
+        prec = F_.get_precision(self.precision)
+        b, tq, _ = y_embed.shape
+        tk = x_embed.shape[1]
+        out = coordinates_merge_forward(prec, [self], [Act.from_f32(y_embed)], [Act.from_f32(x_embed)], None, b, tq, tk, None,
+                                        _additive(cross_attn_mask, b, tq, tk))
+        return out[0].f32.view_as(y_embed).to(y_embed.dtype)
+
+
+def coordinates_merge_forward(prec: Precision, mods: Sequence[CoordinatesMerge], ys: List[Act], xs: Optional[List[Act]],
+                              kv_views, B: int, Tq: int, Tk: int, key_mask: Optional[torch.Tensor],
+                              additive: Optional[torch.Tensor] = None) -> List[Act]:
+    """reference ``model/keypoint_module.py:97-115`` for a group of streams."""
+    ctx = attention_core(prec, [m.attn for m in mods], ys, xs, B, Tq, Tk, L.ATTN_CROSS, key_mask, additive, kv_views)
+    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], ys)
+    return _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h)
+
+
+class SeparativeCoordinateAttention(nn.Module):
+    def __init__(self, cfg=None):
+        super().__init__()
+        self.dropout = cfg["dropout"]
+        n = cfg["attn_layers"]
+        self.self_attn_layers = nn.ModuleList([CoordinateAttention(cfg, attn_type="self_attn") for _ in range(n)])
+        self.causal_attn_layers = nn.ModuleList([CoordinateAttention(cfg, attn_type="causal_attn") for _ in range(n)])
+        self.coordinates_merge = nn.ModuleList([CoordinatesMerge(cfg) for _ in range(n)])
+        self.first_self_norm = nn.LayerNorm(cfg["d_model"])
+        self.first_causal_norm = nn.LayerNorm(cfg["d_model"])
+        self.self_pos_embed = LearningPositionEmbedding(cfg["max_position_embeddings"], cfg["d_model"])
+        self.causal_pos_embed = LearningPositionEmbedding(cfg["max_position_embeddings"], cfg["d_model"])
+        self.x_self = cfg.get("self_attn_x", True)
+        self.precision: Optional[str] = None
+
+    def forward(self, x_embed, y_embed, attention_mask=None, return_attn_map=False):
+        _inference_only(self, self.dropout)
+        F_.require_cuda(x_embed, y_embed, attention_mask)
+        prec = F_.get_precision(self.precision)
+        b, t, d = x_embed.shape
+        s_in, c_in = (x_embed, y_embed) if self.x_self else (y_embed, x_embed)
+        s = F_.posembed_layernorm(prec, s_in, self.self_pos_embed.weight, self.first_self_norm, b, t)
+        c = F_.posembed_layernorm(prec, c_in, self.causal_pos_embed.weight, self.first_causal_norm, b, t)
+        km = F_.key_mask_u8(attention_mask)  # the reference requires a [B,T] mask here too (model/utils.py:5)
+        outs, selfs = sca_forward(prec, [self], [s], [c], km, b, t)
+        outputs = outs[0].f32.view(b, t, d).to(x_embed.dtype)
+        if return_attn_map:
+            return {"outputs": outputs, "self_attn_map": selfs[0].f32.view(b, t, d).to(x_embed.dtype),
+                    "causal_attn_map": outputs}
+        return outputs
+
+
+def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], s: List[Act], c: List[Act],
+                key_mask: torch.Tensor, B: int, T: int):
+    """Layer loops of reference ``model/keypoint_module.py:176-187`` on already
+    position-embedded + normalised inputs, for a group of streams."""
+    n = len(mods[0].self_attn_layers)
+    d = s[0].cols
+    for i in range(n):
+        s = coordinate_attention_forward(prec, [m.self_attn_layers[i] for m in mods], s, B, T, key_mask)
+    # K / V of every merge layer read the same final self map: one N = n*2*D GEMM per stream
+    packs = []
+    for m in mods:
+        lins, scales = [], []
+        for i in range(n):
+            a = m.coordinates_merge[i].attn
+            lins += [a.k_proj, a.v_proj]
+            scales += [1.0, 0.5]
+        packs.append(F_.pack_of(m, "merge_kv", lins, scales))
+    kv_all = F_.linear(prec, s, packs, F_.make_epilogue(), out_planes=False)
+    for i in range(n):
+        c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask)
+        kv_views = [(kv.f32[:, 2 * i * d : (2 * i + 1) * d], kv.f32[:, (2 * i + 1) * d : (2 * i + 2) * d]) for kv in kv_all]
+        c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask)
+    return c, s
+
+
+class KeypointModule(nn.Module):
+    def __init__(self, joint_idx, num_frame, cfg=None):
+        super().__init__()
+        self.joint_idx = joint_idx
+        self.num_frame = num_frame
+        self.coordinate_mapping = CoordinateMapping(len(joint_idx), cfg["d_model"])
+        self.sca = SeparativeCoordinateAttention(cfg)
+        self.residual = ResidualNetwork(cfg["residual_blocks"])
+        self.precision: Optional[str] = None
+
+    def forward(self, keypoints, attention_mask=None):
+        """``keypoints``: the already gathered ``[B,T,K_s,2]`` region, like the reference."""
+        _inference_only(self, self.sca.dropout)
+        F_.require_cuda(keypoints, attention_mask)
+        prec = F_.get_precision(self.precision)
+        b, t, k, _ = keypoints.shape
+        kp = keypoints.float().contiguous()
+        idx = torch.arange(k, dtype=torch.int32, device=kp.device)
+        outs = streams_forward(prec, [self], kp, [idx], F_.key_mask_u8(attention_mask), b, t)
+        (acts, t_out) = outs[-1]
+        return acts[0].f32.view(b, t_out, -1).to(keypoints.dtype)
+
+
+def frontend_forward(prec: Precision, mods: Sequence[KeypointModule], keypoints: torch.Tensor,
+                     joint_idx: Sequence[torch.Tensor], B: int, T: int, want_gathered: bool = False):
+    """K1: region gather + x/y split + CoordinateMapping + position embedding +
+    first LayerNorm for all streams in one launch.  Returns ``(self_acts,
+    causal_acts, gathered)``."""
+    dev = keypoints.device
+    K = keypoints.shape[2]
+    d = mods[0].coordinate_mapping.mapping_x.out_features
+    max_pos = mods[0].sca.self_pos_embed.weight.shape[0] - 2
+    if T > max_pos:
+        raise IndexError("index out of range in self")
+    G = len(mods)
+    arr = (L.FrontendStream * G)()
+    s_acts, c_acts, gathered = [], [], []
+    for g, m in enumerate(mods):
+        sca, cm = m.sca, m.coordinate_mapping
+        maps = (cm.mapping_x, cm.mapping_y) if sca.x_self else (cm.mapping_y, cm.mapping_x)
+        coords = (0, 1) if sca.x_self else (1, 0)
+        tables = (sca.self_pos_embed.weight, sca.causal_pos_embed.weight)
+        norms = (sca.first_self_norm, sca.first_causal_norm)
+        st = arr[g]
+        st.joint_idx = joint_idx[g].data_ptr()
+        st.n_joints = int(joint_idx[g].numel())
+        acts = []
+        for br in range(2):
+            st.coord[br] = coords[br]
+            st.map_w[br] = maps[br].weight.data_ptr()
+            st.map_b[br] = maps[br].bias.data_ptr()
+            st.pos[br] = tables[br].data_ptr()
+            st.ln_g[br] = norms[br].weight.data_ptr()
+            st.ln_b[br] = norms[br].bias.data_ptr()
+            o = torch.empty(B * T, d, dtype=torch.float32, device=dev)
+            op = torch.empty(2, B * T, d, dtype=prec.plane_dtype, device=dev) if prec.uses_planes else None
+            st.out[br] = o.data_ptr()
+            st.out_planes[br] = F_._ptr(op)
+            acts.append(Act(o, op))
+        if want_gathered:
+            gt = torch.empty(B, T, st.n_joints, 2, dtype=torch.float32, device=dev)
+            st.gathered = gt.data_ptr()
+            gathered.append(gt)
+        s_acts.append(acts[0])
+        c_acts.append(acts[1])
+    L.check(L.load().scatt_frontend(keypoints.data_ptr(), B, T, K, d, arr, G, max_pos, prec.plane_fmt, F_._stream()),
+            "scatt_frontend")
+    return s_acts, c_acts, gathered
+
+
+def streams_forward(prec: Precision, mods: Sequence[KeypointModule], keypoints: torch.Tensor,
+                    joint_idx: Sequence[torch.Tensor], key_mask: torch.Tensor, B: int, T: int):
+    """Front end + SCA + residual network for a group of streams reading the
+    same ``keypoints[B,T,K,2]``; returns the residual network's block outputs."""
+    s, c, _ = frontend_forward(prec, mods, keypoints, joint_idx, B, T)
+    h, _ = sca_forward(prec, [m.sca for m in mods], s, c, key_mask, B, T)
+    return residual_network_forward(prec, [m.residual for m in mods], h, B, T)

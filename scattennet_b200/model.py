@@ -1,0 +1,142 @@
+"""The encoder path of ``MSCA_Net`` as one module (reference
+``model/__init__.py:72-159``): region split, the three ``KeypointModule``
+streams (``body_encoder``, ``left_encoder``, ``right_encoder``),
+``coordinates_fusion`` and the four linear classifiers of ``recognition_head``
+with their +-50 clamp.  Sub-module names equal the reference's, so
+``MSCA_Net.state_dict()`` loads with ``strict=False`` (the BiLSTM alignment head,
+the losses and the tokenizer are outside the path - SURVEY.md section 8f).
+
+``forward(keypoints[B,T,K,2], mask[B,T])`` runs ~80 grouped kernel launches;
+``use_graph=True`` replays them from a CUDA graph captured per ``(B, T)``.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import functional as F_
+from .functional import Act
+from .fusion import CoordinatesFusion, coordinates_fusion_forward
+from .keypoint_module import KeypointModule, frontend_forward, streams_forward
+
+PARTS = ("body", "left", "right")  # order of model/__init__.py:133-142
+
+
+class LinearHeads(nn.Module):
+    """The four ``nn.Linear`` classifiers of ``RecognitionHead`` (reference
+    ``model/__init__.py:14-25``), same attribute names."""
+
+    def __init__(self, cfg, vocab_size: int):
+        super().__init__()
+        c = cfg["residual_blocks"][-1]
+        self.left_gloss_classifier = nn.Linear(c, vocab_size)
+        self.right_gloss_classifier = nn.Linear(c, vocab_size)
+        self.body_gloss_classifier = nn.Linear(c, vocab_size)
+        self.fuse_coord_classifier = nn.Linear(cfg["out_fusion_dim"], vocab_size)
+
+
+class MSCAEncoder(nn.Module):
+    def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False):
+        super().__init__()
+        self.cfg = dict(cfg)
+        self.body_encoder = KeypointModule(cfg["body_idx"], num_frame=cfg["num_frame"], cfg=cfg)
+        self.left_encoder = KeypointModule(cfg["left_idx"], num_frame=cfg["num_frame"], cfg=cfg)
+        self.right_encoder = KeypointModule(cfg["right_idx"], num_frame=cfg["num_frame"], cfg=cfg)
+        self.coordinates_fusion = CoordinatesFusion(cfg["in_fusion_dim"], cfg["out_fusion_dim"], 0.2)
+        self.recognition_head = LinearHeads(cfg, vocab_size)
+        self.precision = precision
+        self.use_graph = use_graph
+        self._graphs: Dict = {}
+        self._idx_cache: Dict = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _joint_idx(self, device):
+        key = str(device)
+        if key not in self._idx_cache:
+            self._idx_cache[key] = [torch.tensor(self.cfg[p + "_idx"], dtype=torch.int32, device=device) for p in PARTS]
+        return self._idx_cache[key]
+
+    def load_reference_state_dict(self, state_dict, strict_path: bool = True):
+        """Load an ``MSCA_Net`` state dict: every key of the encoder path must be
+        present and match; keys outside the path (``recognition_head.fuse_alignment_head.*``)
+        are ignored."""
+        own = self.state_dict()
+        picked = {k: v for k, v in state_dict.items() if k in own}
+        missing = [k for k in own if k not in picked]
+        if strict_path and missing:
+            raise KeyError(f"state dict lacks encoder-path keys: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        bad = [k for k in picked if tuple(picked[k].shape) != tuple(own[k].shape)]
+        if bad:
+            raise ValueError(f"shape mismatch for {bad[:5]}")
+        return self.load_state_dict(picked, strict=strict_path)
+
+    # ------------------------------------------------------------------ forward
+    def _run(self, keypoints: torch.Tensor, key_mask: torch.Tensor, with_heads: bool = True) -> Dict[str, torch.Tensor]:
+        prec = F_.get_precision(self.precision)
+        b, t = keypoints.shape[:2]
+        mods = [self.body_encoder, self.left_encoder, self.right_encoder]
+        blocks = streams_forward(prec, mods, keypoints, self._joint_idx(keypoints.device), key_mask, b, t)
+        (body, left, right), tp = blocks[-1]
+        fuse = coordinates_fusion_forward(prec, self.coordinates_fusion, left, right, body, b, tp, out_planes=with_heads)
+        out = {"body_embed": body.f32.view(b, tp, -1), "left_embed": left.f32.view(b, tp, -1),
+               "right_embed": right.f32.view(b, tp, -1), "fuse_embed": fuse.f32.view(b, tp, -1)}
+        if with_heads:
+            rh = self.recognition_head
+            ep = F_.make_epilogue(clamp=50.0)
+            lg = F_.linear(prec, [left, right, body],
+                           [F_.pack_of(rh, "left", [rh.left_gloss_classifier]), F_.pack_of(rh, "right", [rh.right_gloss_classifier]),
+                            F_.pack_of(rh, "body", [rh.body_gloss_classifier])], ep, out_planes=False)
+            fl = F_.linear(prec, [fuse], [F_.pack_of(rh, "fuse", [rh.fuse_coord_classifier])], ep, out_planes=False)[0]
+            out.update(left=lg[0].f32.view(b, tp, -1), right=lg[1].f32.view(b, tp, -1), body=lg[2].f32.view(b, tp, -1),
+                       fuse_coord_gloss_logits=fl.f32.view(b, tp, -1))
+        return out
+
+    def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True) -> Dict[str, torch.Tensor]:
+        """``keypoints [B,T,K,2]`` (the full collated tensor - the region split is
+        part of the path), ``mask [B,T]`` 0/1.  Returns the stream / fusion
+        features and the clamped per-frame logits (fp32)."""
+        if self.training:
+            raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward")
+        F_.require_cuda(keypoints, mask)
+        if keypoints.dtype != torch.float32 or not keypoints.is_contiguous():
+            keypoints = keypoints.float().contiguous()
+        if not self.use_graph:
+            return self._run(keypoints, F_.key_mask_u8(mask), with_heads)
+        return self._run_graph(keypoints, mask, with_heads)
+
+    # ------------------------------------------------------------------ CUDA graph replay
+    def _run_graph(self, keypoints, mask, with_heads):
+        key = (tuple(keypoints.shape), str(keypoints.device), F_.get_precision(self.precision).name, with_heads)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_kp = torch.empty_like(keypoints)
+            static_mask = torch.empty(mask.shape, dtype=torch.uint8, device=mask.device)
+            static_kp.copy_(keypoints)
+            static_mask.copy_(F_.key_mask_u8(mask))
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up: packs weights, sets kernel attributes
+                for _ in range(2):
+                    self._run(static_kp, static_mask, with_heads)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.launch_count()
+            with torch.cuda.graph(graph):
+                static_out = self._run(static_kp, static_mask, with_heads)
+            ent = (graph, static_kp, static_mask, static_out, L.launch_count() - n0)
+            self._graphs[key] = ent
+        graph, static_kp, static_mask, static_out, _ = ent
+        static_kp.copy_(keypoints, non_blocking=True)
+        static_mask.copy_(F_.key_mask_u8(mask), non_blocking=True)
+        graph.replay()
+        return static_out
+
+    def graph_launches(self, keypoints_shape, device, with_heads=True) -> int:
+        """Kernels inside the captured graph for this shape (0 if not captured)."""
+        key = (tuple(keypoints_shape), str(device), F_.get_precision(self.precision).name, with_heads)
+        ent = self._graphs.get(key)
+        return 0 if ent is None else ent[4]
