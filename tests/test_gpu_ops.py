@@ -1,0 +1,239 @@
+"""GPU parity of the individual C-ABI ops against the oracle / plain torch on
+seeded inputs.  Tolerances: exact for gathers, pooling and the split planes'
+reconstruction bound; fp32-order noise for the SIMT engine; per-mode bounds
+for the tcgen05 engine (stated next to each test)."""
+
+import math
+
+import pytest
+import torch
+
+from oracle import scatt_oracle as O
+from scattennet_b200 import _lib as L
+from scattennet_b200 import functional as F_
+from scattennet_b200 import synth
+from scattennet_b200.functional import Act
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+class Lin(torch.nn.Linear):
+    pass
+
+
+def make_linear(n, k, seed):
+    lin = torch.nn.Linear(k, n)
+    synth.load_synth_(lin, seed)
+    return lin.to(DEV)
+
+
+def ref_chain(x, lin, ep_kw, residual=None, ln=None):
+    """torch fp64 restatement of the epilogue chain (checker)."""
+    z = x.double() @ lin.weight.double().t() + lin.bias.double()
+    sc = ep_kw.get("scale_cols", 0)
+    if sc:
+        z[:, :sc] = z[:, :sc] * ep_kw["scale"]
+    act = {L.ACT_NONE: lambda v: v, L.ACT_GELU: torch.nn.functional.gelu, L.ACT_RELU: torch.relu}
+    z = act[ep_kw.get("act_pre", 0)](z)
+    if ep_kw.get("residual_mode", 0) == L.RES_BEFORE_LN:
+        z = z + residual.double()
+    if ep_kw.get("layer_norm", False):
+        z = torch.nn.functional.layer_norm(z, (z.shape[1],), ln.weight.double(), ln.bias.double(), 1e-5)
+    if ep_kw.get("residual_mode", 0) == L.RES_AFTER_LN:
+        z = z + residual.double()
+    z = act[ep_kw.get("act_post", 0)](z)
+    if ep_kw.get("clamp", 0) > 0:
+        z = z.clamp(-ep_kw["clamp"], ep_kw["clamp"])
+    return z
+
+
+EPILOGUES = {
+    "bias": dict(),
+    "qscale": dict(scale_cols=256, scale=0.25),
+    "gelu": dict(act_pre=L.ACT_GELU),
+    "res_ln": dict(residual_mode=L.RES_BEFORE_LN, layer_norm=True),
+    "ln_relu": dict(layer_norm=True, act_post=L.ACT_RELU),
+    "ln_res_relu": dict(layer_norm=True, residual_mode=L.RES_AFTER_LN, act_post=L.ACT_RELU),
+    "gelu_res_ln": dict(act_pre=L.ACT_GELU, residual_mode=L.RES_BEFORE_LN, layer_norm=True),
+    "clamp": dict(clamp=0.5),
+}
+
+# max-abs tolerance on O(1)-magnitude outputs (K <= 1024, |x| ~ 1, Xavier weights)
+MODE_TOL = {"fp32": 2e-5, "fp16x3": 5e-5, "bf16x3": 2e-4, "fp16x2": 3e-3, "fp16x1": 4e-3, "bf16x1": 3e-2}
+
+
+@pytest.mark.parametrize("mode", list(MODE_TOL))
+@pytest.mark.parametrize("epi", list(EPILOGUES))
+@pytest.mark.parametrize("shape", [(200, 256, 256), (1600, 256, 768), (333, 768, 256), (77, 512, 512), (400, 1024, 512), (50, 1120, 1024)])
+def test_linear_epilogues(mode, epi, shape):
+    M, N, K = shape
+    kw = EPILOGUES[epi]
+    if kw.get("layer_norm") and N > 1024:
+        pytest.skip("LayerNorm rows are at most 1024 wide on this path")
+    prec = F_.get_precision(mode)
+    x = rnd(M, K, seed=1)
+    lin = make_linear(N, K, 2)
+    ln = torch.nn.LayerNorm(N)
+    with torch.no_grad():
+        ln.weight.copy_(1.0 + 0.2 * (torch.rand(N, generator=torch.Generator().manual_seed(3)) - 0.5))
+        ln.bias.copy_(0.1 * (torch.rand(N, generator=torch.Generator().manual_seed(4)) - 0.5))
+    ln = ln.to(DEV)
+    res = rnd(M, N, seed=4) if kw.get("residual_mode", 0) else None
+    pk = F_.PackedLinear([lin], None, None)
+    out = F_.linear(prec, [Act(x)], [pk], F_.make_epilogue(**kw), residuals=None if res is None else [res],
+                    lns=[ln] if kw.get("layer_norm") else None)[0]
+    torch.cuda.synchronize()
+    ref = ref_chain(x, lin, kw, res, ln)
+    err = float((out.f32.double() - ref).abs().max())
+    tol = MODE_TOL[mode] * (4.0 if kw.get("layer_norm") else 1.0) * max(1.0, math.sqrt(K / 256))
+    assert err <= tol, (mode, epi, shape, err)
+    if prec.uses_planes:  # exported planes reconstruct the fp32 output to 2^-21 relative (fp16) / 2^-15 (bf16)
+        rec = out.planes[0].float() + out.planes[1].float()
+        rel = 2.0 ** (-21 if mode.startswith("fp16") else -15)
+        assert float((rec - out.f32).abs().max()) <= rel * float(out.f32.abs().max()) + 1e-7
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16x1"])
+def test_linear_grouped_matches_single(mode):
+    prec = F_.get_precision(mode)
+    xs = [rnd(300, 256, seed=10 + g) for g in range(3)]
+    lins = [make_linear(768, 256, 20 + g) for g in range(3)]
+    packs = [F_.PackedLinear([l], None, None) for l in lins]
+    ep = F_.make_epilogue(act_pre=L.ACT_GELU)
+    grouped = F_.linear(prec, [Act(x) for x in xs], packs, ep)
+    for g in range(3):
+        single = F_.linear(prec, [Act(xs[g])], [packs[g]], ep)[0]
+        assert torch.equal(grouped[g].f32, single.f32)
+
+
+def test_packed_linear_concat_and_scale():
+    prec = F_.get_precision("fp32")
+    a, b = make_linear(256, 256, 1), make_linear(256, 256, 2)
+    pk = F_.PackedLinear([a, b], [1.0, 0.5], None)
+    x = rnd(64, 256, seed=3)
+    y = F_.linear(prec, [Act(x)], [pk], F_.make_epilogue())[0].f32
+    ref = torch.cat([x @ a.weight.t() + a.bias, (x / 2) @ b.weight.t() + b.bias], 1)
+    assert float((y - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("fmt", ["fp16x3", "bf16x3"])
+def test_split_planes_bound(fmt):
+    prec = F_.get_precision(fmt)
+    x = rnd(129, 256, seed=5, scale=3.0)
+    p = F_.split_planes(x, prec, scale=0.5)
+    rec = p[0].float() + p[1].float()
+    rel = 2.0 ** (-21 if fmt.startswith("fp16") else -15)
+    assert float((rec - 0.5 * x).abs().max()) <= rel * float(x.abs().max())
+    assert torch.equal(p[0], (0.5 * x).to(prec.plane_dtype))
+
+
+@pytest.mark.parametrize("kind", ["self", "causal", "cross"])
+@pytest.mark.parametrize("B,T", [(2, 24), (3, 37), (8, 200), (1, 130), (2, 400)])
+def test_stream_attention_key_mask(kind, B, T):
+    H, D = 16, 256
+    prec = F_.get_precision("fp32")
+    q, k, v = (rnd(B * T, D, seed=s) for s in (1, 2, 3))
+    lengths = synth.parity_lengths(B, T)
+    mask = (torch.arange(T)[None] < torch.tensor(lengths)[:, None]).long()
+    if B >= 3:
+        mask[2] = 0  # an all-padded sequence: rows must come out uniform over the permitted keys
+    out = F_.stream_attention(prec, [q], [k], [v], B, T, T, H, {"self": 0, "causal": 1, "cross": 2}[kind],
+                              key_mask=F_.key_mask_u8(mask.to(DEV)))[0].f32
+    qh, kh, vh = (t.cpu().view(B, T, H, 16).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    if kind == "causal":
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1)[None, None], float("-inf"))
+        s = s + O.causal_additive(mask, T, torch.float32)
+    else:
+        s = s + O.key_padding_additive(mask, torch.float32)
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * T, D)
+    assert float((out.cpu() - ref).abs().max()) <= 3e-5
+
+
+def test_stream_attention_additive_mask_and_grouping():
+    B, T, H, D = 2, 24, 16, 256
+    prec = F_.get_precision("fp16x3")
+    qs = [rnd(B * T, 3 * D, seed=s) for s in (1, 2, 3)]
+    add = rnd(B, 1, T, T, seed=9)
+    outs = F_.stream_attention(prec, [t[:, :D] for t in qs], [t[:, D:2 * D] for t in qs], [t[:, 2 * D:] for t in qs], B, T, T, H, 0,
+                               additive=add)
+    for g in range(3):
+        q, k, v = (qs[g][:, i * D:(i + 1) * D].cpu().view(B, T, H, 16).transpose(1, 2) for i in range(3))
+        ref = (torch.softmax(q @ k.transpose(-1, -2) + add.cpu(), -1) @ v).transpose(1, 2).reshape(B * T, D)
+        rec = outs[g].planes[0].float() + outs[g].planes[1].float()
+        assert float((rec.cpu() - ref).abs().max()) <= 3e-5
+
+
+@pytest.mark.parametrize("B,T,D", [(2, 7, 1024), (8, 50, 1024), (2, 200, 1024), (3, 9, 512)])
+def test_fusion_attention(B, T, D):
+    prec = F_.get_precision("fp32")
+    q, k, v = (rnd(B * T, D, seed=s, scale=0.6).abs() for s in (1, 2, 3))  # GELU-like positive-heavy operands, large logits
+    out = F_.fusion_attention(prec, q, k, v, B, T).f32
+    qd, kd, vd = (t.double().cpu().view(B, T, D) for t in (q, k, v))
+    ref = (torch.softmax(qd @ kd.transpose(1, 2), -1) @ vd).reshape(B * T, D)
+    assert float((out.double().cpu() - ref).abs().max()) <= 2e-4
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 21, 256), (8, 200, 256), (3, 5, 512), (1, 2, 512)])
+def test_pool_pairs_exact(B, T, C):
+    prec = F_.get_precision("fp16x3")
+    x = rnd(B * T, C, seed=1)
+    out = F_.pool_pairs(prec, x, B, T)
+    ref = O.max_pool_pairs(x.view(B, T, C)).reshape(-1, C)
+    assert torch.equal(out.f32, ref)
+    assert torch.equal(out.planes[0], ref.to(torch.float16))
+    with pytest.raises(RuntimeError):
+        F_.pool_pairs(prec, x[:B], B, 1)
+
+
+def test_rowwise_layernorm_widths():
+    prec = F_.get_precision("fp16x3")
+    for n in (256, 512, 1024):
+        z, r = rnd(77, n, seed=1, scale=2.0), rnd(77, n, seed=2)
+        ln = torch.nn.LayerNorm(n)
+        with torch.no_grad():
+            ln.weight.copy_(1.0 + 0.2 * (torch.rand(n, generator=torch.Generator().manual_seed(3)) - 0.5))
+            ln.bias.copy_(0.1 * (torch.rand(n, generator=torch.Generator().manual_seed(4)) - 0.5))
+        ln = ln.to(DEV)
+        out = F_.rowwise(prec, z, F_.make_epilogue(layer_norm=True, residual_mode=L.RES_AFTER_LN, act_post=L.ACT_RELU), ln, r)
+        ref = torch.relu(torch.nn.functional.layer_norm(z.double(), (n,), ln.weight.double(), ln.bias.double(), 1e-5) + r.double())
+        assert float((out.f32.double() - ref).abs().max()) <= 1e-5
+
+
+def test_frontend_gather_exact_and_embeddings():
+    from scattennet_b200.config import model_config
+    from scattennet_b200.keypoint_module import KeypointModule, frontend_forward
+
+    cfg = model_config("phoenix-2014t")
+    B, T = 3, 37
+    kp, _ = synth.synth_batch(B, T, seed=2)
+    mods, idxs = [], []
+    for i, part in enumerate(("body", "left", "right")):
+        m = KeypointModule(cfg[part + "_idx"], cfg["num_frame"], dict(cfg, self_attn_x=(i != 1))).eval()
+        synth.load_synth_(m, 30 + i)
+        mods.append(m.to(DEV))
+        idxs.append(torch.tensor(cfg[part + "_idx"], dtype=torch.int32, device=DEV))
+    # a non-contiguous, unsorted index list must work too (the API is an arbitrary list)
+    idxs[0] = torch.tensor([500, 3, 541, 0, 77, 12], dtype=torch.int32, device=DEV)
+    prec = F_.get_precision("fp16x3")
+    s, c, gathered = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T, want_gathered=True)
+    for g, m in enumerate(mods):
+        idx = idxs[g].cpu().long()
+        region = kp[:, :, idx, :]
+        assert torch.equal(gathered[g].cpu(), region)  # bit-exact region gather
+        sd = {"m." + k: v.cpu() for k, v in m.state_dict().items()}
+        xe, ye = O.coordinate_mapping(sd, "m.coordinate_mapping", region)
+        s_in, c_in = (xe, ye) if m.sca.x_self else (ye, xe)
+        s_ref = O.layer_norm(sd, "m.sca.first_self_norm", O.position_embed(sd, "m.sca.self_pos_embed", s_in))
+        c_ref = O.layer_norm(sd, "m.sca.first_causal_norm", O.position_embed(sd, "m.sca.causal_pos_embed", c_in))
+        assert float((s[g].f32.cpu().view(B, T, -1) - s_ref).abs().max()) <= 1e-5
+        assert float((c[g].f32.cpu().view(B, T, -1) - c_ref).abs().max()) <= 1e-5
+    with pytest.raises(IndexError):
+        big, _ = synth.synth_batch(1, 257, seed=2)
+        frontend_forward(prec, mods, big.to(DEV), idxs, 1, 257)
