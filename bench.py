@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Encoder frames/sec on synthetic Phoenix-2014T-shaped keypoint batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path (region split -> 3 keypoint streams ->
+coordinate fusion -> 4 linear heads) over one batch of B=8 sequences of T=200
+frames per GPU (BASELINE.json configs[1]); N > 1 runs one such batch per rank
+(weak scaling, no data-path collective) and all-gathers the CTC logits.
+Rank 0 prints ONE JSON line (see the contract in the task description):
+
+  value      frames/s with inputs resident in HBM, CUDA-graph replay, device-timed
+  e2e        same metric from pinned host keypoints to logits back on the host
+  roofline   dominant kernel: algorithmic flops / measured launch time vs measured bf16 peak
+  cpu_baseline  the oracle (CPU port of the reference path) timed on this host
+
+``--impl reference`` times the reference's CPU implementation of the path (the
+oracle port: the reference is Python/ATen and cannot travel to the GPU box) on
+all host cores, same config / metric / unit.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encoder frames/sec, Phoenix-2014T shape"
+UNIT = "frames/s"
+CFG_NAME, BATCH, T = "phoenix-2014t", 8, 200
+VOCAB = 1120
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # pragma: no cover
+        return os.cpu_count() or 1
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while active."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.active = threading.Event()
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+            bits = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            if self.active.is_set():
+                self.sample()
+            time.sleep(self.period)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- reference arm / cpu baseline
+
+
+def time_oracle(steps: int, warmup: int, budget_s: float, batch: int = BATCH):
+    """Time the CPU port of the reference path (oracle) on all host cores."""
+    import torch
+
+    from oracle import scatt_oracle as O
+    from scattennet_b200 import MSCAEncoder, synth
+    from scattennet_b200.config import model_config
+
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    cfg = model_config(CFG_NAME)
+    shapes = {k: tuple(v.shape) for k, v in MSCAEncoder(cfg, VOCAB).state_dict().items()}
+    sd = synth.synth_state_dict(shapes, 0)
+    kp, mask = synth.synth_batch(batch, T, seed=1)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.encoder_forward(sd, cfg, kp, mask)
+        first = time.perf_counter() - t0
+        # bound the sample: shrink the per-step batch if K steps would blow the budget
+        b = batch
+        if steps * first > budget_s:
+            b = max(1, int(batch * budget_s / (steps * first)))
+            kp, mask = kp[:b], mask[:b]
+        for _ in range(max(0, warmup - 1)):
+            O.encoder_forward(sd, cfg, kp, mask)
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.encoder_forward(sd, cfg, kp, mask)
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": b * T * steps / total, "ms_per_step": 1e3 * total / steps, "best_ms": 1e3 * min(times), "cores": cores,
+            "sample": f"{steps} full forwards of {CFG_NAME} B={b} T={T} fp32 (torch CPU, {cores} threads), full-length masks"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_oracle(args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SCAttenNet {CFG_NAME}.yaml encoder forward (3 streams + fusion + 4 linear heads), batch {BATCH}, T={T}",
+                   "host": "CPU only (reference path: the oracle port of model/*.py, ATen fp32)"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from scattennet_b200 import MSCAEncoder, _lib, synth
+    from scattennet_b200 import functional as F_
+    from scattennet_b200.config import model_config
+    from scattennet_b200.distributed import gather_logits
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().scatt_device_check(), "scatt_device_check")
+
+    cfg = model_config(CFG_NAME)
+    model = MSCAEncoder(cfg, VOCAB, precision=args.precision, use_graph=True).eval()
+    synth.load_synth_(model, seed=0)
+    model = model.to(dev)
+    kp_host, mask_host = synth.synth_batch(args.batch, T, seed=1 + rank)
+    kp_pin, mask_pin = kp_host.pin_memory(), mask_host.pin_memory()
+    kp_dev, mask_dev = kp_host.to(dev), mask_host.to(dev)
+    heads = ("left", "right", "body", "fuse_coord_gloss_logits")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        out = model(kp_dev, mask_dev)
+        if world > 1:
+            out = dict(out)
+            out["gathered"] = gather_logits(out["fuse_coord_gloss_logits"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = step()
+        torch.cuda.synchronize()
+        launches_per_step = model.graph_launches(kp_dev.shape, dev)
+
+        sampler = ClockSampler(local)
+        sampler.start()
+
+        # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed in between
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        sampler.active.set()
+        wall0 = time.perf_counter()
+        for e0, e1 in ev:
+            flush.zero_()
+            e0.record()
+            step()
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        sampler.sample()
+        sampler.active.clear()
+        dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+
+        # ---- end to end: pinned host keypoints -> device -> encoder -> logits back on the host
+        out_pin = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in heads}
+        h2d = kp_pin.numel() * kp_pin.element_size() + mask_pin.numel() * mask_pin.element_size()
+        d2h = sum(v.numel() * v.element_size() for v in out_pin.values())
+
+        def e2e_step():
+            kp_dev.copy_(kp_pin, non_blocking=True)
+            mask_dev.copy_(mask_pin, non_blocking=True)
+            o = step()
+            for k in heads:
+                out_pin[k].copy_(o[k], non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        sampler.active.set()
+        for e0, e1 in ev2:
+            flush.zero_()
+            e0.record()
+            e2e_step()
+            e1.record()
+        barrier()
+        sampler.active.clear()
+        e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
+        sampler.stop_flag.set()
+
+        # ---- per-kernel share and achieved rate: eager passes with CUDA-event brackets per C-ABI call
+        model.use_graph = False
+        for _ in range(2):
+            model(kp_dev, mask_dev)
+        with F_.profile_ops() as prof:
+            for _ in range(args.profile_steps):
+                flush.zero_()
+                model(kp_dev, mask_dev)
+        per_kernel = prof.summary()
+        model.use_graph = True
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = measured_peaks()
+        frames = world * args.batch * T * args.steps
+        top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+        tk = per_kernel[top]
+        total_prof_ms = sum(v["ms"] for v in per_kernel.values())
+        terms = F_.get_precision(args.precision).terms
+        tensor_bound = top in ("linear_tc_kernel", "stream_attention_kernel", "fusion_attention_kernel", "linear_simt_kernel")
+        if tensor_bound:
+            achieved = tk["flops"] / (tk["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops"]}
+        else:
+            achieved = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"]}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(top)
+        roof.update({
+            "traffic": traffic, "kernel": top, "launches_profiled": tk["calls"], "avg_launch_us": 1e3 * tk["ms"] / tk["calls"],
+            "share_of_step": tk["ms"] / total_prof_ms, "peak_source": peaks["source"] + ", burst figure",
+            "note": f"algorithmic flops (2*M*N*K, one product per MAC); the {terms}-term split issues {max(terms, 1)}x that on the tensor pipe",
+            "per_kernel_ms_per_step": {k: round(v["ms"] / args.profile_steps, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])},
+        })
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_oracle(steps=8, warmup=2, budget_s=25.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        line = {
+            "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": f"{args.precision} (16-bit split planes on tcgen05, fp32 accumulate; fp32 softmax/LN)",
+            "data": "synthetic",
+            "config": {"workload": f"SCAttenNet {CFG_NAME}.yaml encoder forward (region split + 3 streams + fusion + 4 linear heads), "
+                                   f"batch {args.batch} per GPU, T={T}, V={VOCAB}, random-init weights",
+                       "global_batch": world * args.batch, "seq_len": T, "parallelism": f"dp{world} (batch shards, logits all-gather)",
+                       "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
+                       "timing": "CUDA events per step on the launching stream, summed; max over ranks", "cuda_graph": True},
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "wall_s_timed_region": wall,
+            "clocks": sampler.result(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp16x3")
+    ap.add_argument("--batch", type=int, default=BATCH, help="sequences per GPU (BASELINE config: 8)")
+    ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

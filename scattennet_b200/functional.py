@@ -69,6 +69,64 @@ def get_precision(name: Optional[str] = None) -> Precision:
     return PRECISIONS[name or _default_precision]
 
 
+# ----------------------------------------------------------------------------- per-op profiling hook
+
+
+class OpProfiler:
+    """CUDA-event brackets around every C-ABI call made while active (eager
+    passes only - events cannot be timed inside graph capture).  Used by
+    ``bench.py`` to find the dominant kernel and its achieved rate."""
+
+    def __init__(self):
+        self.records = []  # (kernel name, start event, end event, algorithmic flops, algorithmic bytes)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1, flops, nbytes in self.records:
+            a = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += nbytes
+        return agg
+
+
+_profiler: Optional[OpProfiler] = None
+
+
+class profile_ops:
+    def __enter__(self):
+        global _profiler
+        _profiler = OpProfiler()
+        return _profiler
+
+    def __exit__(self, *exc):
+        global _profiler
+        _profiler = None
+        return False
+
+
+class _timed:
+    __slots__ = ("name", "flops", "nbytes", "e0")
+
+    def __init__(self, name: str, flops: float, nbytes: float):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _profiler is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profiler is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profiler.records.append((self.name, self.e0, e1, self.flops, self.nbytes))
+        return False
+
+
 # ----------------------------------------------------------------------------- helpers
 
 
@@ -216,8 +274,11 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
         keep.append((x, pk))
     ldx = xs[0].f32.stride(0) if xs[0].f32 is not None else K
     ldres = residuals[0].stride(0) if residuals is not None else N
-    L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
-                                  max(prec.terms, 1), _stream()), "scatt_linear")
+    esz = 2 if prec.uses_planes else 4
+    name = "linear_tc_kernel" if prec.uses_planes else "linear_simt_kernel"
+    with _timed(name, 2.0 * G * M * N * K, G * ((M * K + N * K) * esz + M * N * 4.0)):
+        L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
+                                      max(prec.terms, 1), _stream()), "scatt_linear")
     return outs
 
 
@@ -237,8 +298,10 @@ def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: i
         p.key_mask, p.additive = _ptr(key_mask), _ptr(additive)
         p.out, p.out_planes = _ptr(o), _ptr(op)
         outs.append(Act(o, op))
-    L.check(L.load().scatt_attention(probs, G, B, Tq, Tk, H, D // H, qs[0].stride(0), ks[0].stride(0), vs[0].stride(0), kind,
-                                     prec.plane_fmt, _stream()), "scatt_attention")
+    flops = (2.0 * B * Tq * (Tq + 1) * D if kind == L.ATTN_CAUSAL else 4.0 * B * Tq * Tk * D) * G
+    with _timed("stream_attention_kernel", flops, G * 4.0 * B * max(Tq, Tk) * D * 4):
+        L.check(L.load().scatt_attention(probs, G, B, Tq, Tk, H, D // H, qs[0].stride(0), ks[0].stride(0), vs[0].stride(0),
+                                         kind, prec.plane_fmt, _stream()), "scatt_attention")
     return outs
 
 
@@ -246,8 +309,9 @@ def fusion_attention(prec: Precision, q: torch.Tensor, k: torch.Tensor, v: torch
     D = q.shape[1]
     o = torch.empty(B * T, D, dtype=torch.float32, device=q.device) if not prec.uses_planes else None
     op = torch.empty(2, B * T, D, dtype=prec.plane_dtype, device=q.device) if prec.uses_planes else None
-    L.check(L.load().scatt_fusion_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), B, T, D, _ptr(o), _ptr(op),
-                                            prec.plane_fmt, _stream()), "scatt_fusion_attention")
+    with _timed("fusion_attention_kernel", 4.0 * B * T * T * D, 4.0 * B * T * D * 4):
+        L.check(L.load().scatt_fusion_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), B, T, D, _ptr(o), _ptr(op),
+                                                prec.plane_fmt, _stream()), "scatt_fusion_attention")
     return Act(o, op)
 
 
@@ -258,8 +322,9 @@ def pool_pairs(prec: Precision, x: torch.Tensor, B: int, T: int) -> Act:
         raise RuntimeError("max_pool1d() Invalid computed output size: 0")
     y = torch.empty(B * (T // 2), Cc, dtype=torch.float32, device=x.device)
     yp = torch.empty(2, B * (T // 2), Cc, dtype=prec.plane_dtype, device=x.device) if prec.uses_planes else None
-    L.check(L.load().scatt_pool_pairs(x.data_ptr(), B, T, Cc, y.data_ptr(), _ptr(yp), prec.plane_fmt, _stream()),
-            "scatt_pool_pairs")
+    with _timed("pool_pairs_kernel", 0.0, 1.5 * B * T * Cc * 4):
+        L.check(L.load().scatt_pool_pairs(x.data_ptr(), B, T, Cc, y.data_ptr(), _ptr(yp), prec.plane_fmt, _stream()),
+                "scatt_pool_pairs")
     return Act(y, yp)
 
 

@@ -249,8 +249,11 @@ def frontend_forward(prec: Precision, mods: Sequence[KeypointModule], keypoints:
             gathered.append(gt)
         s_acts.append(acts[0])
         c_acts.append(acts[1])
-    L.check(L.load().scatt_frontend(keypoints.data_ptr(), B, T, K, d, arr, G, max_pos, prec.plane_fmt, F_._stream()),
-            "scatt_frontend")
+    n_used = sum(int(j.numel()) for j in joint_idx)
+    out_bytes = 2 * G * d * (4 + (4 if prec.uses_planes else 0))
+    with F_._timed("frontend_kernel", 4.0 * n_used * d * B * T, float(B * T) * (n_used * 8 + out_bytes)):
+        L.check(L.load().scatt_frontend(keypoints.data_ptr(), B, T, K, d, arr, G, max_pos, prec.plane_fmt, F_._stream()),
+                "scatt_frontend")
     return s_acts, c_acts, gathered
 
 
