@@ -54,6 +54,20 @@ inline int after_launch(const char* name) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. at the
+// fp32 rounding level of the exact form) - ~14 instructions instead of ~40 for
+// erff(); used in the tensor-core epilogues where code size matters.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == SCATT_ACT_GELU) return gelu_erf(x);
   if (act == SCATT_ACT_RELU) return fmaxf(x, 0.0f);

@@ -128,120 +128,171 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, uint32_t tmem_acc, int64_t row,
-                                              int n0, bool row_ok) {
-  const scatt_epilogue& ep = P.ep;
-  const int N = P.N;
-  constexpr int kChunks = BN / 32;
-  float v[32];
+// ------------------------------------------------------------------ epilogue
+// One thread owns one output row (TMEM lane); columns arrive 32 at a time.
+// All per-column parameters are fetched as float4 (warp-uniform addresses ->
+// L1 broadcasts), every option is tested once per chunk, never per element,
+// and the chunk loops are not unrolled: the body stays a few KB of SASS so it
+// lives in the instruction cache (the first version of this epilogue was
+// 136 KB of straight-line code and spent ~55 us per launch fetching it).
 
-  auto pre_norm = [&](int c0) {  // acc -> (acc + bias) * scale -> act_pre -> + residual(before LN)
+__device__ __forceinline__ void add_vec32(float* v, const float* __restrict__ p) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c0 + j;
-      float x = v[j];
-      if (col < N) {
-        if (Q.bias) x += __ldg(Q.bias + col);
-        if (col < ep.scale_cols) x *= ep.scale;
-        x = apply_act(x, ep.act_pre);
-      }
-      v[j] = x;
-    }
-    if (row_ok && (ep.residual_mode == SCATT_RES_BEFORE_LN || (!P.fused_ln && ep.residual_mode == SCATT_RES_AFTER_LN))) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (c0 + j < N) {
-          const float4 r = *reinterpret_cast<const float4*>(Q.residual + row * P.ldres + c0 + j);
-          v[j] += r.x, v[j + 1] += r.y, v[j + 2] += r.z, v[j + 3] += r.w;
-        }
-    }
-  };
-  auto finish_store = [&](int c0) {  // act_post -> clamp -> y / planes
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float x = apply_act(v[j], ep.act_post);
-      if (ep.clamp > 0.f) x = fminf(fmaxf(x, -ep.clamp), ep.clamp);
-      v[j] = x;
-    }
-    if (!row_ok) return;
-    if (Q.y) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (c0 + j < N)
-          *reinterpret_cast<float4*>(Q.y + row * P.ldy + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-    if (Q.y_planes) {
-      const int64_t plane = P.M * int64_t(N);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        if (c0 + j < N) {
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint16_t h0, l0, h1, l1;
-            split16_rt(v[j + 2 * e], P.fmt, h0, l0);
-            split16_rt(v[j + 2 * e + 1], P.fmt, h1, l1);
-            h[e] = h0 | (uint32_t(h1) << 16);
-            l[e] = l0 | (uint32_t(l1) << 16);
-          }
-          const int64_t off = row * N + c0 + j;
-          *reinterpret_cast<uint4*>(Q.y_planes + off) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(Q.y_planes + plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
-        }
-    }
-  };
-
-  if (!P.fused_ln) {
-#pragma unroll 1
-    for (int c = 0; c < kChunks; ++c) {
-      const int c0 = n0 + c * 32;
-      if (c0 >= N) break;  // warp-uniform
-      tc_ld32(tmem_acc + c * 32, v);
-      pre_norm(c0);
-      finish_store(c0);
-    }
-    return;
-  }
-
-  // fused LayerNorm over the BN == N columns of this row (n0 == 0)
-  float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    tc_ld32(tmem_acc + c * 32, v);
-    pre_norm(c * 32);
-    if (c == 0) shift = v[0];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = v[j] - shift;
-      s1 += d;
-      s2 = fmaf(d, d, s2);
-    }
-    tc_st32(tmem_acc + c * 32, v);
-  }
-  const float inv_n = 1.0f / float(N);
-  const float dm = s1 * inv_n;
-  const float mean = shift + dm;
-  const float var = fmaxf(s2 * inv_n - dm * dm, 0.f);
-  const float rstd = rsqrtf(var + ep.ln_eps);
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    const int c0 = c * 32;
-    tc_ld32(tmem_acc + c0, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * __ldg(Q.ln_g + c0 + j) + __ldg(Q.ln_b + c0 + j);
-    if (row_ok && ep.residual_mode == SCATT_RES_AFTER_LN) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 r = *reinterpret_cast<const float4*>(Q.residual + row * P.ldres + c0 + j);
-        v[j] += r.x, v[j + 1] += r.y, v[j + 2] += r.z, v[j + 3] += r.w;
-      }
-    }
-    finish_store(c0);
+  for (int j = 0; j < 32; j += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + j));
+    v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
   }
 }
 
-template <int BN>
+__device__ __forceinline__ void act_vec32(float* v, int act) {
+  if (act == SCATT_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+  } else if (act == SCATT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+}
+
+// acc -> (acc + bias) * colscale -> act_pre -> (+ residual)
+__device__ __forceinline__ void chunk_pre(const TcParams& P, const TcProblem& Q, float* v, int c0, int64_t row, bool row_ok,
+                                          bool add_res) {
+  if (Q.bias) add_vec32(v, Q.bias + c0);
+  if (c0 < P.ep.scale_cols) {  // scale_cols is a multiple of 32 (checked on the host)
+    const float s = P.ep.scale;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= s;
+  }
+  act_vec32(v, P.ep.act_pre);
+  if (add_res && row_ok) {
+    const float* r = Q.residual + row * P.ldres + c0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(r + j);
+      v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
+    }
+  }
+}
+
+// act_post -> clamp -> y (fp32) and / or split planes
+__device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, float* v, int c0, int64_t row, bool row_ok) {
+  act_vec32(v, P.ep.act_post);
+  if (P.ep.clamp > 0.f) {
+    const float c = P.ep.clamp;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -c), c);
+  }
+  if (!row_ok) return;
+  if (Q.y) {
+    float* y = Q.y + row * P.ldy + c0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  if (Q.y_planes) {
+    uint16_t* hi = Q.y_planes + row * P.N + c0;
+    uint16_t* lo = hi + P.M * int64_t(P.N);
+    if (P.fmt == SCATT_PLANE_F16) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __half2 hh = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+          const float2 back = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(v[j + 2 * e] - back.x, v[j + 2 * e + 1] - back.y);
+          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi + j) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + j) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+          const float2 back = __bfloat1622float2(hh);
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(v[j + 2 * e] - back.x, v[j + 2 * e + 1] - back.y);
+          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(hi + j) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + j) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
+template <int BN, bool FUSED_LN>
+__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, uint32_t tmem_acc, int64_t row,
+                                              int n0, bool row_ok) {
+  const scatt_epilogue& ep = P.ep;
+  constexpr int kChunks = BN / 32;
+  float v[32];
+
+  if constexpr (!FUSED_LN) {
+    const bool add_res = ep.residual_mode != SCATT_RES_NONE;  // no LayerNorm here: before == after
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      const int c0 = n0 + c * 32;
+      if (c0 >= P.N) break;  // N is a multiple of 32; warp-uniform
+      tc_ld32(tmem_acc + c * 32, v);
+      chunk_pre(P, Q, v, c0, row, row_ok, add_res);
+      chunk_store(P, Q, v, c0, row, row_ok);
+    }
+  } else {
+    // LayerNorm over the BN == N columns of this row (n0 == 0).  Pass 1 builds the
+    // pre-norm value, accumulates shifted sums and parks the value back in TMEM.
+    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+    const bool res_before = ep.residual_mode == SCATT_RES_BEFORE_LN;
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      tc_ld32(tmem_acc + c * 32, v);
+      chunk_pre(P, Q, v, c * 32, row, row_ok, res_before);
+      if (c == 0) shift = v[0];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = v[j] - shift;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+      tc_st32(tmem_acc + c * 32, v);
+    }
+    const float inv_n = 1.0f / float(BN);
+    const float dm = s1 * inv_n;
+    const float mean = shift + dm;
+    const float rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + ep.ln_eps);
+    const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      const int c0 = c * 32;
+      tc_ld32(tmem_acc + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(Q.ln_g + c0 + j));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(Q.ln_b + c0 + j));
+        v[j] = (v[j] - mean) * rstd * g.x + b.x;
+        v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
+        v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
+        v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
+      }
+      if (res_after && row_ok) {
+        const float* r = Q.residual + row * P.ldres + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(r + j);
+          v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
+        }
+      }
+      chunk_store(P, Q, v, c0, row, row_ok);
+    }
+  }
+}
+
+
+template <int BN, bool FUSED_LN>
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, then barriers
@@ -335,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     tc_fence_after();
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const int64_t row = m0 + quad * 32 + lane;
-    epilogue_rows<BN>(P, P.prob[g], tmem_acc + (uint32_t(quad * 32) << 16), row, n0, row < P.M);
+    epilogue_rows<BN, FUSED_LN>(P, P.prob[g], tmem_acc + (uint32_t(quad * 32) << 16), row, n0, row < P.M);
   }
 
   tc_fence_before();
@@ -385,7 +436,7 @@ int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K,
   return SCATT_OK;
 }
 
-template <int BN>
+template <int BN, bool FUSED_LN>
 int launch_bn(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
   const int num_kb = (P.K + BK - 1) / BK;
@@ -397,11 +448,11 @@ int launch_bn(TcParams& P, int group, cudaStream_t s) {
   const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 16;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, FUSED_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done.store(true);
   }
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
-  linear_tc_kernel<BN><<<grid, kThreads, smem, s>>>(P);
+  linear_tc_kernel<BN, FUSED_LN><<<grid, kThreads, smem, s>>>(P);
   return after_launch("linear_tc_kernel");
 }
 
@@ -410,7 +461,8 @@ int launch_bn(TcParams& P, int group, cudaStream_t s) {
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
                      const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s) {
   SCATT_REQUIRE(terms >= 1 && terms <= 3, "linear(tcgen05): terms must be 1, 2 or 3");
-  SCATT_REQUIRE(K % 8 == 0 && N % 8 == 0, "linear(tcgen05): K=%d and N=%d must be multiples of 8", K, N);
+  SCATT_REQUIRE(K % 8 == 0 && N % 32 == 0, "linear(tcgen05): K=%d must be a multiple of 8 and N=%d of 32", K, N);
+  SCATT_REQUIRE(ep.scale_cols % 32 == 0, "linear(tcgen05): scale_cols must be a multiple of 32");
   SCATT_REQUIRE(ldres % 4 == 0 && ldy % 4 == 0, "linear(tcgen05): row strides must be multiples of 4");
   SCATT_REQUIRE(M < (int64_t(1) << 31), "linear(tcgen05): M too large");
   if (M == 0) return SCATT_OK;
@@ -441,7 +493,8 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     P.prob[i] = TcProblem{p[i].bias, p[i].residual, p[i].ln_g, p[i].ln_b, p[i].y,
                           split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes)};
   }
-  int rc = (BN == 256) ? launch_bn<256>(P, group, s) : launch_bn<128>(P, group, s);
+  int rc = fused_ln ? launch_bn<256, true>(P, group, s)
+                    : (BN == 256 ? launch_bn<256, false>(P, group, s) : launch_bn<128, false>(P, group, s));
   if (rc != SCATT_OK || !split_ln) return rc;
   for (int i = 0; i < group; ++i) {
     rc = launch_rowwise(p[i].y, M, N, ldy, p[i].residual, ldres, p[i].ln_g, p[i].ln_b, ep, p[i].y, ldy, p[i].y_planes,

@@ -48,9 +48,10 @@ def gather_logits(local: torch.Tensor, group=None) -> torch.Tensor:
     world = dist.get_world_size(group)
     if world == 1:
         return local
-    local = local.contiguous()
+    local = local.detach().contiguous()
     out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local, group=group)
+    with torch.no_grad():
+        dist.all_gather_into_tensor(out, local, group=group)
     return out
 
 
