@@ -70,6 +70,10 @@ const char* scatt_last_error(void);
 uint64_t scatt_launch_count(void);
 /* 0 if the current device is sm_100 and the kernels are loadable. */
 int scatt_device_check(void);
+/* Developer aid: when `dev_buf` (device memory, >= 16 x int64) is non-NULL, CTA 0 of
+ * every tcgen05 linear launch stores clock64() stamps of its pipeline phases there
+ * (tools/trace_linear.py); NULL switches tracing off. */
+int scatt_debug_set_trace(void* dev_buf);
 
 /* ------------------------------------------------------------------ split planes */
 

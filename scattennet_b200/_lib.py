@@ -14,7 +14,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscatt.so")
+LIB_PATH = os.environ.get("SCATT_LIB", os.path.join(_HERE, "libscatt.so"))  # SCATT_LIB: instrumented dev builds
 
 MAX_GROUP = 4
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
@@ -26,6 +26,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 # every symbol include/scatt.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_launch_count", "scatt_device_check",
+    "scatt_debug_set_trace",
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
     "scatt_attention", "scatt_fusion_attention", "scatt_pool_pairs",
 )
@@ -75,6 +76,8 @@ def _declare(lib):
     lib.scatt_last_error.restype = C.c_char_p
     lib.scatt_launch_count.restype = C.c_uint64
     lib.scatt_device_check.restype = i32
+    lib.scatt_debug_set_trace.argtypes = [vp]
+    lib.scatt_debug_set_trace.restype = i32
     lib.scatt_split_planes.argtypes = [vp, i64, i64, i64, f32, vp, i32, vp]
     lib.scatt_frontend.argtypes = [vp, i32, i32, i32, i32, C.POINTER(FrontendStream), i32, i32, i32, vp]
     lib.scatt_posembed_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]

@@ -46,16 +46,18 @@ def is_current() -> bool:
     return os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read().strip() == _digest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a and link ``libscatt.so``; returns its path."""
-    if not force and is_current():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = OUT) -> str:
+    """Compile every CUDA source for sm_100a and link ``libscatt.so``; returns its path.
+    ``extra_flags`` / ``out`` build instrumented variants for the dev tools."""
+    if not force and not extra_flags and is_current():
         return OUT
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if not extra_flags else OBJ_DIR + "_" + hashlib.sha1(" ".join(extra_flags).encode()).hexdigest()[:8]
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
@@ -67,13 +69,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    link = [nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
+    link = [nvcc, *ARCH, "-shared", "-o", out, *objs, "-cudart", "static", "-Xcompiler", "-fPIC"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    with open(OUT + ".digest", "w") as fh:
-        fh.write(_digest())
-    return OUT
+    if out == OUT:
+        with open(OUT + ".digest", "w") as fh:
+            fh.write(_digest())
+    return out
 
 
 if __name__ == "__main__":

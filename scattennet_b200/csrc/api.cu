@@ -50,6 +50,8 @@ int scatt_device_check(void) {
   return SCATT_OK;
 }
 
+int scatt_debug_set_trace(void* dev_buf) { return debug_set_trace(dev_buf); }
+
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,
                        void* stream) {
   SCATT_REQUIRE(x && planes && fmt_ok(plane_fmt), "split_planes: null pointer or bad plane format");

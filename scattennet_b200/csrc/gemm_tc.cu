@@ -1,19 +1,29 @@
 // tcgen05 engine of scatt_linear (sm_100a):
 //   y = epilogue(x W^T + bias),  x and W given as 16-bit hi/lo split planes.
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0   TMA producer   cp.async.bulk.tensor (3-D maps: K x rows x plane, 128B swizzle)
-//   warp 1   TMEM allocator + single-thread tcgen05.mma issuer (accumulators in TMEM)
-//   warps 2-5 epilogue      tcgen05.ld -> bias / scale / act / residual / LayerNorm -> global
+// One CTA computes a 128 x BN output tile.  Warp roles (320 threads):
+//   warp 0     TMA producer   cp.async.bulk.tensor (3-D maps: K x rows x plane, 128B swizzle)
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer (accumulators in TMEM)
+//   warps 2-9  epilogue: two warps per TMEM lane quadrant, each owning half of the columns
 // A `stages`-deep smem ring is handed between producer and issuer with
 // full/empty mbarriers; the issuer signals the epilogue through a TMEM-full
 // mbarrier (tcgen05.commit).  With `terms` = 3 every K step issues
-// hi*hi + lo*hi + hi*lo so products are fp32-grade while running on the bf16 /
-// fp16 tensor pipe; `terms` = 1 is the plain 16-bit product.
+// hi*hi + lo*hi + hi*lo so products are fp32-grade while running on the fp16 /
+// bf16 tensor pipe; `terms` = 1 is the plain 16-bit product.
 //
-// LayerNorm is fused when the CTA owns the whole row (N == BN <= 256): the
-// pre-norm value is written back to TMEM (tcgen05.st) during the statistics
-// pass, so the residual is read once.
+// What keeps the epilogue short (it used to be 4x the main loop, see
+// profiles/r01_linear_phase_trace.txt):
+//   * accumulator pre-initialisation: while TMA/MMA start up, the (otherwise
+//     idle) epilogue warps write `bias + residual` into the TMEM accumulator
+//     with tcgen05.st, so the residual stream is fetched off the critical
+//     path and the MMAs simply accumulate on top of it;
+//   * per-column parameters (bias, gamma, beta) are staged in shared memory once;
+//   * every global access goes through a per-warp staging tile, so a warp
+//     instruction touches whole row segments (64-byte fp32 / 32-byte plane
+//     pieces) instead of 32 different rows;
+//   * LayerNorm is fused when the CTA owns the whole row (N == BN == 256): one
+//     statistics pass over TMEM (Chan-combined between the two column halves),
+//     one normalise-and-store pass.
 #include <cuda.h>
 
 #include <mutex>
@@ -26,7 +36,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kWaitLimit = 1u << 22;  // bounded mbarrier spin: trap instead of hanging the GPU
 
 struct TcProblem {
@@ -44,8 +55,15 @@ struct alignas(64) TcParams {
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
-  int32_t N, K, stages, terms, fmt, fused_ln;
+  int32_t N, K, stages, terms, fmt, fused_ln, pre_init;
 };
+
+// Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
+// stores clock64() stamps of its pipeline phases.
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+  if (g_trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[slot] = clock64();
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -128,18 +146,63 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // the 8 epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
 // ------------------------------------------------------------------ epilogue
 // One thread owns one output row (TMEM lane); columns arrive 32 at a time.
-// All per-column parameters are fetched as float4 (warp-uniform addresses ->
-// L1 broadcasts), every option is tested once per chunk, never per element,
-// and the chunk loops are not unrolled: the body stays a few KB of SASS so it
-// lives in the instruction cache (the first version of this epilogue was
-// 136 KB of straight-line code and spent ~55 us per launch fetching it).
+// Global I/O goes through a per-warp staging tile of 32 rows x 16 fp32 (rows
+// padded to 20 words) so that a warp instruction moves 8 rows x 64 B.
+constexpr int kEpiLd = 20;
+constexpr int kEpiWarpBytes = 32 * kEpiLd * 4;
 
-__device__ __forceinline__ void add_vec32(float* v, const float* __restrict__ p) {
+struct EpiCtx {
+  float* stage;            // this warp's staging tile
+  const float* col_bias;   // smem copies of the per-column parameters of this CTA's BN columns
+  const float* col_g;
+  const float* col_b;
+  int64_t row0;            // first global row of this warp's 32-row slab
+  int rows_valid;          // rows of the slab that exist (M tail)
+  int lane;
+};
+
+// registers <- 32 x 32 fp32 tile of a row-major matrix (two 16-column halves), coalesced
+__device__ __forceinline__ void tile_fetch(const EpiCtx& E, const float* __restrict__ g, int64_t ld, int c0, float4 (&r)[8]) {
+  const int sub = E.lane >> 2, c4 = (E.lane & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = 8 * i + sub;
+      r[h * 4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < E.rows_valid) r[h * 4 + i] = *reinterpret_cast<const float4*>(g + (E.row0 + row) * ld + c0 + h * 16 + c4);
+    }
+}
+// v[32] (thread-per-row) += the fetched tile, transposed through the staging tile
+__device__ __forceinline__ void tile_add(const EpiCtx& E, const float4 (&r)[8], float* v) {
+  const int sub = E.lane >> 2, c4 = (E.lane & 3) * 4;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(E.stage + (8 * i + sub) * kEpiLd + c4) = r[h * 4 + i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(E.stage + E.lane * kEpiLd + j);
+      v[h * 16 + j] += t.x, v[h * 16 + j + 1] += t.y, v[h * 16 + j + 2] += t.z, v[h * 16 + j + 3] += t.w;
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ void add_cols(float* v, const float* __restrict__ p) {  // p: shared memory, warp-uniform
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p + j));
+    const float4 t = *reinterpret_cast<const float4*>(p + j);
     v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
   }
 }
@@ -154,174 +217,241 @@ __device__ __forceinline__ void act_vec32(float* v, int act) {
   }
 }
 
-// acc -> (acc + bias) * colscale -> act_pre -> (+ residual)
-__device__ __forceinline__ void chunk_pre(const TcParams& P, const TcProblem& Q, float* v, int c0, int64_t row, bool row_ok,
-                                          bool add_res) {
-  if (Q.bias) add_vec32(v, Q.bias + c0);
-  if (c0 < P.ep.scale_cols) {  // scale_cols is a multiple of 32 (checked on the host)
-    const float s = P.ep.scale;
+template <int FMT>
+__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= s;
-  }
-  act_vec32(v, P.ep.act_pre);
-  if (add_res && row_ok) {
-    const float* r = Q.residual + row * P.ldres + c0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(r + j);
-      v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
+  for (int e = 0; e < 4; ++e) {
+    if (FMT == SCATT_PLANE_F16) {
+      const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+      const float2 back = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    } else {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+      const float2 back = __bfloat1622float2(hh);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
+      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }
   }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// act_post -> clamp -> y (fp32) and / or split planes
-__device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, float* v, int c0, int64_t row, bool row_ok) {
+// act_post -> clamp -> y (fp32) and / or split planes, via the staging tile
+__device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, const EpiCtx& E, float* v, int c0) {
   act_vec32(v, P.ep.act_post);
   if (P.ep.clamp > 0.f) {
     const float c = P.ep.clamp;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -c), c);
   }
-  if (!row_ok) return;
-  if (Q.y) {
-    float* y = Q.y + row * P.ldy + c0;
+  const int64_t plane = P.M * int64_t(P.N);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(y + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  }
-  if (Q.y_planes) {
-    uint16_t* hi = Q.y_planes + row * P.N + c0;
-    uint16_t* lo = hi + P.M * int64_t(P.N);
-    if (P.fmt == SCATT_PLANE_F16) {
+  for (int h = 0; h < 2; ++h) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint32_t h[4], l[4];
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(E.stage + E.lane * kEpiLd + j) =
+          make_float4(v[h * 16 + j], v[h * 16 + j + 1], v[h * 16 + j + 2], v[h * 16 + j + 3]);
+    __syncwarp();
+#ifdef SCATT_DBG_NO_Y
+    if (false) {
+#else
+    if (Q.y) {
+#endif
+      const int sub = E.lane >> 2, c4 = (E.lane & 3) * 4;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __half2 hh = __floats2half2_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-          const float2 back = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(v[j + 2 * e] - back.x, v[j + 2 * e + 1] - back.y);
-          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-        *reinterpret_cast<uint4*>(hi + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(lo + j) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-          const float2 back = __bfloat1622float2(hh);
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(v[j + 2 * e] - back.x, v[j + 2 * e + 1] - back.y);
-          h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
-        *reinterpret_cast<uint4*>(hi + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(lo + j) = make_uint4(l[0], l[1], l[2], l[3]);
+      for (int i = 0; i < 4; ++i) {
+        const int row = 8 * i + sub;
+        if (row < E.rows_valid)
+          *reinterpret_cast<float4*>(Q.y + (E.row0 + row) * P.ldy + c0 + h * 16 + c4) =
+              *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c4);
       }
     }
+#ifdef SCATT_DBG_NO_PLANES
+    if (false) {
+#else
+    if (Q.y_planes) {
+#endif
+      const int sub = E.lane >> 1, c8 = (E.lane & 1) * 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int row = 16 * i + sub;
+        if (row < E.rows_valid) {
+          const float4 a = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8);
+          const float4 b = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8 + 4);
+          uint4 hi, lo;
+          if (P.fmt == SCATT_PLANE_F16) split8<SCATT_PLANE_F16>(a, b, hi, lo);
+          else split8<SCATT_PLANE_BF16>(a, b, hi, lo);
+          uint16_t* dst = Q.y_planes + (E.row0 + row) * P.N + c0 + h * 16 + c8;
+          *reinterpret_cast<uint4*>(dst) = hi;
+          *reinterpret_cast<uint4*>(dst + plane) = lo;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// (acc [+ bias]) * colscale -> act_pre -> [+ residual]; returns true if v was modified
+__device__ __forceinline__ bool chunk_pre(const TcParams& P, const TcProblem& Q, const EpiCtx& E, float* v, int cl, int c0,
+                                          bool late_res) {
+  bool modified = false;
+  if (!P.pre_init && Q.bias) {
+    add_cols(v, E.col_bias + cl);
+    modified = true;
+  }
+  if (c0 < P.ep.scale_cols) {  // scale_cols is a multiple of 32 (checked on the host)
+    const float s = P.ep.scale;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= s;
+    modified = true;
+  }
+  if (P.ep.act_pre != SCATT_ACT_NONE) {
+    act_vec32(v, P.ep.act_pre);
+    modified = true;
+  }
+  if (late_res) {
+    float4 r[8];
+    tile_fetch(E, Q.residual, P.ldres, c0, r);
+    tile_add(E, r, v);
+    modified = true;
+  }
+  return modified;
+}
+
+// Runs on the epilogue warps while TMA / MMA start: accumulator <- bias + residual.
+template <int BN>
+__device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
+                                             int half) {
+  constexpr int kMine = BN / 64;  // 32-column chunks per warp
+  float4 r[2][8];
+  int c = half * kMine;
+  if (n0 + c * 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + c * 32, r[0]);
+#pragma unroll
+  for (int i = 0; i < kMine; ++i) {
+    const int cl = (half * kMine + i) * 32;
+    if (n0 + cl >= P.N) break;
+    if (i + 1 < kMine && n0 + cl + 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    if (Q.bias) add_cols(v, E.col_bias + cl);
+    tile_add(E, r[i & 1], v);
+    tc_st32(tmem_acc + cl, v);
   }
 }
 
 template <int BN, bool FUSED_LN>
-__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, uint32_t tmem_acc, int64_t row,
-                                              int n0, bool row_ok) {
+__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
+                                              int half, float2* stats, int row_in_tile) {
   const scatt_epilogue& ep = P.ep;
-  constexpr int kChunks = BN / 32;
+  constexpr int kMine = BN / 64;
   float v[32];
+  const bool late_res_any = ep.residual_mode != SCATT_RES_NONE && !P.pre_init;
 
   if constexpr (!FUSED_LN) {
-    const bool add_res = ep.residual_mode != SCATT_RES_NONE;  // no LayerNorm here: before == after
 #pragma unroll 1
-    for (int c = 0; c < kChunks; ++c) {
-      const int c0 = n0 + c * 32;
+    for (int i = 0; i < kMine; ++i) {
+      const int cl = (half * kMine + i) * 32, c0 = n0 + cl;
       if (c0 >= P.N) break;  // N is a multiple of 32; warp-uniform
-      tc_ld32(tmem_acc + c * 32, v);
-      chunk_pre(P, Q, v, c0, row, row_ok, add_res);
-      chunk_store(P, Q, v, c0, row, row_ok);
+      tc_ld32(tmem_acc + cl, v);
+      chunk_pre(P, Q, E, v, cl, c0, late_res_any);  // no LayerNorm: residual before == after
+      chunk_store(P, Q, E, v, c0);
     }
   } else {
-    // LayerNorm over the BN == N columns of this row (n0 == 0).  Pass 1 builds the
-    // pre-norm value, accumulates shifted sums and parks the value back in TMEM.
+    // LayerNorm over the BN == N columns of the row (n0 == 0).  Pass 1: statistics of this
+    // warp's half of the columns (shifted sums), combined with the other half (Chan et al.).
+    constexpr float kHalfN = float(BN / 2);
+    const bool late_res = late_res_any && ep.residual_mode == SCATT_RES_BEFORE_LN;
     float shift = 0.f, s1 = 0.f, s2 = 0.f;
-    const bool res_before = ep.residual_mode == SCATT_RES_BEFORE_LN;
 #pragma unroll 1
-    for (int c = 0; c < kChunks; ++c) {
-      tc_ld32(tmem_acc + c * 32, v);
-      chunk_pre(P, Q, v, c * 32, row, row_ok, res_before);
-      if (c == 0) shift = v[0];
+    for (int i = 0; i < kMine; ++i) {
+      const int cl = (half * kMine + i) * 32;
+      tc_ld32(tmem_acc + cl, v);
+      if (chunk_pre(P, Q, E, v, cl, cl, late_res)) tc_st32(tmem_acc + cl, v);
+      if (i == 0) shift = v[0];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float d = v[j] - shift;
         s1 += d;
         s2 = fmaf(d, d, s2);
       }
-      tc_st32(tmem_acc + c * 32, v);
     }
-    const float inv_n = 1.0f / float(BN);
-    const float dm = s1 * inv_n;
-    const float mean = shift + dm;
-    const float rstd = rsqrtf(fmaxf(s2 * inv_n - dm * dm, 0.f) + ep.ln_eps);
+    const float dm = s1 / kHalfN;
+    const float my_mean = shift + dm, my_m2 = fmaxf(s2 - s1 * dm, 0.f);
+    stats[half * BM + row_in_tile] = make_float2(my_mean, my_m2);
+    epi_bar_sync();
+    if (threadIdx.x == 64) trace(6);
+    const float2 other = stats[(half ^ 1) * BM + row_in_tile];
+    const float mean = 0.5f * (my_mean + other.x);
+    const float da = my_mean - mean, db = other.x - mean;
+    const float var = (my_m2 + other.y + kHalfN * (da * da + db * db)) / float(BN);
+    const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
-#pragma unroll 1
-    for (int c = 0; c < kChunks; ++c) {
-      const int c0 = c * 32;
-      tc_ld32(tmem_acc + c0, v);
+    float4 r[2][8];
+    if (res_after) tile_fetch(E, Q.residual, P.ldres, half * kMine * 32, r[0]);
+#pragma unroll
+    for (int i = 0; i < kMine; ++i) {
+      const int cl = (half * kMine + i) * 32;
+      if (res_after && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, cl + 32, r[(i + 1) & 1]);
+      tc_ld32(tmem_acc + cl, v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(Q.ln_g + c0 + j));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(Q.ln_b + c0 + j));
+        const float4 g = *reinterpret_cast<const float4*>(E.col_g + cl + j);
+        const float4 b = *reinterpret_cast<const float4*>(E.col_b + cl + j);
         v[j] = (v[j] - mean) * rstd * g.x + b.x;
         v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
         v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
         v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
       }
-      if (res_after && row_ok) {
-        const float* r = Q.residual + row * P.ldres + c0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(r + j);
-          v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
-        }
-      }
-      chunk_store(P, Q, v, c0, row, row_ok);
+      if (res_after) tile_add(E, r[i & 1], v);
+      chunk_store(P, Q, E, v, cl);
     }
   }
 }
 
-
 template <int BN, bool FUSED_LN>
 __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, then barriers
+  // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, barriers, column parameters, LN partials, staging tiles
   constexpr uint32_t kABytes = BM * 128, kBBytes = BN * 128;
   const bool need_a_lo = P.terms >= 2, need_b_lo = P.terms >= 3;
   const uint32_t kBOff = kABytes * (need_a_lo ? 2 : 1);  // B tiles follow the A plane(s) of a stage
   const uint32_t kStageBytes = kBOff + kBBytes * (need_b_lo ? 2 : 1);
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t bar_base = base + stages * kStageBytes;  // full[stages], empty[stages], tmem_full, tmem_ptr
+  const uint32_t bar_base = base + stages * kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   const uint32_t tmem_full_bar = bar_base + 16u * stages;
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - smem_u32(smem_raw)));
+  const uint32_t acc_init_bar = tmem_full_bar + 8u;
+  const uint32_t tmem_ptr_addr = acc_init_bar + 8u;
+  const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][BN]
+  const uint32_t stats_base = col_base + 3u * BN * 4u;               // float2[2][BM]
+  const uint32_t stage_base = stats_base + 2u * BM * 8u;             // kEpiWarps staging tiles
+  auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z;
   const int n0 = blockIdx.x * BN;
   const int64_t m0 = int64_t(blockIdx.y) * BM;
   const int num_kb = (P.K + BK - 1) / BK;
+  const TcProblem& Q = P.prob[g];
 
+  if (threadIdx.x == 0) trace(0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(acc_init_bar, 32 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_a[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
@@ -331,10 +461,20 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) {  // per-column parameters of this CTA's columns -> shared memory
+    float* col = reinterpret_cast<float*>(gen(col_base));
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) {
+      const bool in = n0 + i < P.N;
+      col[i] = (in && Q.bias) ? Q.bias[n0 + i] : 0.f;
+      col[BN + i] = (in && Q.ln_g) ? Q.ln_g[n0 + i] : 0.f;
+      col[2 * BN + i] = (in && Q.ln_b) ? Q.ln_b[n0 + i] : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_gen;
+  if (threadIdx.x == 0) trace(1);
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
@@ -348,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
         if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kb * BK, int(m0), 1);
         tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, n0, 0);
         if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, n0, 1);
+        if (kb == 0) trace(2);
       }
     }
   } else if (warp == 1) {
@@ -356,9 +497,15 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
       const uint32_t idesc = (1u << 4) | (uint32_t(P.fmt) << 7) | (uint32_t(P.fmt) << 10) | (uint32_t(BN >> 3) << 17) |
                              (uint32_t(BM >> 4) << 24);
       uint32_t accumulate = 0;
+      if (P.pre_init) {  // the epilogue warps have put bias + residual into the accumulator
+        mbar_wait(acc_init_bar, 0);
+        tc_fence_after();
+        accumulate = 1;
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % stages;
         mbar_wait(full_bar(s), (kb / stages) & 1);
+        if (kb == 0) trace(3);
         tc_fence_after();
         const uint32_t st = base + s * kStageBytes;
         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kABytes);
@@ -380,17 +527,35 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
         tc_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
       }
       tc_commit(tmem_full_bar);  // accumulator complete
+      trace(4);
     }
-  } else {  // ---------------- epilogue warps 2..5
+  } else {  // ---------------- epilogue warps 2..9
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;   // which half of the columns
+    const float* col = reinterpret_cast<const float*>(gen(col_base));
+    EpiCtx E;
+    E.stage = reinterpret_cast<float*>(gen(stage_base)) + (warp - 2) * (kEpiWarpBytes / 4);
+    E.col_bias = col, E.col_g = col + BN, E.col_b = col + 2 * BN;
+    E.row0 = m0 + quad * 32;
+    E.rows_valid = int(min(int64_t(32), max(int64_t(0), P.M - E.row0)));
+    E.lane = lane;
+    const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
+    if (P.pre_init) {
+      acc_pre_init<BN>(P, Q, E, my_tmem, n0, half);
+      tc_fence_before();
+      mbar_arrive(acc_init_bar);
+      if (threadIdx.x == 64) trace(9);
+    }
     mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 64) trace(5);
     tc_fence_after();
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int64_t row = m0 + quad * 32 + lane;
-    epilogue_rows<BN, FUSED_LN>(P, P.prob[g], tmem_acc + (uint32_t(quad * 32) << 16), row, n0, row < P.M);
+    epilogue_rows<BN, FUSED_LN>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), quad * 32 + lane);
+    if (threadIdx.x == 64) trace(7);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(8);
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(BN)) : "memory");
@@ -440,12 +605,13 @@ template <int BN, bool FUSED_LN>
 int launch_bn(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
   const int num_kb = (P.K + BK - 1) / BK;
-  int stages = int((200u * 1024u) / kStageBytes);
+  int stages = int((198u * 1024u) / kStageBytes);
   if (stages > num_kb) stages = num_kb;
   if (stages > 8) stages = 8;
   if (stages < 1) stages = 1;
   P.stages = stages;
-  const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 16;
+  const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 2 * BM * 8 +
+                      kEpiWarps * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, FUSED_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -457,6 +623,12 @@ int launch_bn(TcParams& P, int group, cudaStream_t s) {
 }
 
 }  // namespace
+
+int debug_set_trace(void* dev_buf) {
+  long long* p = reinterpret_cast<long long*>(dev_buf);
+  SCATT_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+  return SCATT_OK;
+}
 
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
                      const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s) {
@@ -480,6 +652,10 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     if (ep.residual_mode == SCATT_RES_AFTER_LN) P.ep.residual_mode = SCATT_RES_NONE;
   }
   P.M = M, P.N = N, P.K = K, P.ldres = ldres, P.ldy = ldy, P.terms = terms, P.fmt = fmt, P.fused_ln = fused_ln ? 1 : 0;
+  // The residual can be folded into the accumulator's initial value when nothing non-linear
+  // or scaled sits between the GEMM and the add.
+  const bool res_early = P.ep.residual_mode == SCATT_RES_BEFORE_LN || (!fused_ln && P.ep.residual_mode == SCATT_RES_AFTER_LN);
+  P.pre_init = (res_early && P.ep.act_pre == SCATT_ACT_NONE && P.ep.scale_cols == 0) ? 1 : 0;
   for (int i = 0; i < group; ++i) {
     SCATT_REQUIRE(p[i].x_planes && p[i].w_planes, "linear(tcgen05): problem %d lacks split planes", i);
     SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual, "linear(tcgen05): residual missing");
