@@ -279,7 +279,7 @@ def run_ours(args):
         tk = per_kernel[top]
         total_prof_ms = sum(v["ms"] for v in per_kernel.values())
         terms = F_.get_precision(args.precision).terms
-        tensor_bound = top in ("linear_tc_kernel", "stream_attention_kernel", "fusion_attention_kernel", "linear_simt_kernel")
+        tensor_bound = top in ("linear_tc_kernel", "stream_attention_kernel", "stream_attention_tc_kernel", "fusion_attention_kernel", "linear_simt_kernel")
         if tensor_bound:
             achieved = tk["flops"] / (tk["ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",

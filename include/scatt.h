@@ -181,8 +181,12 @@ typedef struct scatt_attention_problem {
   void* out_planes; /* [2][B*Tq][H*hd] or NULL */
 } scatt_attention_problem;
 
+/* `engine` = SCATT_ENGINE_TCGEN05 runs both contractions on the tensor cores
+ * (split planes built in shared memory, `terms` product terms) when Tk <= 256
+ * and no dense additive mask is given; otherwise, and for SCATT_ENGINE_SIMT,
+ * the fp32 CUDA-core kernel runs. */
 int scatt_attention(const scatt_attention_problem* problems_host, int group, int B, int Tq, int Tk, int H, int hd,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int plane_fmt, void* stream);
+                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int engine, int plane_fmt, int terms, void* stream);
 
 /* ------------------------------------------------------------------ K5: fusion attention */
 

@@ -84,7 +84,8 @@ def _declare(lib):
     lib.scatt_linear.argtypes = [C.POINTER(LinearProblem), i32, i64, i32, i32, i64, i64, i64, C.POINTER(Epilogue), i32, i32,
                                  i32, vp]
     lib.scatt_rowwise.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, C.POINTER(Epilogue), vp, i64, vp, i32, vp]
-    lib.scatt_attention.argtypes = [C.POINTER(AttentionProblem), i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, vp]
+    lib.scatt_attention.argtypes = [C.POINTER(AttentionProblem), i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32,
+                                    i32, vp]
     lib.scatt_fusion_attention.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.scatt_pool_pairs.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
     for name in ("scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",

@@ -94,9 +94,13 @@ int scatt_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* re
 }
 
 int scatt_attention(const scatt_attention_problem* problems_host, int group, int B, int Tq, int Tk, int H, int hd,
-                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int plane_fmt, void* stream) {
+                    int64_t ldq, int64_t ldk, int64_t ldv, int kind, int engine, int plane_fmt, int terms, void* stream) {
   SCATT_REQUIRE(problems_host && fmt_ok(plane_fmt), "attention: null pointer or bad plane format");
   SCATT_REQUIRE(kind >= SCATT_ATTN_SELF && kind <= SCATT_ATTN_CROSS, "attention: bad kind %d", kind);
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "attention: group 1..%d", SCATT_MAX_GROUP);
+  if (engine == SCATT_ENGINE_TCGEN05 && attention_tc_supported(Tq, Tk, hd, problems_host, group))
+    return launch_attention_tc(problems_host, group, B, Tq, Tk, H, hd, ldq, ldk, ldv, kind, plane_fmt, terms,
+                               as_stream(stream));
   return launch_attention(problems_host, group, B, Tq, Tk, H, hd, ldq, ldk, ldv, kind, plane_fmt, as_stream(stream));
 }
 

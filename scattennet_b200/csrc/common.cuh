@@ -143,6 +143,9 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
 int debug_set_trace(void* dev_buf);
 int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int64_t ldq,
                      int64_t ldk, int64_t ldv, int kind, int fmt, cudaStream_t s);
+bool attention_tc_supported(int Tq, int Tk, int hd, const scatt_attention_problem* p, int group);
+int launch_attention_tc(const scatt_attention_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int64_t ldq,
+                        int64_t ldk, int64_t ldv, int kind, int fmt, int terms, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);
 
