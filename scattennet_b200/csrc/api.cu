@@ -50,7 +50,10 @@ int scatt_device_check(void) {
   return SCATT_OK;
 }
 
-int scatt_debug_set_trace(void* dev_buf) { return debug_set_trace(dev_buf); }
+int scatt_debug_set_trace(void* dev_buf) {
+  const int rc = debug_set_trace(dev_buf);
+  return rc != SCATT_OK ? rc : debug_set_trace_attention(dev_buf);
+}
 
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,
                        void* stream) {

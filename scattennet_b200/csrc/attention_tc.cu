@@ -12,9 +12,10 @@
 //
 //   warps 0-3  load + split operands; then one thread per query row: read the
 //              S row from TMEM, exact two-pass softmax (max, then exp / sum) with
-//              the reference's mask semantics, write P (hi/lo) to shared memory
-//              as the A operand of the second contraction; finally scale and
-//              store the O row
+//              the reference's mask semantics, write P (hi/lo, packed 16-bit) back
+//              into the TMEM columns S occupied - the second contraction takes its
+//              A operand straight from TMEM (no shared-memory round trip for P);
+//              finally scale and store the O row
 //   warp 4     TMEM allocation and the single MMA-issuing thread
 //
 // Mask semantics (model/utils.py:3-28, model/attention.py:63-72,165-171): a
@@ -36,6 +37,11 @@ constexpr int QT = 128;      // queries per CTA
 constexpr int KMAX = 256;    // keys per CTA (one S tile)
 constexpr int kThreadsAtt = 160;
 
+__device__ long long* g_trace_att = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+  if (g_trace_att != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace_att[slot] = clock64();
+}
+
 struct AttnTcParams {
   scatt_attention_problem p[SCATT_MAX_GROUP];
   int32_t B, Tq, Tk, H, kind, fmt, terms;
@@ -47,9 +53,7 @@ constexpr uint32_t kQOff = 0;                       // [128 rows][128 B]: hi at 
 constexpr uint32_t kKOff = kQOff + QT * 128;        // [256 rows][128 B]: same packing
 constexpr uint32_t kVhOff = kKOff + KMAX * 128;     // V^T hi: 4 key blocks x [16 rows][128 B]
 constexpr uint32_t kVlOff = kVhOff + 4 * 2048;      // V^T lo
-constexpr uint32_t kPhOff = kVlOff + 4 * 2048;      // P hi: 4 key blocks x [128 rows][128 B]
-constexpr uint32_t kPlOff = kPhOff + 4 * 16384;     // P lo
-constexpr uint32_t kPadOff = kPlOff + 4 * 16384;    // float[256] key class: 0 valid / -FLT_MAX padded / -inf absent
+constexpr uint32_t kPadOff = kVlOff + 4 * 2048;     // float[256] key class: 0 valid / -FLT_MAX padded / -inf absent
 constexpr uint32_t kBarOff = kPadOff + KMAX * 4;    // 3 mbarriers + tmem pointer
 constexpr uint32_t kSmemBytes = kBarOff + 64 + 1024;
 
@@ -87,8 +91,35 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (P) is read from tensor memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 template <int FMT>
-__global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(const __grid_constant__ AttnTcParams P) {
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (FMT == SCATT_PLANE_F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 back = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreadsAtt, 2) stream_attention_tc_kernel(const __grid_constant__ AttnTcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -104,8 +135,11 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
   const bool causal = P.kind == SCATT_ATTN_CAUSAL;
   const int nk = causal ? min(Tk, m0 + QT) : Tk;       // keys this tile can see
   const int nkp = (nk + 15) & ~15;                      // MMA N / K granularity
-  const bool lo_planes = P.terms >= 2;
+  // S / P take nkp columns, O the next 16: 256 columns (two CTAs per SM) up to 224 keys, else all 512
+  const uint32_t tmem_cols = nkp <= 224 ? 256u : 512u;
+  const uint32_t o_col = nkp <= 224 ? 224u : 256u;
 
+  if (threadIdx.x == 0) trace(0);
   if (threadIdx.x == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 128);
@@ -113,42 +147,77 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
   // ---------------- operand staging: fp32 global rows -> split 16-bit swizzled tiles
   // Q and K: row r holds hi(k 0..15) in bytes 0..31 and lo(k 0..15) in bytes 32..63
-  for (int i = threadIdx.x; i < (QT + nkp) * 4; i += kThreadsAtt) {
-    const int r = i >> 2, c = i & 3;  // c: which float4 of the 16-wide head row
-    const bool is_q = r < QT;
-    const int row = is_q ? r : r - QT;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (is_q) {
-      if (m0 + row < Tq) x = *reinterpret_cast<const float4*>(A.q + (int64_t(b) * Tq + m0 + row) * P.ldq + h * HD + 4 * c);
-    } else if (row < nk) {
-      x = *reinterpret_cast<const float4*>(A.k + (int64_t(b) * Tk + row) * P.ldk + h * HD + 4 * c);
-    }
-    uint2 hi, lo;
-    split4<FMT>(x, hi, lo);
-    uint8_t* tile = sm + (is_q ? kQOff : kKOff);
-    *reinterpret_cast<uint2*>(tile + sw128(row, 8 * c)) = hi;
-    *reinterpret_cast<uint2*>(tile + sw128(row, 32 + 8 * c)) = lo;
-  }
-  // V^T: B operand of O = P V, [16 rows (head dim)][keys], 64 keys per 2 KB block
-  for (int i = threadIdx.x; i < nkp * 4; i += kThreadsAtt) {
-    const int j = i >> 2, c = i & 3;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < nk) x = *reinterpret_cast<const float4*>(A.v + (int64_t(b) * Tk + j) * P.ldv + h * HD + 4 * c);
-    const float xs[4] = {x.x, x.y, x.z, x.w};
-    const uint32_t blk = (j >> 6) * 2048, kb = (j & 63) * 2;
+  {
+    const int total = (QT + nkp) * 4;
+    constexpr int kBatch = 4;  // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += kThreadsAtt * kBatch) {
+      float4 x[kBatch];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      uint16_t hi, lo;
-      split1<FMT>(xs[e], hi, lo);
-      const uint32_t off = blk + sw128(4 * c + e, kb);
-      *reinterpret_cast<uint16_t*>(sm + kVhOff + off) = hi;
-      *reinterpret_cast<uint16_t*>(sm + kVlOff + off) = lo;
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * kThreadsAtt;
+        const int r = i >> 2, c = i & 3;  // c: which float4 of the 16-wide head row
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total) {
+          if (r < QT) {
+            if (m0 + r < Tq) x[u] = *reinterpret_cast<const float4*>(A.q + (int64_t(b) * Tq + m0 + r) * P.ldq + h * HD + 4 * c);
+          } else if (r - QT < nk) {
+            x[u] = *reinterpret_cast<const float4*>(A.k + (int64_t(b) * Tk + r - QT) * P.ldk + h * HD + 4 * c);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * kThreadsAtt;
+        if (i < total) {
+          const int r = i >> 2, c = i & 3;
+          const bool is_q = r < QT;
+          const int row = is_q ? r : r - QT;
+          uint2 hi, lo;
+          split4<FMT>(x[u], hi, lo);
+          uint8_t* tile = sm + (is_q ? kQOff : kKOff);
+          *reinterpret_cast<uint2*>(tile + sw128(row, 8 * c)) = hi;
+          *reinterpret_cast<uint2*>(tile + sw128(row, 32 + 8 * c)) = lo;
+        }
+      }
+    }
+  }
+  if (threadIdx.x == 0) trace(1);
+  // V^T: B operand of O = P V, [16 rows (head dim)][keys], 64 keys per 2 KB block
+  {
+    const int total = nkp * 4;
+    constexpr int kBatch = 3;
+    for (int i0 = threadIdx.x; i0 < total; i0 += kThreadsAtt * kBatch) {
+      float4 x[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * kThreadsAtt;
+        const int j = i >> 2, c = i & 3;
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total && j < nk) x[u] = *reinterpret_cast<const float4*>(A.v + (int64_t(b) * Tk + j) * P.ldv + h * HD + 4 * c);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * kThreadsAtt;
+        if (i < total) {
+          const int j = i >> 2, c = i & 3;
+          const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+          const uint32_t blk = (j >> 6) * 2048, kb = (j & 63) * 2;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint16_t hi, lo;
+            split1<FMT>(xs[e], hi, lo);
+            const uint32_t off = blk + sw128(4 * c + e, kb);
+            *reinterpret_cast<uint16_t*>(sm + kVhOff + off) = hi;
+            *reinterpret_cast<uint16_t*>(sm + kVlOff + off) = lo;
+          }
+        }
+      }
     }
   }
   for (int j = threadIdx.x; j < KMAX; j += kThreadsAtt) {
@@ -156,12 +225,14 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
     if (j < nk) cls = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
     pad[j] = cls;
   }
+  if (threadIdx.x == 0) trace(2);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (threadIdx.x == 0) trace(3);
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kBarOff + 24);
-  const uint32_t tmem_s = tmem, tmem_o = tmem + 256;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + o_col;
 
   // instruction descriptors: D = f32, A/B = f16|bf16 K-major, M = 128
   const uint32_t idesc_base = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(QT >> 4) << 24);
@@ -188,20 +259,20 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
       const uint32_t idesc_o = idesc_base | (uint32_t(HD >> 3) << 17);
       acc = 0;
       for (int ks = 0; ks < nkp / 16; ++ks) {
+        // P of keys [16 ks, 16 ks + 16): hi in 8 TMEM columns, lo 16 columns further (see the softmax warps)
+        const uint32_t p_hi = tmem_s + 32 * (ks >> 1) + 8 * (ks & 1), p_lo = p_hi + 16;
         const uint32_t blk = ks >> 2, adv = (ks & 3) * 2;
-        const uint64_t ph = umma_desc_sw128(base + kPhOff + blk * 16384) + adv;
-        const uint64_t pl = umma_desc_sw128(base + kPlOff + blk * 16384) + adv;
         const uint64_t vh = umma_desc_sw128(base + kVhOff + blk * 2048) + adv;
         const uint64_t vl = umma_desc_sw128(base + kVlOff + blk * 2048) + adv;
         if (P.terms >= 3) {
-          tc_mma_f16(tmem_o, ph, vl, idesc_o, acc);
+          tc_mma_f16_ts(tmem_o, p_hi, vl, idesc_o, acc);
           acc = 1;
         }
         if (P.terms >= 2) {
-          tc_mma_f16(tmem_o, pl, vh, idesc_o, acc);
+          tc_mma_f16_ts(tmem_o, p_lo, vh, idesc_o, acc);
           acc = 1;
         }
-        tc_mma_f16(tmem_o, ph, vh, idesc_o, acc);
+        tc_mma_f16_ts(tmem_o, p_hi, vh, idesc_o, acc);
         acc = 1;
       }
       tc_commit(bar_o);
@@ -216,6 +287,7 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
     float v[32];
     mbar_wait(bar_s, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) trace(4);
     float mx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < nchunk; ++c) {
@@ -229,6 +301,7 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
         mx = fmaxf(mx, s);
       }
     }
+    if (threadIdx.x == 0) trace(5);
     // rows past Tq (tile tail) have q = 0 and still see >= 1 key, so mx is finite for every row
     const float kLog2e = 1.4426950408889634f;
     float l = 0.f;
@@ -245,24 +318,21 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
         l += p;
         v[j] = p;
       }
-      // P row -> A-operand tiles (8 keys = one 16-byte swizzle chunk per plane)
-      const uint32_t blk = (c >> 1) * 16384, kb0 = (c & 1) * 64;  // 32 keys = 64 bytes inside the 128-byte row
+      // P row back into the columns this S chunk came from, as the TMEM A operand of O = P V:
+      // 16-bit pairs (key 2w, 2w+1) per 32-bit column; hi plane in columns [32c, 32c+16), lo in [32c+16, 32c+32)
+      float w[32];
+      uint32_t* wp = reinterpret_cast<uint32_t*>(w);
 #pragma unroll
-      for (int q8 = 0; q8 < 4; ++q8) {
-        uint2 h0, l0, h1, l1;
-        split4<FMT>(make_float4(v[8 * q8], v[8 * q8 + 1], v[8 * q8 + 2], v[8 * q8 + 3]), h0, l0);
-        split4<FMT>(make_float4(v[8 * q8 + 4], v[8 * q8 + 5], v[8 * q8 + 6], v[8 * q8 + 7]), h1, l1);
-        const uint32_t off = blk + sw128(r, kb0 + 16 * q8);
-        *reinterpret_cast<uint4*>(sm + kPhOff + off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        if (lo_planes) *reinterpret_cast<uint4*>(sm + kPlOff + off) = make_uint4(l0.x, l0.y, l1.x, l1.y);
-      }
+      for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
+      tc_st32(tmem_s + lane_addr + c * 32, w);
     }
-    fence_proxy_async();
+    if (threadIdx.x == 0) trace(6);
     tc_fence_before();
     mbar_arrive(bar_p);
 
     mbar_wait(bar_o, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) trace(7);
     float o[16];
     tc_ld16(tmem_o + lane_addr, o);
     const float inv = 1.0f / l;
@@ -280,13 +350,20 @@ __global__ void __launch_bounds__(kThreadsAtt, 1) stream_attention_tc_kernel(con
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(8);
   if (warp == 4) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
   }
 }
 
 }  // namespace
+
+int debug_set_trace_attention(void* dev_buf) {
+  long long* p = reinterpret_cast<long long*>(dev_buf);
+  SCATT_CUDA(cudaMemcpyToSymbol(g_trace_att, &p, sizeof(p)));
+  return SCATT_OK;
+}
 
 bool attention_tc_supported(int Tq, int Tk, int hd, const scatt_attention_problem* p, int group) {
   if (hd != HD || Tk > KMAX || Tk < 1) return false;
