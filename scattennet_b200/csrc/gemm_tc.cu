@@ -159,9 +159,13 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// act_post -> clamp -> y (fp32) and / or split planes, via the staging tile
+// act_post (none / ReLU) -> clamp -> y (fp32) and / or split planes, via the staging tile
+template <int FMT>
 __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, const EpiCtx& E, float* v, int c0) {
-  act_vec32(v, P.ep.act_post);
+  if (P.ep.act_post == SCATT_ACT_RELU) {  // GELU is only ever a pre-activation on this path (checked on the host)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
   if (P.ep.clamp > 0.f) {
     const float c = P.ep.clamp;
 #pragma unroll
@@ -202,8 +206,7 @@ __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& 
           const float4 a = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8);
           const float4 b = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8 + 4);
           uint4 hi, lo;
-          if (P.fmt == SCATT_PLANE_F16) split8<SCATT_PLANE_F16>(a, b, hi, lo);
-          else split8<SCATT_PLANE_BF16>(a, b, hi, lo);
+          split8<FMT>(a, b, hi, lo);
           uint16_t* dst = Q.y_planes + (E.row0 + row) * P.N + c0 + h * 16 + c8;
           *reinterpret_cast<uint4*>(dst) = hi;
           *reinterpret_cast<uint4*>(dst + plane) = lo;
@@ -249,7 +252,7 @@ __device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem&
   float4 r[2][8];
   int c = half * kMine;
   if (n0 + c * 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + c * 32, r[0]);
-#pragma unroll
+#pragma unroll 2
   for (int i = 0; i < kMine; ++i) {
     const int cl = (half * kMine + i) * 32;
     if (n0 + cl >= P.N) break;
@@ -263,26 +266,45 @@ __device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem&
   }
 }
 
-template <int BN, bool FUSED_LN>
+// cluster helpers (LN == 2: the row's 256 columns live in two CTAs of a cluster)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer_rank, float a, float b) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer_rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
+}
+
+// LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 = the row is split
+// over the two CTAs of a cluster (N == 2 BN), which exchange per-row partial statistics through DSMEM.
+template <int BN, int LN, int FMT>
 __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
-                                              int half, float2* stats, int row_in_tile) {
+                                              int half, float2* stats, uint32_t xstats_addr, int row_in_tile) {
   const scatt_epilogue& ep = P.ep;
   constexpr int kMine = BN / 64;
   float v[32];
   const bool late_res_any = ep.residual_mode != SCATT_RES_NONE && !P.pre_init;
 
-  if constexpr (!FUSED_LN) {
+  if constexpr (LN == 0) {
 #pragma unroll 1
     for (int i = 0; i < kMine; ++i) {
       const int cl = (half * kMine + i) * 32, c0 = n0 + cl;
       if (c0 >= P.N) break;  // N is a multiple of 32; warp-uniform
       tc_ld32(tmem_acc + cl, v);
       chunk_pre(P, Q, E, v, cl, c0, late_res_any);  // no LayerNorm: residual before == after
-      chunk_store(P, Q, E, v, c0);
+      chunk_store<FMT>(P, Q, E, v, c0);
     }
   } else {
-    // LayerNorm over the BN == N columns of the row (n0 == 0).  Pass 1: statistics of this
-    // warp's half of the columns (shifted sums), combined with the other half (Chan et al.).
+    // LayerNorm over the N columns of the row.  Pass 1: statistics of this warp's half of the
+    // CTA's columns (shifted sums), combined with the other half (Chan et al.) and, for LN == 2,
+    // with the peer CTA's half of the row.
     constexpr float kHalfN = float(BN / 2);
     const bool late_res = late_res_any && ep.residual_mode == SCATT_RES_BEFORE_LN;
     float shift = 0.f, s1 = 0.f, s2 = 0.f;
@@ -290,7 +312,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     for (int i = 0; i < kMine; ++i) {
       const int cl = (half * kMine + i) * 32;
       tc_ld32(tmem_acc + cl, v);
-      if (chunk_pre(P, Q, E, v, cl, cl, late_res)) tc_st32(tmem_acc + cl, v);
+      if (chunk_pre(P, Q, E, v, cl, n0 + cl, late_res)) tc_st32(tmem_acc + cl, v);
       if (i == 0) shift = v[0];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -305,17 +327,28 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     epi_bar_sync();
     if (threadIdx.x == 64) trace(6);
     const float2 other = stats[(half ^ 1) * BM + row_in_tile];
-    const float mean = 0.5f * (my_mean + other.x);
+    float mean = 0.5f * (my_mean + other.x);
     const float da = my_mean - mean, db = other.x - mean;
-    const float var = (my_m2 + other.y + kHalfN * (da * da + db * db)) / float(BN);
+    float m2 = my_m2 + other.y + kHalfN * (da * da + db * db);
+    if constexpr (LN == 2) {
+      if (half == 0) st_peer_f32x2(xstats_addr + 8u * row_in_tile, cluster_ctarank() ^ 1u, mean, m2);
+      cluster_sync_all();  // every thread of both CTAs takes part (warps 0 / 1 after their roles)
+      float2 peer;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(peer.x), "=f"(peer.y) : "r"(xstats_addr + 8u * row_in_tile) : "memory");
+      const float mc = mean;
+      mean = 0.5f * (mc + peer.x);
+      const float d1 = mc - mean, d2 = peer.x - mean;
+      m2 = m2 + peer.y + float(BN) * (d1 * d1 + d2 * d2);
+    }
+    const float var = m2 / float(LN == 2 ? 2 * BN : BN);
     const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
     float4 r[2][8];
-    if (res_after) tile_fetch(E, Q.residual, P.ldres, half * kMine * 32, r[0]);
-#pragma unroll
+    if (res_after) tile_fetch(E, Q.residual, P.ldres, n0 + half * kMine * 32, r[0]);
+#pragma unroll 2
     for (int i = 0; i < kMine; ++i) {
       const int cl = (half * kMine + i) * 32;
-      if (res_after && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, cl + 32, r[(i + 1) & 1]);
+      if (res_after && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
       tc_ld32(tmem_acc + cl, v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -327,13 +360,13 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
         v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
       }
       if (res_after) tile_add(E, r[i & 1], v);
-      chunk_store(P, Q, E, v, cl);
+      chunk_store<FMT>(P, Q, E, v, n0 + cl);
     }
   }
 }
 
-template <int BN, bool FUSED_LN>
-__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
+template <int BN, int LN, int FMT>
+__device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, barriers, column parameters, LN partials, staging tiles
   constexpr uint32_t kABytes = BM * 128, kBBytes = BN * 128;
@@ -351,7 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
   const uint32_t tmem_ptr_addr = acc_init_bar + 8u;
   const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][BN]
   const uint32_t stats_base = col_base + 3u * BN * 4u;               // float2[2][BM]
-  const uint32_t stage_base = stats_base + 2u * BM * 8u;             // kEpiWarps staging tiles
+  const uint32_t xstats_base = stats_base + 2u * BM * 8u;            // float2[BM] written by the peer CTA (LN == 2)
+  const uint32_t stage_base = xstats_base + BM * 8u;                 // kEpiWarps staging tiles
   auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
 
@@ -391,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (LN == 2) cluster_sync_all();  // the peer CTA is resident before anybody writes into its smem
   const uint32_t tmem_acc = *tmem_ptr_gen;
   if (threadIdx.x == 0) trace(1);
 
@@ -409,10 +444,14 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
         if (kb == 0) trace(2);
       }
     }
+    if constexpr (LN == 2) {
+      __syncwarp();
+      cluster_sync_all();  // statistics exchange point of the epilogue warps
+    }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
       // instruction descriptor: D=f32, A/B = f16|bf16, both K-major, N, M=128
-      const uint32_t idesc = (1u << 4) | (uint32_t(P.fmt) << 7) | (uint32_t(P.fmt) << 10) | (uint32_t(BN >> 3) << 17) |
+      const uint32_t idesc = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(BN >> 3) << 17) |
                              (uint32_t(BM >> 4) << 24);
       uint32_t accumulate = 0;
       if (P.pre_init) {  // the epilogue warps have put bias + residual into the accumulator
@@ -447,6 +486,10 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
       tc_commit(tmem_full_bar);  // accumulator complete
       trace(4);
     }
+    if constexpr (LN == 2) {
+      __syncwarp();
+      cluster_sync_all();
+    }
   } else {  // ---------------- epilogue warps 2..9
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;   // which half of the columns
@@ -467,7 +510,8 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 64) trace(5);
     tc_fence_after();
-    epilogue_rows<BN, FUSED_LN>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), quad * 32 + lane);
+    epilogue_rows<BN, LN, FMT>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
+                               quad * 32 + lane);
     if (threadIdx.x == 64) trace(7);
   }
 
@@ -478,6 +522,18 @@ __global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_con
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(BN)) : "memory");
   }
+}
+
+template <int BN, int LN, int FMT>
+__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<BN, LN, FMT>(P);
+}
+
+// N = 256 LayerNorm GEMM as 2-CTA clusters (one cluster per 128-row tile, BN = 128 per CTA): twice the
+// CTAs of the single-CTA variant for the small-batch regime, row statistics exchanged through DSMEM.
+template <int FMT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_tc_ln_cluster_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<128, 2, FMT>(P);
 }
 
 // ------------------------------------------------------------------ host side
@@ -519,25 +575,40 @@ int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K,
   return SCATT_OK;
 }
 
-template <int BN, bool FUSED_LN>
-int launch_bn(TcParams& P, int group, cudaStream_t s) {
+template <int BN, int LN, int FMT>
+int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
   const int num_kb = (P.K + BK - 1) / BK;
-  int stages = int((198u * 1024u) / kStageBytes);
+  int stages = int((197u * 1024u) / kStageBytes);
   if (stages > num_kb) stages = num_kb;
   if (stages > 8) stages = 8;
   if (stages < 1) stages = 1;
   P.stages = stages;
-  const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 2 * BM * 8 +
+  const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 +
                       kEpiWarps * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
-  if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, FUSED_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done.store(true);
-  }
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
-  linear_tc_kernel<BN, FUSED_LN><<<grid, kThreads, smem, s>>>(P);
-  return after_launch("linear_tc_kernel");
+  if constexpr (LN == 2) {
+    if (!attr_done.load()) {
+      SCATT_CUDA(cudaFuncSetAttribute(linear_tc_ln_cluster_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done.store(true);
+    }
+    linear_tc_ln_cluster_kernel<FMT><<<grid, kThreads, smem, s>>>(P);
+    return after_launch("linear_tc_ln_cluster_kernel");
+  } else {
+    if (!attr_done.load()) {
+      SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, LN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done.store(true);
+    }
+    linear_tc_kernel<BN, LN, FMT><<<grid, kThreads, smem, s>>>(P);
+    return after_launch("linear_tc_kernel");
+  }
+}
+
+template <int BN, int LN>
+int launch_bn(TcParams& P, int group, cudaStream_t s) {
+  return P.fmt == SCATT_PLANE_F16 ? launch_bn_fmt<BN, LN, SCATT_PLANE_F16>(P, group, s)
+                                  : launch_bn_fmt<BN, LN, SCATT_PLANE_BF16>(P, group, s);
 }
 
 }  // namespace
@@ -553,13 +624,19 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   SCATT_REQUIRE(terms >= 1 && terms <= 3, "linear(tcgen05): terms must be 1, 2 or 3");
   SCATT_REQUIRE(K % 8 == 0 && N % 32 == 0, "linear(tcgen05): K=%d must be a multiple of 8 and N=%d of 32", K, N);
   SCATT_REQUIRE(ep.scale_cols % 32 == 0, "linear(tcgen05): scale_cols must be a multiple of 32");
+  SCATT_REQUIRE(ep.act_post != SCATT_ACT_GELU, "linear(tcgen05): GELU is supported as act_pre only");
   SCATT_REQUIRE(ldres % 4 == 0 && ldy % 4 == 0, "linear(tcgen05): row strides must be multiples of 4");
   SCATT_REQUIRE(M < (int64_t(1) << 31), "linear(tcgen05): M too large");
   if (M == 0) return SCATT_OK;
   const bool fused_ln = ep.layer_norm && N == 256;
   // LayerNorm wider than one tile: GEMM with the pre-norm part of the chain, then the row-wise tail in place.
   const bool split_ln = ep.layer_norm && !fused_ln;
-  const int BN = (fused_ln || N % 256 == 0) ? 256 : 128;
+  // Small-batch regime: when the 128-row tiles of all problems fill at most half of the 148 SMs, halve the
+  // tile width of N = 256 outputs (LayerNorm then spans a 2-CTA cluster) so twice as many SMs share the
+  // memory traffic of the launch.
+  const int64_t row_tiles = ((M + BM - 1) / BM) * group;
+  const bool narrow = N == 256 && row_tiles <= 74;
+  const int BN = ((fused_ln || N % 256 == 0) && !narrow) ? 256 : 128;
 
   TcParams P{};
   P.ep = ep;
@@ -587,8 +664,9 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     P.prob[i] = TcProblem{p[i].bias, p[i].residual, p[i].ln_g, p[i].ln_b, p[i].y,
                           split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes)};
   }
-  int rc = fused_ln ? launch_bn<256, true>(P, group, s)
-                    : (BN == 256 ? launch_bn<256, false>(P, group, s) : launch_bn<128, false>(P, group, s));
+  int rc;
+  if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
+  else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : launch_bn<128, 0>(P, group, s);
   if (rc != SCATT_OK || !split_ln) return rc;
   for (int i = 0; i < group; ++i) {
     rc = launch_rowwise(p[i].y, M, N, ldy, p[i].residual, ldres, p[i].ln_g, p[i].ln_b, ep, p[i].y, ldy, p[i].y_planes,

@@ -99,6 +99,24 @@ def test_linear_epilogues(mode, epi, shape):
         assert float((rec - out.f32).abs().max()) <= rel * float(out.f32.abs().max()) + 1e-7
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
+@pytest.mark.parametrize("epi", ["res_ln", "ln_res_relu", "bias"])
+def test_linear_n256_large_m_single_cta_path(mode, epi):
+    """N = 256 switches from 2-CTA clusters (small batch) to one CTA per 128-row tile once the row tiles
+    alone fill the GPU (> 74 of them); both LayerNorm implementations must agree with the reference chain."""
+    M, N, K = 128 * 80 + 17, 256, 256
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    x = rnd(M, K, seed=1)
+    lin = make_linear(N, K, 2)
+    ln = torch.nn.LayerNorm(N).to(DEV)
+    res = rnd(M, N, seed=4) if kw.get("residual_mode", 0) else None
+    out = F_.linear(prec, [Act(x)], [F_.PackedLinear([lin], None, None)], F_.make_epilogue(**kw),
+                    residuals=None if res is None else [res], lns=[ln] if kw.get("layer_norm") else None)[0]
+    ref = ref_chain(x, lin, kw, res, ln)
+    assert float((out.f32.double() - ref).abs().max()) <= MODE_TOL[mode] * 4
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16x1"])
 def test_linear_grouped_matches_single(mode):
     prec = F_.get_precision(mode)
