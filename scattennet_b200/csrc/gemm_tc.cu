@@ -52,6 +52,8 @@ struct TcProblem {
 struct alignas(64) TcParams {
   CUtensorMap map_a[SCATT_MAX_GROUP];
   CUtensorMap map_b[SCATT_MAX_GROUP];
+  CUtensorMap map_y[SCATT_MAX_GROUP];   // fp32 output  [M][ldy]      (box 32 x 32, 128B swizzle)
+  CUtensorMap map_p[SCATT_MAX_GROUP];   // split planes [2][M][N]     (box 32 x 32 x 1, 64B swizzle)
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
@@ -86,6 +88,11 @@ struct EpiCtx {
   int64_t row0;            // first global row of this warp's 32-row slab
   int rows_valid;          // rows of the slab that exist (M tail)
   int lane;
+  uint32_t out_stage;      // shared address of this warp's 2 x 8 KB output boxes (TMA store sources)
+  uint8_t* out_stage_gen;  // same, generic pointer
+  const CUtensorMap* map_y;
+  const CUtensorMap* map_p;
+  int stores;              // output boxes handed to TMA so far (selects the double buffer)
 };
 
 // registers <- 32 x 32 fp32 tile of a row-major matrix (two 16-column halves), coalesced
@@ -159,9 +166,22 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// act_post (none / ReLU) -> clamp -> y (fp32) and / or split planes, via the staging tile
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// act_post (none / ReLU) -> clamp -> outputs.  Each thread writes its row of the 32 x 32 chunk into
+// this warp's swizzled output boxes (fp32: 128-byte rows; planes: 64-byte rows) and one lane hands the
+// boxes to the TMA engine (cp.async.bulk.tensor store): the SM's LSU store path (~16 B/clk measured)
+// is bypassed, rows past M and columns past N are clipped by the tensor map.
 template <int FMT>
-__device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, const EpiCtx& E, float* v, int c0) {
+__device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& Q, EpiCtx& E, float* v, int c0) {
   if (P.ep.act_post == SCATT_ACT_RELU) {  // GELU is only ever a pre-activation on this path (checked on the host)
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -171,50 +191,41 @@ __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -c), c);
   }
-  const int64_t plane = P.M * int64_t(P.N);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int j = 0; j < 16; j += 4)
-      *reinterpret_cast<float4*>(E.stage + E.lane * kEpiLd + j) =
-          make_float4(v[h * 16 + j], v[h * 16 + j + 1], v[h * 16 + j + 2], v[h * 16 + j + 3]);
-    __syncwarp();
-#ifdef SCATT_DBG_NO_Y
-    if (false) {
-#else
-    if (Q.y) {
-#endif
-      const int sub = E.lane >> 2, c4 = (E.lane & 3) * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = 8 * i + sub;
-        if (row < E.rows_valid)
-          *reinterpret_cast<float4*>(Q.y + (E.row0 + row) * P.ldy + c0 + h * 16 + c4) =
-              *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c4);
-      }
-    }
-#ifdef SCATT_DBG_NO_PLANES
-    if (false) {
-#else
-    if (Q.y_planes) {
-#endif
-      const int sub = E.lane >> 1, c8 = (E.lane & 1) * 8;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int row = 16 * i + sub;
-        if (row < E.rows_valid) {
-          const float4 a = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8);
-          const float4 b = *reinterpret_cast<const float4*>(E.stage + row * kEpiLd + c8 + 4);
-          uint4 hi, lo;
-          split8<FMT>(a, b, hi, lo);
-          uint16_t* dst = Q.y_planes + (E.row0 + row) * P.N + c0 + h * 16 + c8;
-          *reinterpret_cast<uint4*>(dst) = hi;
-          *reinterpret_cast<uint4*>(dst + plane) = lo;
-        }
-      }
-    }
+  const uint32_t buf = (E.stores & 1) * 8192u;
+  if (E.stores >= 2) {  // the box written two chunks ago must have been read out by the TMA engine
+    if (E.lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncwarp();
   }
+  uint8_t* box = E.out_stage_gen + buf;
+  const int r = E.lane;
+  if (Q.y) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(box + r * 128 + ((j ^ (r & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (Q.y_planes) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 hi, lo;
+      split8<FMT>(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                  make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+      const uint32_t off = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(box + 4096 + off) = hi;
+      *reinterpret_cast<uint4*>(box + 6144 + off) = lo;
+    }
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (E.lane == 0) {
+    const int row = int(E.row0);
+    if (Q.y) tma_store_2d(E.map_y, E.out_stage + buf, c0, row);
+    if (Q.y_planes) {
+      tma_store_3d(E.map_p, E.out_stage + buf + 4096, c0, row, 0);
+      tma_store_3d(E.map_p, E.out_stage + buf + 6144, c0, row, 1);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  ++E.stores;
 }
 
 // (acc [+ bias]) * colscale -> act_pre -> [+ residual]; returns true if v was modified
@@ -285,7 +296,7 @@ __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer
 // LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 = the row is split
 // over the two CTAs of a cluster (N == 2 BN), which exchange per-row partial statistics through DSMEM.
 template <int BN, int LN, int FMT>
-__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
+__device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, EpiCtx& E, uint32_t tmem_acc, int n0,
                                               int half, float2* stats, uint32_t xstats_addr, int row_in_tile) {
   const scatt_epilogue& ep = P.ep;
   constexpr int kMine = BN / 64;
@@ -376,7 +387,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t bar_base = base + stages * kStageBytes;
+  const uint32_t ring_bytes = max(uint32_t(stages) * kStageBytes, uint32_t(kEpiWarps) * 16384u);
+  const uint32_t bar_base = base + ring_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   const uint32_t tmem_full_bar = bar_base + 16u * stages;
@@ -407,6 +419,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_a[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
+    if (Q.y) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_y[g]) : "memory");
+    if (Q.y_planes) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_p[g]) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(BN))
@@ -500,6 +514,12 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     E.row0 = m0 + quad * 32;
     E.rows_valid = int(min(int64_t(32), max(int64_t(0), P.M - E.row0)));
     E.lane = lane;
+    // output boxes live in the (by then idle) operand ring: 2 x 8 KB per epilogue warp
+    E.out_stage = base + uint32_t(warp - 2) * 16384u;
+    E.out_stage_gen = gen(E.out_stage);
+    E.map_y = &P.map_y[g];
+    E.map_p = &P.map_p[g];
+    E.stores = 0;
     const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
     if (P.pre_init) {
       acc_pre_init<BN>(P, Q, E, my_tmem, n0, half);
@@ -512,6 +532,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     tc_fence_after();
     epilogue_rows<BN, LN, FMT>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
                                quad * 32 + lane);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // output boxes fully written before exit
+    __syncwarp();
     if (threadIdx.x == 64) trace(7);
   }
 
@@ -575,6 +597,40 @@ int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K,
   return SCATT_OK;
 }
 
+// output maps: 32-row x 32-column boxes written by one epilogue warp
+int encode_out_maps(CUtensorMap* map_y, CUtensorMap* map_p, float* y, int64_t ldy, void* planes, int64_t M, int N, int fmt) {
+  EncodeFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SCATT_ERR_CUDA;
+  }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (y) {
+    const cuuint64_t dims[2] = {cuuint64_t(N), cuuint64_t(M)};
+    const cuuint64_t strides[1] = {cuuint64_t(ldy) * 4};
+    const cuuint32_t box[2] = {32, 32};
+    CUresult r = enc(map_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(y) failed with CUresult %d", int(r));
+      return SCATT_ERR_CUDA;
+    }
+  }
+  if (planes) {
+    const cuuint64_t dims[3] = {cuuint64_t(N), cuuint64_t(M), 2};
+    const cuuint64_t strides[2] = {cuuint64_t(N) * 2, cuuint64_t(M) * cuuint64_t(N) * 2};
+    const cuuint32_t box[3] = {32, 32, 1};
+    CUresult r = enc(map_p, fmt == SCATT_PLANE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                     planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(planes out) failed with CUresult %d", int(r));
+      return SCATT_ERR_CUDA;
+    }
+  }
+  return SCATT_OK;
+}
+
 template <int BN, int LN, int FMT>
 int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
@@ -584,8 +640,9 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   if (stages > 8) stages = 8;
   if (stages < 1) stages = 1;
   P.stages = stages;
-  const size_t smem = size_t(stages) * kStageBytes + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 +
-                      kEpiWarps * kEpiWarpBytes;
+  size_t ring = size_t(stages) * kStageBytes;
+  if (ring < size_t(kEpiWarps) * 16384) ring = size_t(kEpiWarps) * 16384;  // the epilogue's output boxes reuse the ring
+  const size_t smem = ring + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 + kEpiWarps * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
   if constexpr (LN == 2) {
@@ -663,6 +720,8 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     if (rc != SCATT_OK) return rc;
     P.prob[i] = TcProblem{p[i].bias, p[i].residual, p[i].ln_g, p[i].ln_b, p[i].y,
                           split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes)};
+    rc = encode_out_maps(&P.map_y[i], &P.map_p[i], P.prob[i].y, ldy, P.prob[i].y_planes, M, N, fmt);
+    if (rc != SCATT_OK) return rc;
   }
   int rc;
   if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
