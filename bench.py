@@ -183,7 +183,7 @@ def run_ours(args):
     _lib.check(_lib.load().scatt_device_check(), "scatt_device_check")
 
     cfg = model_config(CFG_NAME)
-    model = MSCAEncoder(cfg, VOCAB, precision=args.precision, use_graph=True).eval()
+    model = MSCAEncoder(cfg, VOCAB, precision=args.precision, use_graph=True, micro_batches=args.micro_batches).eval()
     synth.load_synth_(model, seed=0)
     model = model.to(dev)
     kp_host, mask_host = synth.synth_batch(args.batch, T, seed=1 + rank)
@@ -336,6 +336,7 @@ def main():
     ap.add_argument("--precision", default="fp16x3")
     ap.add_argument("--batch", type=int, default=BATCH, help="sequences per GPU (BASELINE config: 8)")
     ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--micro-batches", type=int, default=1, help="independent sub-batches run as parallel CUDA-graph branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -108,12 +108,7 @@ int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int 
   linear_simt_kernel<<<grid, 256, 0, s>>>(grp, M, N, K, ldx, ldres, ldy, ep, fmt, fuse_tail);
   int rc = after_launch("linear_simt_kernel");
   if (rc != SCATT_OK || fuse_tail) return rc;
-  for (int i = 0; i < group; ++i) {  // LayerNorm tail, in place on y
-    rc = launch_rowwise(p[i].y, M, N, ldy, p[i].residual, ldres, p[i].ln_g, p[i].ln_b, ep, p[i].y, ldy, p[i].y_planes,
-                        fmt, s);
-    if (rc != SCATT_OK) return rc;
-  }
-  return SCATT_OK;
+  return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);
 }
 
 }  // namespace scatt

@@ -727,12 +727,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : launch_bn<128, 0>(P, group, s);
   if (rc != SCATT_OK || !split_ln) return rc;
-  for (int i = 0; i < group; ++i) {
-    rc = launch_rowwise(p[i].y, M, N, ldy, p[i].residual, ldres, p[i].ln_g, p[i].ln_b, ep, p[i].y, ldy, p[i].y_planes,
-                        fmt, s);
-    if (rc != SCATT_OK) return rc;
-  }
-  return SCATT_OK;
+  return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);
 }
 
 }  // namespace scatt

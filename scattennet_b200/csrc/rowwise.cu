@@ -40,11 +40,23 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---------------------------------------------------------------- row-wise tail
-__global__ void __launch_bounds__(256) rowwise_kernel(const float* __restrict__ z, int64_t M, int N, int64_t ldz,
-                                                      const float* __restrict__ residual, int64_t ldres,
-                                                      const float* __restrict__ g, const float* __restrict__ b,
-                                                      scatt_epilogue ep, float* __restrict__ y, int64_t ldy,
-                                                      uint16_t* __restrict__ planes, int fmt) {
+struct RowwiseGroup {  // one entry per problem of a grouped launch (blockIdx.y)
+  const float* z[SCATT_MAX_GROUP];
+  const float* residual[SCATT_MAX_GROUP];
+  const float* g[SCATT_MAX_GROUP];
+  const float* b[SCATT_MAX_GROUP];
+  float* y[SCATT_MAX_GROUP];
+  uint16_t* planes[SCATT_MAX_GROUP];
+};
+
+__global__ void __launch_bounds__(256) rowwise_kernel(RowwiseGroup grp, int64_t M, int N, int64_t ldz, int64_t ldres,
+                                                      scatt_epilogue ep, int64_t ldy, int fmt) {
+  const float* __restrict__ z = grp.z[blockIdx.y];
+  const float* __restrict__ residual = grp.residual[blockIdx.y];
+  const float* __restrict__ g = grp.g[blockIdx.y];
+  const float* __restrict__ b = grp.b[blockIdx.y];
+  float* __restrict__ y = grp.y[blockIdx.y];
+  uint16_t* __restrict__ planes = grp.planes[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int nvec_row = N >> 2;
@@ -237,8 +249,27 @@ int launch_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* r
   SCATT_REQUIRE(!ep.layer_norm || (g && b), "rowwise: LayerNorm needs gamma and beta");
   SCATT_REQUIRE(ep.residual_mode != SCATT_RES_AFTER_LN || (residual && ldres % 4 == 0), "rowwise: residual missing");
   if (M == 0) return SCATT_OK;
-  rowwise_kernel<<<grid_for(M, 8), 256, 0, s>>>(z, M, N, ldz, residual, ldres, g, b, ep, y, ldy,
-                                                reinterpret_cast<uint16_t*>(planes), fmt);
+  RowwiseGroup grp{};
+  grp.z[0] = z, grp.residual[0] = residual, grp.g[0] = g, grp.b[0] = b, grp.y[0] = y;
+  grp.planes[0] = reinterpret_cast<uint16_t*>(planes);
+  rowwise_kernel<<<dim3(grid_for(M, 8), 1), 256, 0, s>>>(grp, M, N, ldz, ldres, ep, ldy, fmt);
+  return after_launch("rowwise_kernel");
+}
+
+// LayerNorm tail of a grouped linear launch, in place on y: one launch for all problems.
+int launch_rowwise_linear_tail(const scatt_linear_problem* p, int group, int64_t M, int N, int64_t ldres, int64_t ldy,
+                               const scatt_epilogue& ep, int fmt, cudaStream_t s) {
+  SCATT_REQUIRE(N % 4 == 0 && N <= 1024 && N > 0, "rowwise: N=%d must be a multiple of 4 and <= 1024", N);
+  SCATT_REQUIRE(ldy % 4 == 0 && ldres % 4 == 0, "rowwise: row strides must be multiples of 4");
+  if (M == 0) return SCATT_OK;
+  RowwiseGroup grp{};
+  for (int i = 0; i < group; ++i) {
+    SCATT_REQUIRE(p[i].y && (!ep.layer_norm || (p[i].ln_g && p[i].ln_b)), "rowwise: LayerNorm needs y, gamma and beta");
+    SCATT_REQUIRE(ep.residual_mode != SCATT_RES_AFTER_LN || p[i].residual, "rowwise: residual missing");
+    grp.z[i] = p[i].y, grp.residual[i] = p[i].residual, grp.g[i] = p[i].ln_g, grp.b[i] = p[i].ln_b, grp.y[i] = p[i].y;
+    grp.planes[i] = reinterpret_cast<uint16_t*>(p[i].y_planes);
+  }
+  rowwise_kernel<<<dim3(grid_for(M, 8, 148 * 8 / group), group), 256, 0, s>>>(grp, M, N, ldy, ldres, ep, ldy, fmt);
   return after_launch("rowwise_kernel");
 }
 

@@ -40,7 +40,7 @@ class LinearHeads(nn.Module):
 
 
 class MSCAEncoder(nn.Module):
-    def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False):
+    def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False, micro_batches: int = 1):
         super().__init__()
         self.cfg = dict(cfg)
         self.body_encoder = KeypointModule(cfg["body_idx"], num_frame=cfg["num_frame"], cfg=cfg)
@@ -50,6 +50,9 @@ class MSCAEncoder(nn.Module):
         self.recognition_head = LinearHeads(cfg, vocab_size)
         self.precision = precision
         self.use_graph = use_graph
+        # > 1: inside the captured graph the batch is cut into this many independent sub-batches that
+        # run as parallel graph branches (sequences are independent); their latency-bound kernels overlap
+        self.micro_batches = micro_batches
         self._graphs: Dict = {}
         self._idx_cache: Dict = {}
 
@@ -126,7 +129,7 @@ class MSCAEncoder(nn.Module):
             graph = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(graph):
-                static_out = self._run(static_kp, static_mask, with_heads)
+                static_out = self._run_branches(static_kp, static_mask, with_heads)
             ent = (graph, static_kp, static_mask, static_out, L.launch_count() - n0)
             self._graphs[key] = ent
         graph, static_kp, static_mask, static_out, _ = ent
@@ -134,6 +137,32 @@ class MSCAEncoder(nn.Module):
         static_mask.copy_(F_.key_mask_u8(mask), non_blocking=True)
         graph.replay()
         return static_out
+
+    def _run_branches(self, kp, km, with_heads):
+        """One `_run` per sub-batch on forked streams (captured as parallel graph branches), joined and
+        concatenated on the capturing stream."""
+        b = kp.shape[0]
+        n = min(self.micro_batches, b)
+        if n <= 1:
+            return self._run(kp, km, with_heads)
+        bounds = [(i * b) // n for i in range(n + 1)]
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        parts, joins = [], []
+        for i in range(n):
+            st = main if i == 0 else torch.cuda.Stream()
+            if i:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                parts.append(self._run(kp[bounds[i]:bounds[i + 1]], km[bounds[i]:bounds[i + 1]], with_heads))
+                if i:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    joins.append(ev)
+        for ev in joins:
+            main.wait_event(ev)
+        return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
 
     def graph_launches(self, keypoints_shape, device, with_heads=True) -> int:
         """Kernels inside the captured graph for this shape (0 if not captured)."""
