@@ -282,6 +282,9 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     return outs
 
 
+ATTN_TC_MAX_T = 256  # longest key sequence the tcgen05 attention kernel takes (longer ones run on the fp32 kernel)
+
+
 def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: int, kind: int,
                      key_mask: Optional[torch.Tensor] = None, additive: Optional[torch.Tensor] = None) -> List[Act]:
     """Grouped flash-style attention; ``qs/ks/vs`` are fp32 2-D views (row stride = leading dim)."""
@@ -299,7 +302,7 @@ def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: i
         p.out, p.out_planes = _ptr(o), _ptr(op)
         outs.append(Act(o, op))
     flops = (2.0 * B * Tq * (Tq + 1) * D if kind == L.ATTN_CAUSAL else 4.0 * B * Tq * Tk * D) * G
-    tc = prec.uses_planes and Tk <= 256 and additive is None
+    tc = prec.uses_planes and Tk <= ATTN_TC_MAX_T and additive is None
     with _timed("stream_attention_tc_kernel" if tc else "stream_attention_kernel", flops, G * 4.0 * B * max(Tq, Tk) * D * 4):
         L.check(L.load().scatt_attention(probs, G, B, Tq, Tk, H, D // H, qs[0].stride(0), ks[0].stride(0), vs[0].stride(0),
                                          kind, prec.engine, prec.plane_fmt, max(prec.terms, 1), _stream()), "scatt_attention")

@@ -1,0 +1,114 @@
+"""Batch sweep (BASELINE config 4, one GPU) and isolated kernel sweep (config 5) - prints markdown tables.
+
+    python tools/sweep.py batch   [--precision fp16x3]     # frames/s vs batch at T=200
+    python tools/sweep.py kernels                          # attention / linear launches vs roofline
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from scattennet_b200 import MSCAEncoder, synth, functional as F_, _lib as L
+from scattennet_b200.config import model_config
+from scattennet_b200.functional import Act
+from oracle.scatt_oracle import encoder_flops_per_frame  # flop model only (no oracle arithmetic here)
+
+PEAK_TF, PEAK_GBS = 1658.0, 6549.4
+p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(p):
+    d = json.load(open(p)); PEAK_TF, PEAK_GBS = d["bf16_tflops"], d["hbm_gbs"]
+dev = "cuda"
+flush = None
+
+def timed(fn, reps):
+    global flush
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3): fn()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for e0, e1 in ev:
+        flush.zero_(); e0.record(); fn(); e1.record()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    return ts[len(ts) // 2]
+
+def batch_sweep(args):
+    cfg = model_config(args.config, **({"max_position_embeddings": 512} if args.T > 256 else {}))
+    print(f"| batch | T | precision | ms/step | frames/s | model TFLOP/s (algorithmic) | % of bf16 peak ({PEAK_TF:.0f}) |")
+    print("|---|---|---|---|---|---|---|")
+    for prec in args.precision.split(","):
+        model = MSCAEncoder(cfg, 1120, precision=prec, use_graph=True).eval()
+        synth.load_synth_(model, 0)
+        model = model.to(dev)
+        for b in [int(x) for x in args.batches.split(",")]:
+            kp, mask = synth.synth_batch(b, args.T, seed=1)
+            kp, mask = kp.to(dev), mask.to(dev)
+            with torch.no_grad():
+                ms = timed(lambda: model(kp, mask), 10 if b >= 256 else 30)
+            fl = encoder_flops_per_frame(cfg, args.T, 1120) * b * args.T
+            print(f"| {b} | {args.T} | {prec} | {ms:.3f} | {b * args.T / ms * 1e3:,.0f} | {fl / ms / 1e9:.1f} | {100 * fl / ms / 1e9 / PEAK_TF:.2f} |", flush=True)
+            model._graphs.clear(); torch.cuda.empty_cache()
+
+def graph_time(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps): fn()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3  # us per launch (back to back, L2-warm)
+
+def kernel_sweep(args):
+    H, D = 16, 256
+    gen = torch.Generator().manual_seed(0)
+    print(f"### stream attention, B*3 streams grouped, H=16, hd=16 (us per grouped launch, back-to-back in a CUDA graph)\n")
+    print("| T | B | kind | engine | us | TFLOP/s (4BT^2D, causal half) | % bf16 peak | exp/s (1e12) |")
+    print("|---|---|---|---|---|---|---|---|")
+    for T in (64, 128, 192, 200, 256, 320, 384, 448, 512):
+        B = max(1, 12800 // T)
+        qkv = [torch.randn(B * T, 3 * D, generator=gen).to(dev) for _ in range(3)]
+        km = torch.ones(B, T, dtype=torch.uint8, device=dev)
+        for kind, kn in ((0, "self"), (1, "causal"), (2, "cross")):
+            for mode in ("fp16x3", "fp16x1", "fp32"):
+                prec = F_.get_precision(mode)
+                fn = lambda: F_.stream_attention(prec, [t[:, :D] for t in qkv], [t[:, D:2*D] for t in qkv], [t[:, 2*D:] for t in qkv], B, T, T, H, kind, key_mask=km)
+                us = graph_time(fn)
+                fl = 3 * (2.0 * B * T * (T + 1) * D if kind == 1 else 4.0 * B * T * T * D)
+                ex = 3 * B * H * (T * (T + 1) / 2 if kind == 1 else T * T)
+                eng = "tcgen05" if (prec.uses_planes and T <= F_.ATTN_TC_MAX_T) else "cuda-core fp32"
+                print(f"| {T} | {B} | {kn} | {mode} {eng} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {ex / us / 1e6:.2f} |", flush=True)
+    print(f"\n### linear (tcgen05), 3 streams grouped (us per launch, back-to-back in a CUDA graph)\n")
+    print("| M | N | K | epilogue | mode | us | TFLOP/s (2MNK) | % bf16 peak | GB/s (operands+outputs) |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    def lin(n, k):
+        l = torch.nn.Linear(k, n); synth.load_synth_(l, 1); return l.to(dev)
+    for M in (1600, 12800, 51200):
+        for (N, K, name, kw, of32, opl) in ((768, 256, "qkv (fp32 out)", dict(scale_cols=256, scale=0.25), True, False),
+                                            (768, 256, "fc1+gelu (planes out)", dict(act_pre=L.ACT_GELU), False, True),
+                                            (256, 256, "out_proj+res+LN", dict(residual_mode=L.RES_BEFORE_LN, layer_norm=True), True, True),
+                                            (256, 768, "fc2+res+LN", dict(residual_mode=L.RES_BEFORE_LN, layer_norm=True), True, True)):
+            for mode in ("fp16x3", "fp16x1"):
+                prec = F_.get_precision(mode)
+                xs = [Act(torch.randn(M, K, generator=gen).to(dev)).with_planes(prec) for _ in range(3)]
+                packs = [F_.PackedLinear([lin(N, K)], None, None) for _ in range(3)]
+                res = [torch.randn(M, N, generator=gen).to(dev) for _ in range(3)]
+                lns = [torch.nn.LayerNorm(N).to(dev) for _ in range(3)]
+                ep = F_.make_epilogue(**kw)
+                fn = lambda: F_.linear(prec, xs, packs, ep, residuals=res if kw.get("residual_mode") else None, lns=lns if kw.get("layer_norm") else None, out_f32=of32, out_planes=opl)
+                us = graph_time(fn, reps=10)
+                fl = 3 * 2.0 * M * N * K
+                planes = 2 if prec.terms >= 2 else 1
+                by = 3 * ((M * K + N * K) * 2 * planes + (M * N * 4 if kw.get("residual_mode") else 0) + M * N * (4 * of32 + 4 * opl))
+                print(f"| {M} | {N} | {K} | {name} | {mode} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {by / us / 1e3:.0f} |", flush=True)
+                del xs, packs, res
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["batch", "kernels"])
+    ap.add_argument("--precision", default="fp16x3,fp16x1")
+    ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024")
+    ap.add_argument("--T", type=int, default=200)
+    ap.add_argument("--config", default="phoenix-2014t")
+    a = ap.parse_args()
+    (batch_sweep if a.what == "batch" else kernel_sweep)(a)
