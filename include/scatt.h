@@ -188,6 +188,30 @@ typedef struct scatt_attention_problem {
 int scatt_attention(const scatt_attention_problem* problems_host, int group, int B, int Tq, int Tk, int H, int hd,
                     int64_t ldq, int64_t ldk, int64_t ldv, int kind, int engine, int plane_fmt, int terms, void* stream);
 
+/* Same attention, operands taken as the split planes a projection GEMM wrote
+ * (`scatt_linear` with y_planes): planes[2][rows][ld], head h at columns
+ * [col + hd*h, col + hd*(h+1)).  Tiles are fetched by TMA straight into tensor-core
+ * layout - nothing is converted or transposed - so this is the fast path used by
+ * SeparativeCoordinateAttention / Encoder.  Requires hd = 16 and Tk <= 224 (use
+ * scatt_attention otherwise); q must already carry the head_dim^-0.5 scaling. */
+typedef struct scatt_attn_operand {
+  const void* planes;
+  int64_t rows; /* rows of the plane matrix (>= B*T) */
+  int64_t ld;   /* row stride in elements, multiple of 8 */
+  int32_t col;  /* first column of head 0, multiple of 8 */
+  int32_t reserved;
+} scatt_attn_operand;
+
+typedef struct scatt_attention_planes_problem {
+  scatt_attn_operand q, k, v;
+  const uint8_t* key_mask; /* [B,Tk] 1 = valid, or NULL */
+  float* out;              /* [B*Tq, H*hd] fp32 or NULL */
+  void* out_planes;        /* [2][B*Tq][H*hd] or NULL */
+} scatt_attention_planes_problem;
+
+int scatt_attention_planes(const scatt_attention_planes_problem* problems_host, int group, int B, int Tq, int Tk, int H,
+                           int hd, int kind, int plane_fmt, int terms, void* stream);
+
 /* ------------------------------------------------------------------ K5: fusion attention */
 
 /* out[b] = softmax(q[b] k[b]^T) v[b], single head of width D, no mask, no

@@ -28,7 +28,7 @@ SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
-    "scatt_attention", "scatt_fusion_attention", "scatt_pool_pairs",
+    "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
 )
 
 
@@ -55,6 +55,15 @@ class AttentionProblem(C.Structure):
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("key_mask", C.c_void_p), ("additive", C.c_void_p),
         ("out", C.c_void_p), ("out_planes", C.c_void_p),
     ]
+
+
+class AttnOperand(C.Structure):
+    _fields_ = [("planes", C.c_void_p), ("rows", C.c_int64), ("ld", C.c_int64), ("col", C.c_int32), ("reserved", C.c_int32)]
+
+
+class AttentionPlanesProblem(C.Structure):
+    _fields_ = [("q", AttnOperand), ("k", AttnOperand), ("v", AttnOperand), ("key_mask", C.c_void_p), ("out", C.c_void_p),
+                ("out_planes", C.c_void_p)]
 
 
 class FrontendStream(C.Structure):
@@ -86,6 +95,8 @@ def _declare(lib):
     lib.scatt_rowwise.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, C.POINTER(Epilogue), vp, i64, vp, i32, vp]
     lib.scatt_attention.argtypes = [C.POINTER(AttentionProblem), i32, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32, i32,
                                     i32, vp]
+    lib.scatt_attention_planes.argtypes = [C.POINTER(AttentionPlanesProblem), i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.scatt_attention_planes.restype = i32
     lib.scatt_fusion_attention.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.scatt_pool_pairs.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
     for name in ("scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",

@@ -76,6 +76,27 @@ def attention_core(prec: Precision, mods: Sequence[BaseAttention], xq: List[Act]
     views (the merge ladder projects K/V of all layers in one GEMM)."""
     d, h = mods[0].d_model, mods[0].num_heads
     scale = mods[0].scaling
+    if (prec.uses_planes and additive is None and d // h == 16 and Tk <= F_.ATTN_PLANES_MAX_T
+            and (kv_views is None or isinstance(kv_views[0][0], tuple))):
+        # fast path: the projection GEMMs write split planes, the attention kernel TMA-loads them as they are
+        ep_q = F_.make_epilogue(scale_cols=d, scale=scale)
+        if xkv is None and kv_views is None:
+            packs = [F_.pack_of(m, "qkv", [m.q_proj, m.k_proj, m.v_proj]) for m in mods]
+            qkv = F_.linear(prec, xq, packs, ep_q, out_f32=False)
+            qs = [(t.planes, 0) for t in qkv]
+            ks = [(t.planes, d) for t in qkv]
+            vs = [(t.planes, 2 * d) for t in qkv]
+        else:
+            packs = [F_.pack_of(m, "q", [m.q_proj]) for m in mods]
+            q = F_.linear(prec, xq, packs, ep_q, out_f32=False)
+            qs = [(t.planes, 0) for t in q]
+            if kv_views is None:
+                kv = cross_kv(prec, mods, xkv, planes=True)
+                ks = [(t.planes, 0) for t in kv]
+                vs = [(t.planes, d) for t in kv]
+            else:
+                ks, vs = [kv[0] for kv in kv_views], [kv[1] for kv in kv_views]
+        return F_.stream_attention_planes(prec, qs, ks, vs, B, Tq, Tk, h, kind, key_mask)
     if xkv is None and kv_views is None:  # self / causal: one N = 3D GEMM
         packs = [F_.pack_of(m, "qkv", [m.q_proj, m.k_proj, m.v_proj]) for m in mods]
         qkv = F_.linear(prec, xq, packs, F_.make_epilogue(scale_cols=d, scale=scale), out_planes=False)
@@ -95,11 +116,11 @@ def attention_core(prec: Precision, mods: Sequence[BaseAttention], xq: List[Act]
     return F_.stream_attention(prec, qs, ks, vs, B, Tq, Tk, h, kind, key_mask, additive)
 
 
-def cross_kv(prec: Precision, mods: Sequence[BaseAttention], xkv: List[Act]) -> List[Act]:
+def cross_kv(prec: Precision, mods: Sequence[BaseAttention], xkv: List[Act], planes: bool = False) -> List[Act]:
     """``[k_proj(x) | v_proj(x / 2)]`` as one N = 2D GEMM; the halving is folded
     into ``W_v`` (exact: a power of two), the bias is not halved (``:103``)."""
     packs = [F_.pack_of(m, "kv", [m.k_proj, m.v_proj], scales=[1.0, 0.5]) for m in mods]
-    return F_.linear(prec, xkv, packs, F_.make_epilogue(), out_planes=False)
+    return F_.linear(prec, xkv, packs, F_.make_epilogue(), out_f32=not planes, out_planes=planes)
 
 
 class SelfAttention(BaseAttention):

@@ -107,6 +107,14 @@ int scatt_attention(const scatt_attention_problem* problems_host, int group, int
   return launch_attention(problems_host, group, B, Tq, Tk, H, hd, ldq, ldk, ldv, kind, plane_fmt, as_stream(stream));
 }
 
+int scatt_attention_planes(const scatt_attention_planes_problem* problems_host, int group, int B, int Tq, int Tk, int H,
+                           int hd, int kind, int plane_fmt, int terms, void* stream) {
+  SCATT_REQUIRE(problems_host && fmt_ok(plane_fmt), "attention_planes: null pointer or bad plane format");
+  SCATT_REQUIRE(kind >= SCATT_ATTN_SELF && kind <= SCATT_ATTN_CROSS, "attention_planes: bad kind %d", kind);
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "attention_planes: group 1..%d", SCATT_MAX_GROUP);
+  return launch_attention_planes(problems_host, group, B, Tq, Tk, H, hd, kind, plane_fmt, terms, as_stream(stream));
+}
+
 int scatt_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* out_planes,
                            int plane_fmt, void* stream) {
   SCATT_REQUIRE(q && k && v && (out || out_planes) && fmt_ok(plane_fmt), "fusion_attention: bad argument");

@@ -1,0 +1,349 @@
+// K3 stream attention, TMA-fed variant: q / k / v arrive as the 16-bit hi/lo split
+// planes the projection GEMMs wrote ([2][rows][ld], head h at columns col + 16 h),
+// so no operand is converted or re-laid-out by this kernel:
+//
+//   TMA (32-byte-swizzle boxes of 16 columns)  ->  Q [128 x 16], K [keys x 16], V [keys x 16] tiles
+//   S = Q K^T   one tcgen05.mma per product term (M=128, N=keys<=224, K=16), K-major operands
+//   softmax     thread per query row out of TMEM (exact two-pass, reference mask semantics)
+//   P           written back into the S columns of TMEM (packed 16-bit hi | lo)
+//   O = P V     tcgen05.mma, A from TMEM, B = V read MN-major (keys x 16 rows as stored: no transpose)
+//
+// One CTA = one (batch, head, 128-query tile); 256 TMEM columns (S/P 224 + O 16) -> two CTAs per SM.
+// Key sequences longer than 224 and dense additive masks are served by the other attention kernels.
+#include <cfloat>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace scatt {
+
+namespace {
+
+using namespace tc;
+
+constexpr int HD = 16;
+constexpr int QT = 128;
+constexpr int KMAX = 224;  // keys per CTA: S/P columns [0, 224), O columns [224, 240)
+constexpr int kThreadsFa = 160;
+
+struct FaProblem {
+  const uint8_t* key_mask;
+  float* out;
+  uint16_t* out_planes;
+  int32_t q_col, k_col, v_col;
+};
+
+struct alignas(64) FaParams {
+  CUtensorMap map_q[SCATT_MAX_GROUP];
+  CUtensorMap map_k[SCATT_MAX_GROUP];
+  CUtensorMap map_v[SCATT_MAX_GROUP];
+  FaProblem p[SCATT_MAX_GROUP];
+  int32_t B, Tq, Tk, H, kind, terms, kbox;
+};
+
+// shared memory map (relative to a 1024-aligned base); every tile row is 32 bytes (16 halves)
+constexpr uint32_t kQh = 0, kQl = kQh + QT * 32;
+constexpr uint32_t kKh = kQl + QT * 32, kKl = kKh + 256 * 32;
+constexpr uint32_t kVh = kKl + 256 * 32, kVl = kVh + 256 * 32;
+constexpr uint32_t kCls = kVl + 256 * 32;           // float[256] key class: 0 valid / -FLT_MAX padded / -inf absent
+constexpr uint32_t kBar = kCls + 256 * 4;           // 4 mbarriers + tmem pointer
+constexpr uint32_t kFaSmem = kBar + 64 + 1024;
+
+// 32-byte-swizzled tile: 8-row groups of 256 bytes.  K-major use (Q, K): rows = M/N index, 16 K-elements per row.
+// MN-major use (V as B operand): rows = K index (keys), 16 N-elements per row.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+  d |= uint64_t(1) << 16;            // leading byte offset: unused (one swizzle atom wide)
+  d |= uint64_t(256 >> 4) << 32;     // stride byte offset: next 8-row group
+  d |= uint64_t(1) << 46;            // descriptor version (sm_100)
+  d |= uint64_t(6) << 61;            // SWIZZLE_32B
+  return d;
+}
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int FMT>
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (FMT == SCATT_PLANE_F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 back = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(const __grid_constant__ FaParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar_qk = base + kBar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
+  const uint32_t tmem_ptr_addr = bar_qk + 40;
+  float* cls = reinterpret_cast<float*>(sm + kCls);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.z / P.B, b = blockIdx.z % P.B, h = blockIdx.y;
+  const FaProblem& A = P.p[g];
+  const int m0 = blockIdx.x * QT;
+  const int Tq = P.Tq, Tk = P.Tk, D = P.H * HD;
+  const bool causal = P.kind == SCATT_ATTN_CAUSAL;
+  const int kbox = P.kbox;                               // keys loaded and multiplied (multiple of 16, >= Tk)
+  const int nk = causal ? min(Tk, m0 + QT) : Tk;         // keys this tile may see
+  const bool lo_q = P.terms >= 2, lo_k = P.terms >= 3;   // S: q_hi k_lo (3), q_lo k_hi (2), q_hi k_hi
+  constexpr uint32_t kTmemCols = 256, kOCol = 224;
+
+  if (threadIdx.x == 128) {
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_q[g]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_k[g]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_v[g]) : "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    for (int j = threadIdx.x; j < 256; j += 128) {
+      float c = -INFINITY;  // absent key: probability exactly 0
+      if (j < nk) c = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
+      cls[j] = c;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kBar + 40);
+  const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
+  const uint32_t idesc_base = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(QT >> 4) << 24);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- operands: three (x2 planes) TMA boxes
+      const int qrow = b * Tq + m0, krow = b * Tk;
+      const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
+      mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + kbox * 32 * nkpl));
+      tma_load_3d(base + kQh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
+      if (lo_q) tma_load_3d(base + kQl, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
+      tma_load_3d(base + kKh, &P.map_k[g], bar_qk, A.k_col + h * HD, krow, 0);
+      if (lo_k) tma_load_3d(base + kKl, &P.map_k[g], bar_qk, A.k_col + h * HD, krow, 1);
+      mbar_expect_tx(bar_v, uint32_t(kbox * 32 * nkpl));
+      tma_load_3d(base + kVh, &P.map_v[g], bar_v, A.v_col + h * HD, krow, 0);
+      if (lo_k) tma_load_3d(base + kVl, &P.map_v[g], bar_v, A.v_col + h * HD, krow, 1);
+      // ---- S = Q K^T
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      const uint32_t idesc_s = idesc_base | (uint32_t(kbox >> 3) << 17);
+      const uint64_t qh = umma_desc_sw32(base + kQh), ql = umma_desc_sw32(base + kQl);
+      const uint64_t kh = umma_desc_sw32(base + kKh), kl = umma_desc_sw32(base + kKl);
+      uint32_t acc = 0;
+      if (lo_k) {
+        tc_mma_f16(tmem_s, qh, kl, idesc_s, acc);
+        acc = 1;
+      }
+      if (lo_q) {
+        tc_mma_f16(tmem_s, ql, kh, idesc_s, acc);
+        acc = 1;
+      }
+      tc_mma_f16(tmem_s, qh, kh, idesc_s, acc);
+      tc_commit(bar_s);
+      // ---- O = P V (A = P from TMEM, B = V MN-major)
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      const uint32_t idesc_o = idesc_base | (1u << 16) | (uint32_t(HD >> 3) << 17);  // bit 16: B is MN-major
+      acc = 0;
+      for (int ks = 0; ks < kbox / 16; ++ks) {
+        const uint32_t p_hi = tmem_s + 32 * (ks >> 1) + 8 * (ks & 1), p_lo = p_hi + 16;
+        const uint64_t adv = uint64_t(ks * 512 >> 4);  // 16 keys x 32 bytes
+        const uint64_t vh = umma_desc_sw32(base + kVh) + adv, vl = umma_desc_sw32(base + kVl) + adv;
+        if (lo_k) {
+          tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc);
+          acc = 1;
+        }
+        if (lo_q) {
+          tc_mma_ts(tmem_o, p_lo, vh, idesc_o, acc);
+          acc = 1;
+        }
+        tc_mma_ts(tmem_o, p_hi, vh, idesc_o, acc);
+        acc = 1;
+      }
+      tc_commit(bar_o);
+    }
+  } else {
+    // ---------------- softmax: thread = query row (TMEM lane = warp * 32 + lane)
+    const int r = warp * 32 + lane;
+    const int i = m0 + r;
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const int nchunk = (kbox + 31) >> 5;
+    const int jmax = causal ? i : 0x7fffffff;
+    float v[32];
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < nchunk; ++c) {
+      tc_ld32(tmem_s + lane_addr + c * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = c * 32 + j;
+        const float kc = cls[key];
+        float s = kc == 0.f ? v[j] : kc;
+        if (key > jmax) s = -INFINITY;
+        mx = fmaxf(mx, s);
+      }
+    }
+    const float kLog2e = 1.4426950408889634f;
+    float l = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < nchunk; ++c) {
+      tc_ld32(tmem_s + lane_addr + c * 32, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int key = c * 32 + j;
+        const float kc = cls[key];
+        float s = kc == 0.f ? v[j] : kc;
+        if (key > jmax) s = -INFINITY;
+        const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
+        l += p;
+        v[j] = p;
+      }
+      float w[32];
+      uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
+      tc_st32(tmem_s + lane_addr + c * 32, w);
+    }
+    tc_fence_before();
+    mbar_arrive(bar_p);
+
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    float o[16];
+    tc_ld16(tmem_o + lane_addr, o);
+    const float inv = 1.0f / l;
+    if (i < Tq) {
+      const int64_t row = int64_t(b) * Tq + i;
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 ov = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+        if (A.out) *reinterpret_cast<float4*>(A.out + row * D + h * HD + c) = ov;
+        if (A.out_planes) store_planes4(A.out_planes, int64_t(P.B) * Tq * D, row * D + h * HD + c, ov, FMT);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fa() {
+  static EncodeFn fn = nullptr;
+  static std::atomic<bool> done{false};
+  if (!done.load()) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+    done.store(true);
+  }
+  return fn;
+}
+
+// planes [2][rows][ld] -> boxes of 16 columns x box_rows rows x 1 plane, 32-byte swizzle
+int encode_operand_map(CUtensorMap* map, const scatt_attn_operand& op, int box_rows, int fmt) {
+  EncodeFn enc = get_encode_fa();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return SCATT_ERR_CUDA;
+  }
+  const cuuint64_t dims[3] = {cuuint64_t(op.ld), cuuint64_t(op.rows), 2};
+  const cuuint64_t strides[2] = {cuuint64_t(op.ld) * 2, cuuint64_t(op.rows) * cuuint64_t(op.ld) * 2};
+  const cuuint32_t box[3] = {HD, cuuint32_t(box_rows), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, fmt == SCATT_PLANE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(op.planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(attention operand) failed with CUresult %d (rows=%lld ld=%lld box_rows=%d)", int(r),
+              (long long)op.rows, (long long)op.ld, box_rows);
+    return SCATT_ERR_CUDA;
+  }
+  return SCATT_OK;
+}
+
+}  // namespace
+
+bool attention_planes_supported(int Tq, int Tk, int hd) { return hd == HD && Tk >= 1 && Tk <= KMAX; }
+
+int launch_attention_planes(const scatt_attention_planes_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int kind,
+                            int fmt, int terms, cudaStream_t s) {
+  SCATT_REQUIRE(attention_planes_supported(Tq, Tk, hd), "attention(planes): needs head_dim 16 and 1 <= Tk <= %d", KMAX);
+  SCATT_REQUIRE(terms >= 1 && terms <= 3, "attention(planes): terms must be 1..3");
+  SCATT_REQUIRE(kind != SCATT_ATTN_CAUSAL || Tq == Tk, "attention(planes): causal needs Tq == Tk");
+  SCATT_REQUIRE(int64_t(B) * group <= 65535 && H <= 65535, "attention(planes): grid too large");
+  if (B == 0 || Tq == 0) return SCATT_OK;
+  FaParams P{};
+  P.B = B, P.Tq = Tq, P.Tk = Tk, P.H = H, P.kind = kind, P.terms = terms;
+  P.kbox = (Tk + 15) & ~15;
+  for (int i = 0; i < group; ++i) {
+    const scatt_attention_planes_problem& a = p[i];
+    SCATT_REQUIRE(a.q.planes && a.k.planes && a.v.planes && (a.out || a.out_planes), "attention(planes): null operand");
+    SCATT_REQUIRE(a.q.ld % 8 == 0 && a.k.ld % 8 == 0 && a.v.ld % 8 == 0 && a.q.col % 8 == 0 && a.k.col % 8 == 0 && a.v.col % 8 == 0,
+                  "attention(planes): leading dimensions and column offsets must be multiples of 8");
+    SCATT_REQUIRE(a.q.rows >= int64_t(B) * Tq && a.k.rows >= int64_t(B) * Tk && a.v.rows >= int64_t(B) * Tk,
+                  "attention(planes): operand has fewer rows than B*T");
+    int rc = encode_operand_map(&P.map_q[i], a.q, QT, fmt);
+    if (rc == SCATT_OK) rc = encode_operand_map(&P.map_k[i], a.k, P.kbox, fmt);
+    if (rc == SCATT_OK) rc = encode_operand_map(&P.map_v[i], a.v, P.kbox, fmt);
+    if (rc != SCATT_OK) return rc;
+    P.p[i] = FaProblem{a.key_mask, a.out, reinterpret_cast<uint16_t*>(a.out_planes), a.q.col, a.k.col, a.v.col};
+  }
+  static std::atomic<bool> attr_done{false};
+  if (!attr_done.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFaSmem)));
+    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFaSmem)));
+    attr_done.store(true);
+  }
+  dim3 grid((Tq + QT - 1) / QT, H, B * group);
+  if (fmt == SCATT_PLANE_F16)
+    stream_attention_fa_kernel<SCATT_PLANE_F16><<<grid, kThreadsFa, kFaSmem, s>>>(P);
+  else
+    stream_attention_fa_kernel<SCATT_PLANE_BF16><<<grid, kThreadsFa, kFaSmem, s>>>(P);
+  return after_launch("stream_attention_fa_kernel");
+}
+
+}  // namespace scatt

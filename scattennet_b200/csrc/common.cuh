@@ -149,6 +149,9 @@ int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq,
 bool attention_tc_supported(int Tq, int Tk, int hd, const scatt_attention_problem* p, int group);
 int launch_attention_tc(const scatt_attention_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int64_t ldq,
                         int64_t ldk, int64_t ldv, int kind, int fmt, int terms, cudaStream_t s);
+bool attention_planes_supported(int Tq, int Tk, int hd);
+int launch_attention_planes(const scatt_attention_planes_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int kind,
+                            int fmt, int terms, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);
 

@@ -309,6 +309,34 @@ def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: i
     return outs
 
 
+ATTN_PLANES_MAX_T = 224  # longest key sequence of the TMA-fed tcgen05 attention kernel
+
+
+def stream_attention_planes(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: int, kind: int,
+                            key_mask: Optional[torch.Tensor] = None) -> List[Act]:
+    """Grouped attention whose operands are plane outputs of projection GEMMs.
+    ``qs / ks / vs``: per stream ``(planes [2, rows, ld], first column of head 0)``."""
+    G = len(qs)
+    D = H * 16
+    dev = qs[0][0].device
+    probs = (L.AttentionPlanesProblem * G)()
+    outs = []
+    for g in range(G):
+        op = torch.empty(2, B * Tq, D, dtype=prec.plane_dtype, device=dev)
+        p = probs[g]
+        for field, (pl, col) in (("q", qs[g]), ("k", ks[g]), ("v", vs[g])):
+            o = getattr(p, field)
+            o.planes, o.rows, o.ld, o.col = pl.data_ptr(), pl.shape[1], pl.shape[2], col
+        p.key_mask = _ptr(key_mask)
+        p.out, p.out_planes = None, op.data_ptr()
+        outs.append(Act(None, op))
+    flops = (2.0 * B * Tq * (Tq + 1) * D if kind == L.ATTN_CAUSAL else 4.0 * B * Tq * Tk * D) * G
+    with _timed("stream_attention_fa_kernel", flops, G * 4.0 * B * max(Tq, Tk) * D * 4):
+        L.check(L.load().scatt_attention_planes(probs, G, B, Tq, Tk, H, 16, kind, prec.plane_fmt, max(prec.terms, 1), _stream()),
+                "scatt_attention_planes")
+    return outs
+
+
 def fusion_attention(prec: Precision, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, T: int) -> Act:
     D = q.shape[1]
     o = torch.empty(B * T, D, dtype=torch.float32, device=q.device) if not prec.uses_planes else None

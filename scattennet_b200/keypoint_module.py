@@ -176,10 +176,14 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
             lins += [a.k_proj, a.v_proj]
             scales += [1.0, 0.5]
         packs.append(F_.pack_of(m, "merge_kv", lins, scales))
-    kv_all = F_.linear(prec, s, packs, F_.make_epilogue(), out_planes=False)
+    kv_planes = prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T  # TMA-fed attention takes the planes as they are
+    kv_all = F_.linear(prec, s, packs, F_.make_epilogue(), out_f32=not kv_planes, out_planes=kv_planes)
     for i in range(n):
         c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask)
-        kv_views = [(kv.f32[:, 2 * i * d : (2 * i + 1) * d], kv.f32[:, (2 * i + 1) * d : (2 * i + 2) * d]) for kv in kv_all]
+        if kv_planes:
+            kv_views = [((kv.planes, 2 * i * d), (kv.planes, (2 * i + 1) * d)) for kv in kv_all]
+        else:
+            kv_views = [(kv.f32[:, 2 * i * d : (2 * i + 1) * d], kv.f32[:, (2 * i + 1) * d : (2 * i + 2) * d]) for kv in kv_all]
         c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask)
     return c, s
 

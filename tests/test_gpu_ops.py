@@ -181,6 +181,34 @@ def test_stream_attention_key_mask(kind, B, T, mode):
     assert float((out.cpu() - ref).abs().max()) <= ATT_TOL[mode]
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
+@pytest.mark.parametrize("kind", ["self", "causal", "cross"])
+@pytest.mark.parametrize("B,T", [(2, 24), (3, 37), (8, 200), (1, 130), (2, 224), (5, 16)])
+def test_stream_attention_planes(kind, B, T, mode):
+    """TMA-fed tcgen05 kernel: operands are split planes inside a wider [rows, 768] buffer, like the QKV GEMM writes them."""
+    H, D = 16, 256
+    prec = F_.get_precision(mode)
+    qkv = rnd(B * T, 3 * D, seed=7)
+    planes = F_.split_planes(qkv, prec)
+    lengths = synth.parity_lengths(B, T)
+    mask = (torch.arange(T)[None] < torch.tensor(lengths)[:, None]).long()
+    if B >= 3:
+        mask[2] = 0
+    act = F_.stream_attention_planes(prec, [(planes, 0)], [(planes, D)], [(planes, 2 * D)], B, T, T, H,
+                                     {"self": 0, "causal": 1, "cross": 2}[kind], key_mask=F_.key_mask_u8(mask.to(DEV)))[0]
+    out = act.planes[0].float() + act.planes[1].float()
+    q, k, v = (qkv[:, i * D:(i + 1) * D].cpu().view(B, T, H, 16).transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2)
+    if kind == "causal":
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu(1)[None, None], float("-inf"))
+        s = s + O.causal_additive(mask, T, torch.float32)
+    else:
+        s = s + O.key_padding_additive(mask, torch.float32)
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, D)
+    assert torch.isfinite(out).all()
+    assert float((out.cpu() - ref).abs().max()) <= ATT_TOL[mode]
+
+
 def test_stream_attention_additive_mask_and_grouping():
     B, T, H, D = 2, 24, 16, 256
     prec = F_.get_precision("fp16x3")
