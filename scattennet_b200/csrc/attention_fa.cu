@@ -4,7 +4,9 @@
 //
 //   TMA (32-byte-swizzle boxes of 16 columns)  ->  Q [128 x 16], K [keys x 16], V [keys x 16] tiles
 //   S = Q K^T   one tcgen05.mma per product term (M=128, N=keys<=224, K=16), K-major operands
-//   softmax     thread per query row out of TMEM (exact two-pass, reference mask semantics)
+//   softmax     two threads per query row (alternate 32-key chunks) out of TMEM: exact two-pass with
+//               the reference's mask semantics; chunks with no padded / future key take a
+//               branch-free fast path
 //   P           written back into the S columns of TMEM (packed 16-bit hi | lo)
 //   O = P V     tcgen05.mma, A from TMEM, B = V read MN-major (keys x 16 rows as stored: no transpose)
 //
@@ -24,7 +26,8 @@ using namespace tc;
 constexpr int HD = 16;
 constexpr int QT = 128;
 constexpr int KMAX = 224;  // keys per CTA: S/P columns [0, 224), O columns [224, 240)
-constexpr int kThreadsFa = 160;
+constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quadrant
+constexpr int kThreadsFa = 32 * kSoftmaxWarps + 32;  // + TMA / MMA warp
 
 struct FaProblem {
   const uint8_t* key_mask;
@@ -46,7 +49,9 @@ constexpr uint32_t kQh = 0, kQl = kQh + QT * 32;
 constexpr uint32_t kKh = kQl + QT * 32, kKl = kKh + 256 * 32;
 constexpr uint32_t kVh = kKl + 256 * 32, kVl = kVh + 256 * 32;
 constexpr uint32_t kCls = kVl + 256 * 32;           // float[256] key class: 0 valid / -FLT_MAX padded / -inf absent
-constexpr uint32_t kBar = kCls + 256 * 4;           // 4 mbarriers + tmem pointer
+constexpr uint32_t kXch = kCls + 256 * 4;           // float[2][128] row max, float[2][128] row sum (pair exchange)
+constexpr uint32_t kFlag = kXch + 4 * 128 * 4;      // uint32[8]: chunk has only valid keys
+constexpr uint32_t kBar = kFlag + 32;               // 5 mbarriers + tmem pointer
 constexpr uint32_t kFaSmem = kBar + 64 + 1024;
 
 // 32-byte-swizzled tile: 8-row groups of 256 bytes.  K-major use (Q, K): rows = M/N index, 16 K-elements per row.
@@ -114,35 +119,38 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   const bool lo_q = P.terms >= 2, lo_k = P.terms >= 3;   // S: q_hi k_lo (3), q_lo k_hi (2), q_hi k_hi
   constexpr uint32_t kTmemCols = 256, kOCol = 224;
 
-  if (threadIdx.x == 128) {
+  constexpr int kMmaWarp = kSoftmaxWarps;
+  if (threadIdx.x == 32 * kMmaWarp) {
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 32 * kSoftmaxWarps);
     mbar_init(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_q[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_k[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_v[g]) : "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    for (int j = threadIdx.x; j < 256; j += 128) {
-      float c = -INFINITY;  // absent key: probability exactly 0
-      if (j < nk) c = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
-      cls[j] = c;
-    }
+    // key classes; warp w also publishes whether chunk w (keys 32w .. 32w+31) holds valid keys only
+    const int j = threadIdx.x;  // 0..255
+    float c = -INFINITY;        // absent key: probability exactly 0
+    if (j < nk) c = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
+    cls[j] = c;
+    const bool all_valid = __all_sync(0xffffffffu, c == 0.f);
+    if (lane == 0) reinterpret_cast<uint32_t*>(sm + kFlag)[warp] = all_valid ? 1u : 0u;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kBar + 40);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kBar + 40);  // written by tcgen05.alloc
   const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
   const uint32_t idesc_base = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(QT >> 4) << 24);
 
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       // ---- operands: three (x2 planes) TMA boxes
       const int qrow = b * Tq + m0, krow = b * Tk;
@@ -196,42 +204,67 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       tc_commit(bar_o);
     }
   } else {
-    // ---------------- softmax: thread = query row (TMEM lane = warp * 32 + lane)
-    const int r = warp * 32 + lane;
+    // ---------------- softmax: two threads per query row; row = (warp % 4) * 32 + lane (TMEM lane),
+    // warp / 4 picks the even or the odd 32-key chunks
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
     const int i = m0 + r;
-    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     const int nchunk = (kbox + 31) >> 5;
     const int jmax = causal ? i : 0x7fffffff;
+    const uint32_t* chunk_valid = reinterpret_cast<const uint32_t*>(sm + kFlag);
+    float* xch = reinterpret_cast<float*>(sm + kXch);
+    const float kLog2e = 1.4426950408889634f;
     float v[32];
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < nchunk; ++c) {
+    for (int c = half; c < nchunk; c += 2) {
       tc_ld32(tmem_s + lane_addr + c * 32, v);
+      // fast path: every key of the chunk is valid and visible to every row of this warp
+      const bool fast = chunk_valid[c] != 0u && (!causal || c * 32 + 31 <= m0 + quad * 32);
+      if (fast) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = c * 32 + j;
-        const float kc = cls[key];
-        float s = kc == 0.f ? v[j] : kc;
-        if (key > jmax) s = -INFINITY;
-        mx = fmaxf(mx, s);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c * 32 + j;
+          const float kc = cls[key];
+          float s = kc == 0.f ? v[j] : kc;
+          if (key > jmax) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
       }
     }
-    const float kLog2e = 1.4426950408889634f;
+    xch[half * 128 + r] = mx;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
+    mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);  // every row sees key 0, so mx is finite
+    const float mneg = -mx * kLog2e;
     float l = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < nchunk; ++c) {
+    for (int c = half; c < nchunk; c += 2) {
       tc_ld32(tmem_s + lane_addr + c * 32, v);
+      const bool fast = chunk_valid[c] != 0u && (!causal || c * 32 + 31 <= m0 + quad * 32);
+      if (fast) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = c * 32 + j;
-        const float kc = cls[key];
-        float s = kc == 0.f ? v[j] : kc;
-        if (key > jmax) s = -INFINITY;
-        const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
-        l += p;
-        v[j] = p;
+        for (int j = 0; j < 32; ++j) {
+          const float p = ex2(fmaf(v[j], kLog2e, mneg));
+          l += p;
+          v[j] = p;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int key = c * 32 + j;
+          const float kc = cls[key];
+          float s = kc == 0.f ? v[j] : kc;
+          if (key > jmax) s = -INFINITY;
+          const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
+          l += p;
+          v[j] = p;
+        }
       }
       float w[32];
       uint32_t* wp = reinterpret_cast<uint32_t*>(w);
@@ -241,26 +274,31 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     }
     tc_fence_before();
     mbar_arrive(bar_p);
+    xch[256 + half * 128 + r] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
 
-    mbar_wait(bar_o, 0);
-    tc_fence_after();
-    float o[16];
-    tc_ld16(tmem_o + lane_addr, o);
-    const float inv = 1.0f / l;
-    if (i < Tq) {
-      const int64_t row = int64_t(b) * Tq + i;
+    if (half == 0) {  // one thread of the pair scales and stores the row
+      l += xch[256 + 128 + r];
+      mbar_wait(bar_o, 0);
+      tc_fence_after();
+      float o[16];
+      tc_ld16(tmem_o + lane_addr, o);
+      const float inv = 1.0f / l;
+      if (i < Tq) {
+        const int64_t row = int64_t(b) * Tq + i;
 #pragma unroll
-      for (int c = 0; c < HD; c += 4) {
-        const float4 ov = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
-        if (A.out) *reinterpret_cast<float4*>(A.out + row * D + h * HD + c) = ov;
-        if (A.out_planes) store_planes4(A.out_planes, int64_t(P.B) * Tq * D, row * D + h * HD + c, ov, FMT);
+        for (int c = 0; c < HD; c += 4) {
+          const float4 ov = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+          if (A.out) *reinterpret_cast<float4*>(A.out + row * D + h * HD + c) = ov;
+          if (A.out_planes) store_planes4(A.out_planes, int64_t(P.B) * Tq * D, row * D + h * HD + c, ov, FMT);
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
   }
