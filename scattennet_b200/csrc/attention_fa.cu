@@ -11,7 +11,11 @@
 //   O = P V     tcgen05.mma, A from TMEM, B = V read MN-major (keys x 16 rows as stored: no transpose)
 //
 // One CTA = one (batch, head, 128-query tile); 256 TMEM columns (S/P 224 + O 16) -> two CTAs per SM.
-// Key sequences longer than 224 and dense additive masks are served by the other attention kernels.
+// Longer key sequences are walked in blocks of 224 keys with an exact two-pass softmax: pass A
+// recomputes S block by block for the row maxima, pass B recomputes it again, exponentiates and
+// accumulates O = sum_blocks P_blk V_blk (QK^T is one K=16 MMA per term, so recomputing it is free;
+// all K / V rows of the sequence stay resident in shared memory).  Up to 3 blocks (672 keys);
+// beyond that, and for dense additive masks, the fp32 CUDA-core kernel runs.
 #include <cfloat>
 
 #include "common.cuh"
@@ -25,7 +29,9 @@ using namespace tc;
 
 constexpr int HD = 16;
 constexpr int QT = 128;
-constexpr int KMAX = 224;  // keys per CTA: S/P columns [0, 224), O columns [224, 240)
+constexpr int KBLK = 224;  // keys per block: S/P columns [0, 224), O columns [224, 240)
+constexpr int kMaxBlocks = 3;
+constexpr int KMAX = KBLK * kMaxBlocks;
 constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quadrant
 constexpr int kThreadsFa = 32 * kSoftmaxWarps + 32;  // + TMA / MMA warp
 
@@ -41,18 +47,26 @@ struct alignas(64) FaParams {
   CUtensorMap map_k[SCATT_MAX_GROUP];
   CUtensorMap map_v[SCATT_MAX_GROUP];
   FaProblem p[SCATT_MAX_GROUP];
-  int32_t B, Tq, Tk, H, kind, terms, kbox;
+  int32_t B, Tq, Tk, H, kind, terms, kbox, nblk;   // kbox: rows per TMA box / keys per block; nblk: blocks covering Tk
 };
 
-// shared memory map (relative to a 1024-aligned base); every tile row is 32 bytes (16 halves)
-constexpr uint32_t kQh = 0, kQl = kQh + QT * 32;
-constexpr uint32_t kKh = kQl + QT * 32, kKl = kKh + 256 * 32;
-constexpr uint32_t kVh = kKl + 256 * 32, kVl = kVh + 256 * 32;
-constexpr uint32_t kCls = kVl + 256 * 32;           // float[256] key class: 0 valid / -FLT_MAX padded / -inf absent
-constexpr uint32_t kXch = kCls + 256 * 4;           // float[2][128] row max, float[2][128] row sum (pair exchange)
-constexpr uint32_t kFlag = kXch + 4 * 128 * 4;      // uint32[8]: chunk has only valid keys
-constexpr uint32_t kBar = kFlag + 32;               // 5 mbarriers + tmem pointer
-constexpr uint32_t kFaSmem = kBar + 64 + 1024;
+// shared memory map (relative to a 1024-aligned base); every tile row is 32 bytes (16 halves).
+// K / V regions hold nblk * kbox rows each, so their offsets depend on the launch.
+struct FaSmem {
+  uint32_t qh, ql, kh, kl, vh, vl, cls, xch, flag, bar, total;
+};
+__host__ __device__ inline FaSmem fa_smem_map(int nblk, int kbox) {
+  FaSmem m;
+  const uint32_t kv = (uint32_t(nblk) * uint32_t(kbox) * 32u + 1023u) & ~1023u;
+  m.qh = 0, m.ql = QT * 32;
+  m.kh = 2 * QT * 32, m.kl = m.kh + kv, m.vh = m.kl + kv, m.vl = m.vh + kv;
+  m.cls = m.vl + kv;                              // float[nblk * 224 + 32] key class: 0 valid / -FLT_MAX padded / -inf absent
+  m.xch = m.cls + (uint32_t(nblk) * KBLK + 32) * 4;   // float[2][128] row max, float[2][128] row sum (pair exchange)
+  m.flag = m.xch + 4 * 128 * 4;                   // uint32[nblk * 7]: chunk has only valid keys
+  m.bar = (m.flag + uint32_t(nblk) * 7 * 4 + 15u) & ~15u;  // 6 mbarriers + tmem pointer
+  m.total = m.bar + 64 + 1024;
+  return m;
+}
 
 // 32-byte-swizzled tile: 8-row groups of 256 bytes.  K-major use (Q, K): rows = M/N index, 16 K-elements per row.
 // MN-major use (V as B operand): rows = K index (keys), 16 N-elements per row.
@@ -104,9 +118,10 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t bar_qk = base + kBar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
-  const uint32_t tmem_ptr_addr = bar_qk + 40;
-  float* cls = reinterpret_cast<float*>(sm + kCls);
+  const FaSmem L = fa_smem_map(P.nblk, P.kbox);
+  const uint32_t bar_qk = base + L.bar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
+  const uint32_t bar_sf = bar_qk + 40, tmem_ptr_addr = bar_qk + 48;
+  float* cls = reinterpret_cast<float*>(sm + L.cls);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z / P.B, b = blockIdx.z % P.B, h = blockIdx.y;
@@ -114,8 +129,10 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   const int m0 = blockIdx.x * QT;
   const int Tq = P.Tq, Tk = P.Tk, D = P.H * HD;
   const bool causal = P.kind == SCATT_ATTN_CAUSAL;
-  const int kbox = P.kbox;                               // keys loaded and multiplied (multiple of 16, >= Tk)
+  const int kbox = P.kbox;                               // keys per block (multiple of 16)
   const int nk = causal ? min(Tk, m0 + QT) : Tk;         // keys this tile may see
+  const int nblk = (nk + kbox - 1) / kbox;               // key blocks this tile walks (<= P.nblk)
+  const int nchunk = (kbox + 31) >> 5;                   // 32-key chunks per block
   const bool lo_q = P.terms >= 2, lo_k = P.terms >= 3;   // S: q_hi k_lo (3), q_lo k_hi (2), q_hi k_hi
   constexpr uint32_t kTmemCols = 256, kOCol = 224;
 
@@ -126,6 +143,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     mbar_init(bar_s, 1);
     mbar_init(bar_p, 32 * kSoftmaxWarps);
     mbar_init(bar_o, 1);
+    mbar_init(bar_sf, 32 * kSoftmaxWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_q[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_k[g]) : "memory");
@@ -135,71 +153,95 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    // key classes; warp w also publishes whether chunk w (keys 32w .. 32w+31) holds valid keys only
-    const int j = threadIdx.x;  // 0..255
-    float c = -INFINITY;        // absent key: probability exactly 0
-    if (j < nk) c = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
-    cls[j] = c;
-    const bool all_valid = __all_sync(0xffffffffu, c == 0.f);
-    if (lane == 0) reinterpret_cast<uint32_t*>(sm + kFlag)[warp] = all_valid ? 1u : 0u;
+    // key classes; a warp also publishes whether its 32-key chunk holds valid keys only
+    // (keys of block blk live at class / flag index blk * nchunk * 32 + ..., blocks padded to whole chunks)
+    uint32_t* flags = reinterpret_cast<uint32_t*>(sm + L.flag);
+    for (int cc = warp; cc < nblk * nchunk; cc += kSoftmaxWarps) {
+      const int blk = cc / nchunk, j = blk * kbox + (cc % nchunk) * 32 + lane;  // key index
+      float c = -INFINITY;  // absent key (past the block, past nk): probability exactly 0
+      if ((cc % nchunk) * 32 + lane < kbox && j < nk) c = (A.key_mask && A.key_mask[int64_t(b) * Tk + j] == 0) ? -FLT_MAX : 0.f;
+      cls[cc * 32 + lane] = c;
+      const bool all_valid = __all_sync(0xffffffffu, c == 0.f);
+      if (lane == 0) flags[cc] = all_valid ? 1u : 0u;
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kBar + 40);  // written by tcgen05.alloc
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.bar + 48);  // written by tcgen05.alloc
   const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
   const uint32_t idesc_base = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(QT >> 4) << 24);
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      // ---- operands: three (x2 planes) TMA boxes
+      // ---- operands: Q box + nblk K boxes, nblk V boxes (x2 planes)
       const int qrow = b * Tq + m0, krow = b * Tk;
       const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
-      mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + kbox * 32 * nkpl));
-      tma_load_3d(base + kQh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
-      if (lo_q) tma_load_3d(base + kQl, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
-      tma_load_3d(base + kKh, &P.map_k[g], bar_qk, A.k_col + h * HD, krow, 0);
-      if (lo_k) tma_load_3d(base + kKl, &P.map_k[g], bar_qk, A.k_col + h * HD, krow, 1);
-      mbar_expect_tx(bar_v, uint32_t(kbox * 32 * nkpl));
-      tma_load_3d(base + kVh, &P.map_v[g], bar_v, A.v_col + h * HD, krow, 0);
-      if (lo_k) tma_load_3d(base + kVl, &P.map_v[g], bar_v, A.v_col + h * HD, krow, 1);
-      // ---- S = Q K^T
+      mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + nblk * kbox * 32 * nkpl));
+      tma_load_3d(base + L.qh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
+      if (lo_q) tma_load_3d(base + L.ql, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
+      for (int blk = 0; blk < nblk; ++blk) {
+        tma_load_3d(base + L.kh + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 0);
+        if (lo_k) tma_load_3d(base + L.kl + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 1);
+      }
+      mbar_expect_tx(bar_v, uint32_t(nblk * kbox * 32 * nkpl));
+      for (int blk = 0; blk < nblk; ++blk) {
+        tma_load_3d(base + L.vh + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 0);
+        if (lo_k) tma_load_3d(base + L.vl + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 1);
+      }
       mbar_wait(bar_qk, 0);
       tc_fence_after();
       const uint32_t idesc_s = idesc_base | (uint32_t(kbox >> 3) << 17);
-      const uint64_t qh = umma_desc_sw32(base + kQh), ql = umma_desc_sw32(base + kQl);
-      const uint64_t kh = umma_desc_sw32(base + kKh), kl = umma_desc_sw32(base + kKl);
-      uint32_t acc = 0;
-      if (lo_k) {
-        tc_mma_f16(tmem_s, qh, kl, idesc_s, acc);
-        acc = 1;
-      }
-      if (lo_q) {
-        tc_mma_f16(tmem_s, ql, kh, idesc_s, acc);
-        acc = 1;
-      }
-      tc_mma_f16(tmem_s, qh, kh, idesc_s, acc);
-      tc_commit(bar_s);
-      // ---- O = P V (A = P from TMEM, B = V MN-major)
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
       const uint32_t idesc_o = idesc_base | (1u << 16) | (uint32_t(HD >> 3) << 17);  // bit 16: B is MN-major
-      acc = 0;
-      for (int ks = 0; ks < kbox / 16; ++ks) {
-        const uint32_t p_hi = tmem_s + 32 * (ks >> 1) + 8 * (ks & 1), p_lo = p_hi + 16;
-        const uint64_t adv = uint64_t(ks * 512 >> 4);  // 16 keys x 32 bytes
-        const uint64_t vh = umma_desc_sw32(base + kVh) + adv, vl = umma_desc_sw32(base + kVl) + adv;
+      const uint64_t qh = umma_desc_sw32(base + L.qh), ql = umma_desc_sw32(base + L.ql);
+      auto issue_s = [&](int blk) {  // S = Q K_blk^T, one K = 16 MMA per product term
+        const uint64_t off = uint64_t(blk * kbox * 32 >> 4);
+        const uint64_t kh = umma_desc_sw32(base + L.kh) + off, kl = umma_desc_sw32(base + L.kl) + off;
+        uint32_t acc = 0;
         if (lo_k) {
-          tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc);
+          tc_mma_f16(tmem_s, qh, kl, idesc_s, acc);
           acc = 1;
         }
         if (lo_q) {
-          tc_mma_ts(tmem_o, p_lo, vh, idesc_o, acc);
+          tc_mma_f16(tmem_s, ql, kh, idesc_s, acc);
           acc = 1;
         }
-        tc_mma_ts(tmem_o, p_hi, vh, idesc_o, acc);
-        acc = 1;
+        tc_mma_f16(tmem_s, qh, kh, idesc_s, acc);
+        tc_commit(bar_s);
+      };
+      // ---- pass A: row maxima (the softmax warps hand the S buffer back through bar_sf)
+      for (int blk = 0; blk < nblk; ++blk) {
+        if (blk > 0) {
+          mbar_wait(bar_sf, (blk - 1) & 1);
+          tc_fence_after();
+        }
+        issue_s(blk);
+      }
+      mbar_wait(bar_sf, (nblk - 1) & 1);
+      tc_fence_after();
+      // ---- pass B: S again, P = exp(S - max) written over it by the softmax warps, O += P V_blk
+      // (tcgen05.mma executes in issue order, so S of the next block cannot overtake the PV MMAs reading P)
+      mbar_wait(bar_v, 0);
+      uint32_t acc_o = 0;
+      for (int blk = 0; blk < nblk; ++blk) {
+        issue_s(blk);
+        mbar_wait(bar_p, blk & 1);
+        tc_fence_after();
+        for (int ks = 0; ks < kbox / 16; ++ks) {
+          const uint32_t p_hi = tmem_s + 32 * (ks >> 1) + 8 * (ks & 1), p_lo = p_hi + 16;
+          const uint64_t adv = uint64_t((blk * kbox + ks * 16) * 32 >> 4);  // 16 keys x 32 bytes per step
+          const uint64_t vh = umma_desc_sw32(base + L.vh) + adv, vl = umma_desc_sw32(base + L.vl) + adv;
+          if (lo_k) {
+            tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc_o);
+            acc_o = 1;
+          }
+          if (lo_q) {
+            tc_mma_ts(tmem_o, p_lo, vh, idesc_o, acc_o);
+            acc_o = 1;
+          }
+          tc_mma_ts(tmem_o, p_hi, vh, idesc_o, acc_o);
+          acc_o = 1;
+        }
       }
       tc_commit(bar_o);
     }
@@ -210,33 +252,38 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     const int r = quad * 32 + lane;
     const int i = m0 + r;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
-    const int nchunk = (kbox + 31) >> 5;
     const int jmax = causal ? i : 0x7fffffff;
-    const uint32_t* chunk_valid = reinterpret_cast<const uint32_t*>(sm + kFlag);
-    float* xch = reinterpret_cast<float*>(sm + kXch);
+    const uint32_t* chunk_valid = reinterpret_cast<const uint32_t*>(sm + L.flag);
+    float* xch = reinterpret_cast<float*>(sm + L.xch);
+    uint32_t s_uses = 0;  // completed phases of bar_s
     const float kLog2e = 1.4426950408889634f;
     float v[32];
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = half; c < nchunk; c += 2) {
-      tc_ld32(tmem_s + lane_addr + c * 32, v);
-      // fast path: every key of the chunk is valid and visible to every row of this warp
-      const bool fast = chunk_valid[c] != 0u && (!causal || c * 32 + 31 <= m0 + quad * 32);
-      if (fast) {
+    for (int blk = 0; blk < nblk; ++blk) {
+      mbar_wait(bar_s, s_uses++ & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < nchunk; c += 2) {
+        tc_ld32(tmem_s + lane_addr + c * 32, v);
+        const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
+        // fast path: every key of the chunk is valid and visible to every row of this warp
+        const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
+        if (fast) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-      } else {
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j;
-          const float kc = cls[key];
-          float s = kc == 0.f ? v[j] : kc;
-          if (key > jmax) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int j = 0; j < 32; ++j) {
+            const float kc = cls[cc * 32 + j];
+            float s = kc == 0.f ? v[j] : kc;
+            if (key0 + j > jmax) s = -INFINITY;
+            mx = fmaxf(mx, s);
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(bar_sf);  // this thread is done reading the block's S
     }
     xch[half * 128 + r] = mx;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
@@ -244,36 +291,41 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     const float mneg = -mx * kLog2e;
     float l = 0.f;
 #pragma unroll 1
-    for (int c = half; c < nchunk; c += 2) {
-      tc_ld32(tmem_s + lane_addr + c * 32, v);
-      const bool fast = chunk_valid[c] != 0u && (!causal || c * 32 + 31 <= m0 + quad * 32);
-      if (fast) {
+    for (int blk = 0; blk < nblk; ++blk) {
+      mbar_wait(bar_s, s_uses++ & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < nchunk; c += 2) {
+        tc_ld32(tmem_s + lane_addr + c * 32, v);
+        const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
+        const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
+        if (fast) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float p = ex2(fmaf(v[j], kLog2e, mneg));
-          l += p;
-          v[j] = p;
-        }
-      } else {
+          for (int j = 0; j < 32; ++j) {
+            const float p = ex2(fmaf(v[j], kLog2e, mneg));
+            l += p;
+            v[j] = p;
+          }
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = c * 32 + j;
-          const float kc = cls[key];
-          float s = kc == 0.f ? v[j] : kc;
-          if (key > jmax) s = -INFINITY;
-          const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
-          l += p;
-          v[j] = p;
+          for (int j = 0; j < 32; ++j) {
+            const float kc = cls[cc * 32 + j];
+            float s = kc == 0.f ? v[j] : kc;
+            if (key0 + j > jmax) s = -INFINITY;
+            const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
+            l += p;
+            v[j] = p;
+          }
         }
+        float w[32];
+        uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
+        tc_st32(tmem_s + lane_addr + c * 32, w);
       }
-      float w[32];
-      uint32_t* wp = reinterpret_cast<uint32_t*>(w);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
-      tc_st32(tmem_s + lane_addr + c * 32, w);
+      tc_fence_before();
+      mbar_arrive(bar_p);
     }
-    tc_fence_before();
-    mbar_arrive(bar_p);
     xch[256 + half * 128 + r] = l;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
 
@@ -346,6 +398,7 @@ int encode_operand_map(CUtensorMap* map, const scatt_attn_operand& op, int box_r
 }  // namespace
 
 bool attention_planes_supported(int Tq, int Tk, int hd) { return hd == HD && Tk >= 1 && Tk <= KMAX; }
+int attention_planes_max_keys() { return KMAX; }
 
 int launch_attention_planes(const scatt_attention_planes_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int kind,
                             int fmt, int terms, cudaStream_t s) {
@@ -356,7 +409,8 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
   if (B == 0 || Tq == 0) return SCATT_OK;
   FaParams P{};
   P.B = B, P.Tq = Tq, P.Tk = Tk, P.H = H, P.kind = kind, P.terms = terms;
-  P.kbox = (Tk + 15) & ~15;
+  P.nblk = (Tk + KBLK - 1) / KBLK;
+  P.kbox = P.nblk == 1 ? ((Tk + 15) & ~15) : KBLK;
   for (int i = 0; i < group; ++i) {
     const scatt_attention_planes_problem& a = p[i];
     SCATT_REQUIRE(a.q.planes && a.k.planes && a.v.planes && (a.out || a.out_planes), "attention(planes): null operand");
@@ -370,10 +424,12 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
     if (rc != SCATT_OK) return rc;
     P.p[i] = FaProblem{a.key_mask, a.out, reinterpret_cast<uint16_t*>(a.out_planes), a.q.col, a.k.col, a.v.col};
   }
+  const uint32_t kFaSmem = fa_smem_map(P.nblk, P.kbox).total;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFaSmem)));
-    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFaSmem)));
+    const int max_smem = int(fa_smem_map(kMaxBlocks, KBLK).total);
+    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_done.store(true);
   }
   dim3 grid((Tq + QT - 1) / QT, H, B * group);

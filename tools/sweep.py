@@ -72,11 +72,15 @@ def kernel_sweep(args):
         for kind, kn in ((0, "self"), (1, "causal"), (2, "cross")):
             for mode in ("fp16x3", "fp16x1", "fp32"):
                 prec = F_.get_precision(mode)
-                fn = lambda: F_.stream_attention(prec, [t[:, :D] for t in qkv], [t[:, D:2*D] for t in qkv], [t[:, 2*D:] for t in qkv], B, T, T, H, kind, key_mask=km)
+                if prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T:
+                    pl = [F_.split_planes(t, prec) for t in qkv]
+                    fn = lambda: F_.stream_attention_planes(prec, [(t, 0) for t in pl], [(t, D) for t in pl], [(t, 2 * D) for t in pl], B, T, T, H, kind, key_mask=km)
+                else:
+                    fn = lambda: F_.stream_attention(prec, [t[:, :D] for t in qkv], [t[:, D:2*D] for t in qkv], [t[:, 2*D:] for t in qkv], B, T, T, H, kind, key_mask=km)
                 us = graph_time(fn)
                 fl = 3 * (2.0 * B * T * (T + 1) * D if kind == 1 else 4.0 * B * T * T * D)
                 ex = 3 * B * H * (T * (T + 1) / 2 if kind == 1 else T * T)
-                eng = "tcgen05" if (prec.uses_planes and T <= F_.ATTN_TC_MAX_T) else "cuda-core fp32"
+                eng = "tcgen05 (TMA-fed)" if (prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T) else "cuda-core fp32"
                 print(f"| {T} | {B} | {kn} | {mode} {eng} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {ex / us / 1e6:.2f} |", flush=True)
     print(f"\n### linear (tcgen05), 3 streams grouped (us per launch, back-to-back in a CUDA graph)\n")
     print("| M | N | K | epilogue | mode | us | TFLOP/s (2MNK) | % bf16 peak | GB/s (operands+outputs) |")
