@@ -52,7 +52,9 @@ int scatt_device_check(void) {
 
 int scatt_debug_set_trace(void* dev_buf) {
   const int rc = debug_set_trace(dev_buf);
-  return rc != SCATT_OK ? rc : debug_set_trace_attention(dev_buf);
+  if (rc != SCATT_OK) return rc;
+  const int rc2 = debug_set_trace_attention(dev_buf);
+  return rc2 != SCATT_OK ? rc2 : debug_set_trace_fa(dev_buf);
 }
 
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,

@@ -35,6 +35,11 @@ constexpr int KMAX = KBLK * kMaxBlocks;
 constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quadrant
 constexpr int kThreadsFa = 32 * kSoftmaxWarps + 32;  // + TMA / MMA warp
 
+__device__ long long* g_trace_fa = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+  if (g_trace_fa != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace_fa[slot] = clock64();
+}
+
 struct FaProblem {
   const uint8_t* key_mask;
   float* out;
@@ -137,6 +142,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   constexpr uint32_t kTmemCols = 256, kOCol = 224;
 
   constexpr int kMmaWarp = kSoftmaxWarps;
+  if (threadIdx.x == 0) trace(0);
   if (threadIdx.x == 32 * kMmaWarp) {
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
@@ -170,13 +176,15 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.bar + 48);  // written by tcgen05.alloc
   const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
+  if (threadIdx.x == 0) trace(1);
   const uint32_t idesc_base = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(QT >> 4) << 24);
 
   if (warp == kMmaWarp) {
-    if (lane == 0) {
+    // The whole warp walks this role uniformly; single-thread instructions are issued by an elected lane.
+    const int qrow = b * Tq + m0, krow = b * Tk;
+    const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
+    if (elect_one()) {
       // ---- operands: Q box + nblk K boxes, nblk V boxes (x2 planes)
-      const int qrow = b * Tq + m0, krow = b * Tk;
-      const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
       mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + nblk * kbox * 32 * nkpl));
       tma_load_3d(base + L.qh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
       if (lo_q) tma_load_3d(base + L.ql, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
@@ -189,62 +197,75 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
         tma_load_3d(base + L.vh + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 0);
         if (lo_k) tma_load_3d(base + L.vl + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 1);
       }
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      const uint32_t idesc_s = idesc_base | (uint32_t(kbox >> 3) << 17);
-      const uint32_t idesc_o = idesc_base | (1u << 16) | (uint32_t(HD >> 3) << 17);  // bit 16: B is MN-major
-      const uint64_t qh = umma_desc_sw32(base + L.qh), ql = umma_desc_sw32(base + L.ql);
-      auto issue_s = [&](int blk) {  // S = Q K_blk^T, one K = 16 MMA per product term
-        const uint64_t off = uint64_t(blk * kbox * 32 >> 4);
-        const uint64_t kh = umma_desc_sw32(base + L.kh) + off, kl = umma_desc_sw32(base + L.kl) + off;
+    }
+    __syncwarp();
+    if (lane == 0) trace(2);
+    mbar_wait(bar_qk, 0);
+    if (lane == 0) trace(3);
+    tc_fence_after();
+    const uint32_t idesc_s = idesc_base | (uint32_t(kbox >> 3) << 17);
+    const uint32_t idesc_o = idesc_base | (1u << 16) | (uint32_t(HD >> 3) << 17);  // bit 16: B is MN-major
+    const uint64_t qh = umma_desc_sw32(base + L.qh), ql = umma_desc_sw32(base + L.ql);
+    const uint64_t kh0 = umma_desc_sw32(base + L.kh), kl0 = umma_desc_sw32(base + L.kl);
+    const uint64_t vh0 = umma_desc_sw32(base + L.vh), vl0 = umma_desc_sw32(base + L.vl);
+    auto issue_s = [&](int blk) {  // S = Q K_blk^T, one K = 16 MMA per product term
+      const uint64_t off = uint64_t(blk * kbox * 32 >> 4);
+      if (elect_one()) {
         uint32_t acc = 0;
         if (lo_k) {
-          tc_mma_f16(tmem_s, qh, kl, idesc_s, acc);
+          tc_mma_f16(tmem_s, qh, kl0 + off, idesc_s, acc);
           acc = 1;
         }
         if (lo_q) {
-          tc_mma_f16(tmem_s, ql, kh, idesc_s, acc);
+          tc_mma_f16(tmem_s, ql, kh0 + off, idesc_s, acc);
           acc = 1;
         }
-        tc_mma_f16(tmem_s, qh, kh, idesc_s, acc);
+        tc_mma_f16(tmem_s, qh, kh0 + off, idesc_s, acc);
         tc_commit(bar_s);
-      };
-      // ---- pass A: row maxima (the softmax warps hand the S buffer back through bar_sf)
-      for (int blk = 0; blk < nblk; ++blk) {
-        if (blk > 0) {
-          mbar_wait(bar_sf, (blk - 1) & 1);
-          tc_fence_after();
-        }
-        issue_s(blk);
       }
-      mbar_wait(bar_sf, (nblk - 1) & 1);
-      tc_fence_after();
-      // ---- pass B: S again, P = exp(S - max) written over it by the softmax warps, O += P V_blk
-      // (tcgen05.mma executes in issue order, so S of the next block cannot overtake the PV MMAs reading P)
-      mbar_wait(bar_v, 0);
-      uint32_t acc_o = 0;
-      for (int blk = 0; blk < nblk; ++blk) {
-        issue_s(blk);
-        mbar_wait(bar_p, blk & 1);
+      __syncwarp();
+    };
+    // ---- pass A: row maxima (the softmax warps hand the S buffer back through bar_sf)
+    for (int blk = 0; blk < nblk; ++blk) {
+      if (blk > 0) {
+        mbar_wait(bar_sf, (blk - 1) & 1);
         tc_fence_after();
+      }
+      issue_s(blk);
+    }
+    mbar_wait(bar_sf, (nblk - 1) & 1);
+    tc_fence_after();
+    // ---- pass B: S again, P = exp(S - max) written over it by the softmax warps, O += P V_blk
+    // (tcgen05.mma executes in issue order, so S of the next block cannot overtake the PV MMAs reading P)
+    mbar_wait(bar_v, 0);
+    uint32_t acc_o = 0;
+    for (int blk = 0; blk < nblk; ++blk) {
+      issue_s(blk);
+      mbar_wait(bar_p, blk & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        uint64_t vh = vh0 + uint64_t(blk * kbox * 32 >> 4), vl = vl0 + uint64_t(blk * kbox * 32 >> 4);
+        uint32_t p_hi = tmem_s;  // P of keys [16 ks, 16 ks + 16): hi in 8 columns, lo 16 columns further
         for (int ks = 0; ks < kbox / 16; ++ks) {
-          const uint32_t p_hi = tmem_s + 32 * (ks >> 1) + 8 * (ks & 1), p_lo = p_hi + 16;
-          const uint64_t adv = uint64_t((blk * kbox + ks * 16) * 32 >> 4);  // 16 keys x 32 bytes per step
-          const uint64_t vh = umma_desc_sw32(base + L.vh) + adv, vl = umma_desc_sw32(base + L.vl) + adv;
           if (lo_k) {
             tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc_o);
             acc_o = 1;
           }
           if (lo_q) {
-            tc_mma_ts(tmem_o, p_lo, vh, idesc_o, acc_o);
+            tc_mma_ts(tmem_o, p_hi + 16, vh, idesc_o, acc_o);
             acc_o = 1;
           }
           tc_mma_ts(tmem_o, p_hi, vh, idesc_o, acc_o);
           acc_o = 1;
+          vh += 32, vl += 32;            // 16 keys x 32 bytes
+          p_hi += (ks & 1) ? 24 : 8;     // next 16 keys: +8 columns inside a 32-key chunk, +24 to the next chunk
         }
       }
-      tc_commit(bar_o);
+      __syncwarp();
+      acc_o = 1;
     }
+    if (elect_one()) tc_commit(bar_o);
+    __syncwarp();
   } else {
     // ---------------- softmax: two threads per query row; row = (warp % 4) * 32 + lane (TMEM lane),
     // warp / 4 picks the even or the odd 32-key chunks
@@ -262,6 +283,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
       mbar_wait(bar_s, s_uses++ & 1);
+      if (threadIdx.x == 0 && blk == 0) trace(4);
       tc_fence_after();
 #pragma unroll 1
       for (int c = half; c < nchunk; c += 2) {
@@ -285,6 +307,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       tc_fence_before();
       mbar_arrive(bar_sf);  // this thread is done reading the block's S
     }
+    if (threadIdx.x == 0) trace(5);
     xch[half * 128 + r] = mx;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
     mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);  // every row sees key 0, so mx is finite
@@ -326,12 +349,14 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       tc_fence_before();
       mbar_arrive(bar_p);
     }
+    if (threadIdx.x == 0) trace(6);
     xch[256 + half * 128 + r] = l;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
 
     if (half == 0) {  // one thread of the pair scales and stores the row
       l += xch[256 + 128 + r];
       mbar_wait(bar_o, 0);
+      if (threadIdx.x == 0) trace(7);
       tc_fence_after();
       float o[16];
       tc_ld16(tmem_o + lane_addr, o);
@@ -348,8 +373,10 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     }
   }
 
+  if (threadIdx.x == 0) trace(8);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(9);
   if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
@@ -396,6 +423,12 @@ int encode_operand_map(CUtensorMap* map, const scatt_attn_operand& op, int box_r
 }
 
 }  // namespace
+
+int debug_set_trace_fa(void* dev_buf) {
+  long long* p = reinterpret_cast<long long*>(dev_buf);
+  SCATT_CUDA(cudaMemcpyToSymbol(g_trace_fa, &p, sizeof(p)));
+  return SCATT_OK;
+}
 
 bool attention_planes_supported(int Tq, int Tk, int hd) { return hd == HD && Tk >= 1 && Tk <= KMAX; }
 int attention_planes_max_keys() { return KMAX; }

@@ -443,63 +443,69 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t tmem_acc = *tmem_ptr_gen;
   if (threadIdx.x == 0) trace(1);
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
-      const uint32_t tx = kStageBytes;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        mbar_wait(empty_bar(s), ((kb / stages) & 1) ^ 1);
-        const uint32_t st = base + s * kStageBytes;
+  // Producer and issuer warps walk their loops warp-uniformly; the single-thread instructions (TMA,
+  // tcgen05.mma, tcgen05.commit) are issued by an elected lane so they compile to bare UTMALDG / UTCHMMA.
+  if (warp == 0) {  // ---------------- TMA producer
+    const uint32_t tx = kStageBytes;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      mbar_wait(empty_bar(s), ((kb / stages) & 1) ^ 1);
+      const uint32_t st = base + s * kStageBytes;
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
         tma_load_3d(st, &P.map_a[g], full_bar(s), kb * BK, int(m0), 0);
         if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kb * BK, int(m0), 1);
         tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, n0, 0);
         if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, n0, 1);
-        if (kb == 0) trace(2);
       }
+      __syncwarp();
+      if (kb == 0 && lane == 0) trace(2);
     }
     if constexpr (LN == 2) {
       __syncwarp();
       cluster_sync_all();  // statistics exchange point of the epilogue warps
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
-      // instruction descriptor: D=f32, A/B = f16|bf16, both K-major, N, M=128
-      const uint32_t idesc = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(BN >> 3) << 17) |
-                             (uint32_t(BM >> 4) << 24);
-      uint32_t accumulate = 0;
-      if (P.pre_init) {  // the epilogue warps have put bias + residual into the accumulator
-        mbar_wait(acc_init_bar, 0);
-        tc_fence_after();
-        accumulate = 1;
-      }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        mbar_wait(full_bar(s), (kb / stages) & 1);
-        if (kb == 0) trace(3);
-        tc_fence_after();
-        const uint32_t st = base + s * kStageBytes;
-        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kABytes);
-        const uint64_t b_hi = umma_desc_sw128(st + kBOff), b_lo = umma_desc_sw128(st + kBOff + kBBytes);
+  } else if (warp == 1) {  // ---------------- MMA issuer
+    // instruction descriptor: D=f32, A/B = f16|bf16, both K-major, N, M=128
+    const uint32_t idesc = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(BN >> 3) << 17) |
+                           (uint32_t(BM >> 4) << 24);
+    uint32_t accumulate = 0;
+    if (P.pre_init) {  // the epilogue warps have put bias + residual into the accumulator
+      mbar_wait(acc_init_bar, 0);
+      tc_fence_after();
+      accumulate = 1;
+    }
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % stages;
+      mbar_wait(full_bar(s), (kb / stages) & 1);
+      if (kb == 0 && lane == 0) trace(3);
+      tc_fence_after();
+      const uint32_t st = base + s * kStageBytes;
+      const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kABytes);
+      const uint64_t b_hi = umma_desc_sw128(st + kBOff), b_lo = umma_desc_sw128(st + kBOff + kBBytes);
+      if (elect_one()) {
+        uint32_t acc = accumulate;
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t adv = uint64_t(kk * 32 >> 4);  // 16 elements x 2 B along K inside the swizzle row
           if (need_b_lo) {
-            tc_mma_f16(tmem_acc, a_hi + adv, b_lo + adv, idesc, accumulate);
-            accumulate = 1;
+            tc_mma_f16(tmem_acc, a_hi + adv, b_lo + adv, idesc, acc);
+            acc = 1;
           }
           if (need_a_lo) {
-            tc_mma_f16(tmem_acc, a_lo + adv, b_hi + adv, idesc, accumulate);
-            accumulate = 1;
+            tc_mma_f16(tmem_acc, a_lo + adv, b_hi + adv, idesc, acc);
+            acc = 1;
           }
-          tc_mma_f16(tmem_acc, a_hi + adv, b_hi + adv, idesc, accumulate);
-          accumulate = 1;
+          tc_mma_f16(tmem_acc, a_hi + adv, b_hi + adv, idesc, acc);
+          acc = 1;
         }
         tc_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
+        if (kb == num_kb - 1) tc_commit(tmem_full_bar);  // accumulator complete
       }
-      tc_commit(tmem_full_bar);  // accumulator complete
-      trace(4);
+      __syncwarp();
+      accumulate = 1;
     }
+    if (lane == 0) trace(4);
     if constexpr (LN == 2) {
       __syncwarp();
       cluster_sync_all();

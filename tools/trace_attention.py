@@ -6,7 +6,7 @@ from scattennet_b200 import functional as F_, _lib as L
 dev = "cuda"
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
 lib = L.load()
-NAMES = ["start", "Q/K staged", "V^T staged", "setup sync done", "S ready", "row max done", "P written", "O ready", "all done"]
+NAMES = ["start", "setup done", "TMA issued", "Q/K landed", "S ready", "row max done", "P written", "O ready", "row stored", "all done"]
 B, T, H, D = 8, 200, 16, 256
 g = torch.Generator().manual_seed(0)
 qkv = [torch.randn(B * T, 3 * D, generator=g).to(dev) for _ in range(3)]
@@ -14,7 +14,8 @@ km = torch.ones(B, T, dtype=torch.uint8, device=dev)
 for mode in ("fp16x3", "fp16x1"):
     prec = F_.get_precision(mode)
     for kind in (0, 1):
-        run = lambda: F_.stream_attention(prec, [t[:, :D] for t in qkv], [t[:, D:2*D] for t in qkv], [t[:, 2*D:] for t in qkv], B, T, T, H, kind, key_mask=km)
+        pl = [F_.split_planes(t, prec) for t in qkv]
+        run = lambda: F_.stream_attention_planes(prec, [(t, 0) for t in pl], [(t, D) for t in pl], [(t, 2 * D) for t in pl], B, T, T, H, kind, key_mask=km)
         for _ in range(3): run()
         torch.cuda.synchronize()
         L.check(lib.scatt_debug_set_trace(buf.data_ptr()), "on"); run(); torch.cuda.synchronize(); L.check(lib.scatt_debug_set_trace(None), "off")
