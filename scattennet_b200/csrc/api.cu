@@ -1,5 +1,6 @@
 // extern "C" surface of libscatt.so (see include/scatt.h).  Argument checking
 // and engine selection only; kernels live in the other translation units.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -7,6 +8,10 @@
 namespace scatt {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_pdl{[] {
+  const char* e = std::getenv("SCATT_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}()};
 
 namespace {
 thread_local char t_error[512] = "";

@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(128) stream_attention_kernel(AttnGroup grp, in
   const int g = blockIdx.z / B, b = blockIdx.z % B, h = blockIdx.y;
   const scatt_attention_problem& P = grp.p[g];
   const int D = H * HD;
+  pdl_launch_dependents();
+  pdl_wait();
 
   // causal CTAs only need keys up to their last query
   const int q_hi = min(Tq, int(blockIdx.x + 1) * 128);
@@ -104,6 +106,8 @@ __global__ void __launch_bounds__(256) fusion_attention_kernel(const float* __re
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                  // [FK][D]
   float* sc = smem + size_t(FK) * D;   // [FQ][T] scores / probabilities
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y, i = blockIdx.x * FQ + warp;
   const bool live = i < T;
@@ -216,7 +220,7 @@ int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq,
     attr_done.store(true);
   }
   dim3 grid((Tq + 127) / 128, H, B * group);
-  stream_attention_kernel<<<grid, 128, smem, s>>>(grp, B, Tq, Tk, H, ldq, ldk, ldv, kind, fmt);
+  (void)launch_kernel(stream_attention_kernel, grid, dim3(128), smem, s, grp, B, Tq, Tk, H, ldq, ldk, ldv, kind, fmt);
   return after_launch("stream_attention_kernel");
 }
 
@@ -233,7 +237,7 @@ int launch_fusion_attention(const float* q, const float* k, const float* v, int 
     attr_done.store(true);
   }
   dim3 grid((T + FQ - 1) / FQ, B);
-  fusion_attention_kernel<<<grid, 256, smem, s>>>(q, k, v, B, T, D, out, reinterpret_cast<uint16_t*>(planes), fmt);
+  (void)launch_kernel(fusion_attention_kernel, grid, dim3(256), smem, s, q, k, v, B, T, D, out, reinterpret_cast<uint16_t*>(planes), fmt);
   return after_launch("fusion_attention_kernel");
 }
 

@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // q / k / v planes come from the preceding GEMM
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.bar + 48);  // written by tcgen05.alloc
   const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
   if (threadIdx.x == 0) trace(1);
@@ -467,9 +469,9 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
   }
   dim3 grid((Tq + QT - 1) / QT, H, B * group);
   if (fmt == SCATT_PLANE_F16)
-    stream_attention_fa_kernel<SCATT_PLANE_F16><<<grid, kThreadsFa, kFaSmem, s>>>(P);
+    (void)launch_kernel(stream_attention_fa_kernel<SCATT_PLANE_F16>, grid, dim3(kThreadsFa), kFaSmem, s, P);
   else
-    stream_attention_fa_kernel<SCATT_PLANE_BF16><<<grid, kThreadsFa, kFaSmem, s>>>(P);
+    (void)launch_kernel(stream_attention_fa_kernel<SCATT_PLANE_BF16>, grid, dim3(kThreadsFa), kFaSmem, s, P);
   return after_launch("stream_attention_fa_kernel");
 }
 

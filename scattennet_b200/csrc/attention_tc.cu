@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(kThreadsAtt, 2) stream_attention_tc_kernel(con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
+  pdl_launch_dependents();
+  pdl_wait();
   // ---------------- operand staging: fp32 global rows -> split 16-bit swizzled tiles
   // Q and K: row r holds hi(k 0..15) in bytes 0..31 and lo(k 0..15) in bytes 32..63
   {
@@ -397,9 +399,9 @@ int launch_attention_tc(const scatt_attention_problem* p, int group, int B, int 
   }
   dim3 grid((Tq + QT - 1) / QT, H, B * group);
   if (fmt == SCATT_PLANE_F16)
-    stream_attention_tc_kernel<SCATT_PLANE_F16><<<grid, kThreadsAtt, kSmemBytes, s>>>(P);
+    (void)launch_kernel(stream_attention_tc_kernel<SCATT_PLANE_F16>, grid, dim3(kThreadsAtt), kSmemBytes, s, P);
   else
-    stream_attention_tc_kernel<SCATT_PLANE_BF16><<<grid, kThreadsAtt, kSmemBytes, s>>>(P);
+    (void)launch_kernel(stream_attention_tc_kernel<SCATT_PLANE_BF16>, grid, dim3(kThreadsAtt), kSmemBytes, s, P);
   return after_launch("stream_attention_tc_kernel");
 }
 

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearGroup grp, int64
                                                           int64_t ldres, int64_t ldy, scatt_epilogue ep, int fmt,
                                                           int fuse_tail) {
   const scatt_linear_problem& P = grp.p[blockIdx.z];
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float xs[BK][BM + 4];
   __shared__ __align__(16) float ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -105,7 +107,7 @@ int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int 
   if (M == 0) return SCATT_OK;
   const int fuse_tail = ep.layer_norm ? 0 : 1;
   dim3 grid((N + BN - 1) / BN, unsigned((M + BM - 1) / BM), group);
-  linear_simt_kernel<<<grid, 256, 0, s>>>(grp, M, N, K, ldx, ldres, ldy, ep, fmt, fuse_tail);
+  (void)launch_kernel(linear_simt_kernel, grid, dim3(256), 0, s, grp, M, N, K, ldx, ldres, ldy, ep, fmt, fuse_tail);
   int rc = after_launch("linear_simt_kernel");
   if (rc != SCATT_OK || fuse_tail) return rc;
   return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);

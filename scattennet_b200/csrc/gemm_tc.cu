@@ -440,6 +440,9 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   __syncthreads();
   tc_fence_after();
   if constexpr (LN == 2) cluster_sync_all();  // the peer CTA is resident before anybody writes into its smem
+  // Everything above touched only this CTA's resources and static weights; activations follow stream order.
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_acc = *tmem_ptr_gen;
   if (threadIdx.x == 0) trace(1);
 
@@ -656,14 +659,14 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
       SCATT_CUDA(cudaFuncSetAttribute(linear_tc_ln_cluster_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
-    linear_tc_ln_cluster_kernel<FMT><<<grid, kThreads, smem, s>>>(P);
+    (void)launch_kernel(linear_tc_ln_cluster_kernel<FMT>, grid, dim3(kThreads), smem, s, P);
     return after_launch("linear_tc_ln_cluster_kernel");
   } else {
     if (!attr_done.load()) {
       SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, LN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
-    linear_tc_kernel<BN, LN, FMT><<<grid, kThreads, smem, s>>>(P);
+    (void)launch_kernel(linear_tc_kernel<BN, LN, FMT>, grid, dim3(kThreads), smem, s, P);
     return after_launch("linear_tc_kernel");
   }
 }

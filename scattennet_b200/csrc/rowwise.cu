@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(256) rowwise_kernel(RowwiseGroup grp, int64_t 
   const float* __restrict__ b = grp.b[blockIdx.y];
   float* __restrict__ y = grp.y[blockIdx.y];
   uint16_t* __restrict__ planes = grp.planes[blockIdx.y];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int nvec_row = N >> 2;
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(256) posembed_ln_kernel(const float* __restric
                                                           const float* __restrict__ g, const float* __restrict__ b,
                                                           float* __restrict__ out, uint16_t* __restrict__ planes, int B,
                                                           int T, int D, int fmt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t M = int64_t(B) * T;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
@@ -154,6 +158,8 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__
       const int j = i / D, d = i % D;
       wt[br][i] = S.map_w[br][d * nj + j];
     }
+  pdl_launch_dependents();
+  pdl_wait();  // weights above are static; keypoints / outputs below follow stream order
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -205,6 +211,8 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__
 // ---------------------------------------------------------------- K4 temporal max-pool
 __global__ void __launch_bounds__(256) pool_pairs_kernel(const float* __restrict__ x, int B, int T, int C,
                                                          float* __restrict__ y, uint16_t* __restrict__ planes, int fmt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int To = T >> 1, cv = C >> 2;
   const int64_t total = int64_t(B) * To * cv;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -223,6 +231,8 @@ __global__ void __launch_bounds__(256) pool_pairs_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, int64_t rows, int64_t cols,
                                                            int64_t ldx, float scale, uint16_t* __restrict__ planes,
                                                            int fmt) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t cv = cols >> 2, total = rows * cv;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = i / cv, c = (i % cv) * 4;
@@ -252,7 +262,7 @@ int launch_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* r
   RowwiseGroup grp{};
   grp.z[0] = z, grp.residual[0] = residual, grp.g[0] = g, grp.b[0] = b, grp.y[0] = y;
   grp.planes[0] = reinterpret_cast<uint16_t*>(planes);
-  rowwise_kernel<<<dim3(grid_for(M, 8), 1), 256, 0, s>>>(grp, M, N, ldz, ldres, ep, ldy, fmt);
+  (void)launch_kernel(rowwise_kernel, dim3(grid_for(M, 8), 1), dim3(256), 0, s, grp, M, N, ldz, ldres, ep, ldy, fmt);
   return after_launch("rowwise_kernel");
 }
 
@@ -269,7 +279,7 @@ int launch_rowwise_linear_tail(const scatt_linear_problem* p, int group, int64_t
     grp.z[i] = p[i].y, grp.residual[i] = p[i].residual, grp.g[i] = p[i].ln_g, grp.b[i] = p[i].ln_b, grp.y[i] = p[i].y;
     grp.planes[i] = reinterpret_cast<uint16_t*>(p[i].y_planes);
   }
-  rowwise_kernel<<<dim3(grid_for(M, 8, 148 * 8 / group), group), 256, 0, s>>>(grp, M, N, ldy, ldres, ep, ldy, fmt);
+  (void)launch_kernel(rowwise_kernel, dim3(grid_for(M, 8, 148 * 8 / group), group), dim3(256), 0, s, grp, M, N, ldy, ldres, ep, ldy, fmt);
   return after_launch("rowwise_kernel");
 }
 
@@ -277,7 +287,7 @@ int launch_posembed_ln(const float* x, const float* table, const float* g, const
                        int B, int T, int D, int fmt, cudaStream_t s) {
   SCATT_REQUIRE(D % 4 == 0 && D <= 1024, "posembed_layernorm: D=%d unsupported", D);
   if (int64_t(B) * T == 0) return SCATT_OK;
-  posembed_ln_kernel<<<grid_for(int64_t(B) * T, 8), 256, 0, s>>>(x, table, g, b, out, reinterpret_cast<uint16_t*>(planes),
+  (void)launch_kernel(posembed_ln_kernel, dim3(grid_for(int64_t(B) * T, 8)), dim3(256), 0, s, x, table, g, b, out, reinterpret_cast<uint16_t*>(planes),
                                                                  B, T, D, fmt);
   return after_launch("posembed_ln_kernel");
 }
@@ -303,7 +313,7 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
     attr_done.store(true);
   }
   dim3 grid(grid_for(int64_t(B) * T, 8 * 4, 148 * 2), n);
-  frontend_kernel<<<grid, 256, smem, s>>>(kp, B, T, K, prm, fmt, wt_stride);
+  (void)launch_kernel(frontend_kernel, grid, dim3(256), smem, s, kp, B, T, K, prm, fmt, wt_stride);
   return after_launch("frontend_kernel");
 }
 
@@ -312,7 +322,7 @@ int launch_pool_pairs(const float* x, int B, int T, int C, float* y, void* plane
   SCATT_REQUIRE(T >= 2, "pool_pairs: T=%d gives an empty output (the reference raises too)", T);
   const int64_t total = int64_t(B) * (T / 2) * (C / 4);
   if (total == 0) return SCATT_OK;
-  pool_pairs_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, T, C, y, reinterpret_cast<uint16_t*>(planes), fmt);
+  (void)launch_kernel(pool_pairs_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x, B, T, C, y, reinterpret_cast<uint16_t*>(planes), fmt);
   return after_launch("pool_pairs_kernel");
 }
 
@@ -320,7 +330,7 @@ int launch_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx,
                         cudaStream_t s) {
   SCATT_REQUIRE(cols % 4 == 0 && ldx % 4 == 0, "split_planes: cols and ldx must be multiples of 4");
   if (rows * cols == 0) return SCATT_OK;
-  split_planes_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, s>>>(x, rows, cols, ldx, scale,
+  (void)launch_kernel(split_planes_kernel, dim3(grid_for(rows * (cols / 4), 256)), dim3(256), 0, s, x, rows, cols, ldx, scale,
                                                                        reinterpret_cast<uint16_t*>(planes), fmt);
   return after_launch("split_planes_kernel");
 }
