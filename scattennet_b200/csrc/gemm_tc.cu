@@ -283,9 +283,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  cluster_arrive();
+  cluster_wait();
 }
 __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer_rank, float a, float b) {
   uint32_t remote;
@@ -342,8 +344,9 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     const float da = my_mean - mean, db = other.x - mean;
     float m2 = my_m2 + other.y + kHalfN * (da * da + db * db);
     if constexpr (LN == 2) {
+      cluster_wait();  // phase 1 (armed at kernel start): the peer CTA is running
       if (half == 0) st_peer_f32x2(xstats_addr + 8u * row_in_tile, cluster_ctarank() ^ 1u, mean, m2);
-      cluster_sync_all();  // every thread of both CTAs takes part (warps 0 / 1 after their roles)
+      cluster_sync_all();  // phase 2: every thread of both CTAs takes part (warps 0 / 1 after their roles)
       float2 peer;
       asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(peer.x), "=f"(peer.y) : "r"(xstats_addr + 8u * row_in_tile) : "memory");
       const float mc = mean;
@@ -439,7 +442,9 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if constexpr (LN == 2) cluster_sync_all();  // the peer CTA is resident before anybody writes into its smem
+  // LN == 2: the peer CTA must be resident before anybody writes into its smem.  Only arrive here; the
+  // matching wait sits right before the remote store, so nobody stalls on the peer's start-up.
+  if constexpr (LN == 2) cluster_arrive();
   // Everything above touched only this CTA's resources and static weights; activations follow stream order.
   pdl_launch_dependents();
   pdl_wait();
@@ -466,7 +471,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     }
     if constexpr (LN == 2) {
       __syncwarp();
-      cluster_sync_all();  // statistics exchange point of the epilogue warps
+      cluster_wait();      // phase 1
+      cluster_sync_all();  // phase 2: statistics exchange point of the epilogue warps
     }
   } else if (warp == 1) {  // ---------------- MMA issuer
     // instruction descriptor: D=f32, A/B = f16|bf16, both K-major, N, M=128
@@ -511,6 +517,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     if (lane == 0) trace(4);
     if constexpr (LN == 2) {
       __syncwarp();
+      cluster_wait();
       cluster_sync_all();
     }
   } else {  // ---------------- epilogue warps 2..9
