@@ -36,6 +36,16 @@ if which.startswith("linear"):
         F_.linear(prec, xs, packs, ep, residuals=res, lns=lns, out_planes=(which != "linear_qkv"))
     ev1.record(); torch.cuda.synchronize()
     print(which, mode, "avg us per launch", 1e3 * ev0.elapsed_time(ev1) / reps)
+elif which == "attention_fa":
+    B, T, H, D = 8, 200, 16, 256
+    qkv = [F_.split_planes(torch.randn(B * T, 3 * D, generator=g).to(dev), prec) for _ in range(3)]
+    km = torch.ones(B, T, dtype=torch.uint8, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(reps + 3):
+        if i == 3: ev0.record()
+        F_.stream_attention_planes(prec, [(t, 0) for t in qkv], [(t, D) for t in qkv], [(t, 2 * D) for t in qkv], B, T, T, H, 0, key_mask=km)
+    ev1.record(); torch.cuda.synchronize()
+    print(which, "avg us per launch", 1e3 * ev0.elapsed_time(ev1) / reps)
 else:
     B, T, H, D = 8, 200, 16, 256
     qkv = [torch.randn(B * T, 3 * D, generator=g).to(dev) for _ in range(3)]
