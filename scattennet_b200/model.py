@@ -63,6 +63,19 @@ class MSCAEncoder(nn.Module):
             self._idx_cache[key] = [torch.tensor(self.cfg[p + "_idx"], dtype=torch.int32, device=device) for p in PARTS]
         return self._idx_cache[key]
 
+    def _n_used(self) -> int:
+        return len(sorted({j for p in PARTS for j in self.cfg[p + "_idx"]}))
+
+    def _compact_idx(self, device):
+        """``(used joints, per-stream indices into the used-joint list)`` for the host-gather path."""
+        key = "compact:" + str(device)
+        if key not in self._idx_cache:
+            used = sorted({j for p in PARTS for j in self.cfg[p + "_idx"]})
+            pos = {j: i for i, j in enumerate(used)}
+            remap = [torch.tensor([pos[j] for j in self.cfg[p + "_idx"]], dtype=torch.int32, device=device) for p in PARTS]
+            self._idx_cache[key] = (torch.tensor(used, dtype=torch.int64), remap)
+        return self._idx_cache[key]
+
     def load_reference_state_dict(self, state_dict, strict_path: bool = True):
         """Load an ``MSCA_Net`` state dict: every key of the encoder path must be
         present and match; keys outside the path (``recognition_head.fuse_alignment_head.*``)
@@ -82,7 +95,9 @@ class MSCAEncoder(nn.Module):
         prec = F_.get_precision(self.precision)
         b, t = keypoints.shape[:2]
         mods = [self.body_encoder, self.left_encoder, self.right_encoder]
-        blocks = streams_forward(prec, mods, keypoints, self._joint_idx(keypoints.device), key_mask, b, t)
+        # a compact tensor (only the joints the three streams use, see forward_host) carries remapped indices
+        idx = self._compact_idx(keypoints.device)[1] if keypoints.shape[2] == self._n_used() else self._joint_idx(keypoints.device)
+        blocks = streams_forward(prec, mods, keypoints, idx, key_mask, b, t)
         (body, left, right), tp = blocks[-1]
         fuse = coordinates_fusion_forward(prec, self.coordinates_fusion, left, right, body, b, tp, out_planes=with_heads)
         out = {"body_embed": body.f32.view(b, tp, -1), "left_embed": left.f32.view(b, tp, -1),
@@ -110,6 +125,58 @@ class MSCAEncoder(nn.Module):
         if not self.use_graph:
             return self._run(keypoints, F_.key_mask_u8(mask), with_heads)
         return self._run_graph(keypoints, mask, with_heads)
+
+    def forward_host(self, keypoints: torch.Tensor, mask: torch.Tensor, heads=("fuse_coord_gloss_logits",), device=None,
+                     gather: bool = False):
+        """End-to-end call for host-resident batches (the collator -> device path).
+
+        ``keypoints [B,T,K,2]`` / ``mask [B,T]`` are CPU tensors.  Only the joints the three streams read
+        (48 of 542 for the Phoenix configs: 384 of 4336 bytes per frame) are gathered - an exact copy - into a
+        pinned staging buffer and sent to the device; the requested ``heads`` come back in pinned host
+        tensors.  Returns ``{name: host tensor}``; call ``torch.cuda.current_stream().synchronize()`` (or use
+        the tensors after any sync) before reading them.  ``gather=True`` (inside an initialised
+        ``torch.distributed`` job): the first head is all-gathered over NVLink before the read-back, and only
+        rank 0 reads the gathered ``[world*B, T', V]`` logits (the others read their own shard)."""
+        if self.training:
+            raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward")
+        dev = device or next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("scattennet_b200 runs on a CUDA device (sm_100a) only; there is no CPU fallback")
+        used, _ = self._compact_idx(dev)
+        b, t = keypoints.shape[:2]
+        key = ("host", b, t, str(dev))
+        st = self._host_staging.get(key) if hasattr(self, "_host_staging") else None
+        if st is None:
+            if not hasattr(self, "_host_staging"):
+                self._host_staging = {}
+            st = {"kp_pin": torch.empty(b, t, used.numel(), 2, dtype=torch.float32).pin_memory(),
+                  "mask_pin": torch.empty(b, t, dtype=torch.uint8).pin_memory(),
+                  "kp_dev": torch.empty(b, t, used.numel(), 2, dtype=torch.float32, device=dev),
+                  "mask_dev": torch.empty(b, t, dtype=torch.uint8, device=dev), "out_pin": {}}
+            self._host_staging[key] = st
+        torch.index_select(keypoints, 2, used, out=st["kp_pin"])  # exact gather on the host
+        st["mask_pin"].copy_(mask != 0)
+        st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
+        st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
+        out = self.forward(st["kp_dev"], st["mask_dev"])
+        if gather:
+            import torch.distributed as dist
+
+            from .distributed import gather_logits
+
+            full = gather_logits(out[heads[0]])
+            if dist.get_rank() == 0:
+                out = dict(out)
+                out[heads[0]] = full
+        res = {}
+        for k in heads:
+            pin = st["out_pin"].get(k)
+            if pin is None or pin.shape != out[k].shape:
+                pin = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                st["out_pin"][k] = pin
+            pin.copy_(out[k], non_blocking=True)
+            res[k] = pin
+        return res
 
     # ------------------------------------------------------------------ CUDA graph replay
     def _run_graph(self, keypoints, mask, with_heads):

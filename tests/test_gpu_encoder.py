@@ -125,3 +125,19 @@ def test_position_limit_raises_like_reference():
     with pytest.raises(RuntimeError):  # T=3 cannot be pooled twice (reference: max_pool1d output size 0)
         kp, mask = synth.synth_batch(1, 3, seed=1)
         m(kp.to(DEV), mask.to(DEV))
+
+
+def test_forward_host_matches_device_path(golden):
+    """Host-gather entry point (compact H2D of the 48 used joints) == device path on the full tensor, exactly."""
+    arr, meta = golden("enc_2014t_odd")
+    cfg, sd, kp, mask = case_inputs(meta)
+    m = S.MSCAEncoder(cfg, VOCAB_STUB, precision="fp16x3", use_graph=True).eval()
+    m.load_reference_state_dict(sd)
+    m = m.to(DEV)
+    with torch.no_grad():
+        dev_out = {k: v.clone() for k, v in m(kp.to(DEV), mask.to(DEV)).items()}
+        host = m.forward_host(kp, mask, heads=("fuse_coord_gloss_logits", "body"))
+        torch.cuda.synchronize()
+    assert m._n_used() == 48
+    for k in host:
+        assert torch.equal(host[k], dev_out[k].cpu()), k
