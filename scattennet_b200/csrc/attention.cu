@@ -93,107 +93,108 @@ __global__ void __launch_bounds__(128) stream_attention_kernel(AttnGroup grp, in
   }
 }
 
-// Fusion attention: one CTA = 8 query rows (one per warp) of one batch element.
-// Keys / values stream through shared memory 8 rows at a time so the 8 warps
-// share every K / V load; each lane owns D/32 contiguous-by-4 columns.
+// Fusion attention (single head of width D, no mask, no scaling): one CTA = FQ query rows of one batch
+// element, 256 threads.
+//   phase 1  warp w takes keys j = w, w+8, ...: it reads the key row once (coalesced float4s straight from
+//            L2) and dots it with all FQ query rows held in shared memory -> logits[FQ][T]
+//   phase 2  one warp per query row: max, exp, sum over the T logits
+//   phase 3  thread t owns output columns 4t..4t+3 of all FQ rows and walks the value rows (coalesced)
 // Requires D % 128 == 0 and D <= 1024.
-constexpr int FQ = 8, FK = 8, FMAXV = 8;
+constexpr int FQ = 4, FMAXV = 8;
 
 __global__ void __launch_bounds__(256) fusion_attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v, int B, int T, int D,
                                                                float* __restrict__ out, uint16_t* __restrict__ planes,
                                                                int fmt) {
   extern __shared__ __align__(16) float smem[];
-  float* tile = smem;                  // [FK][D]
-  float* sc = smem + size_t(FK) * D;   // [FQ][T] scores / probabilities
+  float* qs = smem;                    // [FQ][D]
+  float* sc = smem + size_t(FQ) * D;   // [FQ][T] logits, then probabilities
+  float* inv = sc + size_t(FQ) * T;    // [FQ] 1 / row sum
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y, i = blockIdx.x * FQ + warp;
-  const bool live = i < T;
+  const int b = blockIdx.y, i0 = blockIdx.x * FQ;
+  const int nq = min(FQ, T - i0);
   const int nv = D >> 7;  // float4 chunks per lane
-  const float* qb = q + int64_t(b) * T * D;
+  const float* qb = q + (int64_t(b) * T + i0) * D;
   const float* kb = k + int64_t(b) * T * D;
   const float* vb = v + int64_t(b) * T * D;
-  float4 qr[FMAXV];
-#pragma unroll
-  for (int c = 0; c < FMAXV; ++c)
-    if (c < nv) qr[c] = live ? *reinterpret_cast<const float4*>(qb + int64_t(i) * D + 4 * (lane + 32 * c))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = threadIdx.x; e < FQ * (D >> 2); e += blockDim.x) {
+    const int r = e / (D >> 2), c = (e % (D >> 2)) * 4;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nq) t = *reinterpret_cast<const float4*>(qb + int64_t(r) * D + c);
+    *reinterpret_cast<float4*>(qs + r * D + c) = t;
+  }
+  __syncthreads();
 
-  // pass 1: logits
-  for (int j0 = 0; j0 < T; j0 += FK) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < FK * (D >> 2); e += blockDim.x) {
-      const int jj = e / (D >> 2), c = (e % (D >> 2)) * 4;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + jj < T) t = *reinterpret_cast<const float4*>(kb + int64_t(j0 + jj) * D + c);
-      *reinterpret_cast<float4*>(tile + jj * D + c) = t;
-    }
-    __syncthreads();
+  // phase 1: logits
+  for (int j = warp; j < T; j += 8) {
+    float4 kr[FMAXV];
 #pragma unroll
-    for (int jj = 0; jj < FK; ++jj) {
-      float s = 0.f;
+    for (int c = 0; c < FMAXV; ++c)
+      if (c < nv) kr[c] = *reinterpret_cast<const float4*>(kb + int64_t(j) * D + 4 * (lane + 32 * c));
+    float s[FQ];
+#pragma unroll
+    for (int r = 0; r < FQ; ++r) {
+      float a0 = 0.f, a1 = 0.f;  // two chains per row
 #pragma unroll
       for (int c = 0; c < FMAXV; ++c)
         if (c < nv) {
-          const float4 kk = *reinterpret_cast<const float4*>(tile + jj * D + 4 * (lane + 32 * c));
-          s = fmaf(qr[c].x, kk.x, s), s = fmaf(qr[c].y, kk.y, s), s = fmaf(qr[c].z, kk.z, s), s = fmaf(qr[c].w, kk.w, s);
+          const float4 qq = *reinterpret_cast<const float4*>(qs + r * D + 4 * (lane + 32 * c));
+          a0 = fmaf(qq.x, kr[c].x, a0), a1 = fmaf(qq.y, kr[c].y, a1);
+          a0 = fmaf(qq.z, kr[c].z, a0), a1 = fmaf(qq.w, kr[c].w, a1);
         }
-      s = warp_sum(s);
-      if (lane == 0 && j0 + jj < T) sc[warp * T + j0 + jj] = s;
+      s[r] = a0 + a1;
+    }
+#pragma unroll
+    for (int r = 0; r < FQ; ++r) s[r] = warp_sum(s[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < FQ; ++r) sc[r * T + j] = s[r];
     }
   }
-  __syncwarp();
-  // softmax over the T logits of this warp's row
-  float mx = -INFINITY;
-  for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sc[warp * T + j]);
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < T; j += 32) {
-    const float p = expf(sc[warp * T + j] - mx);
-    sc[warp * T + j] = p;
-    sum += p;
+  __syncthreads();
+  // phase 2: softmax of each row (warps 0 .. FQ-1)
+  if (warp < FQ) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) mx = fmaxf(mx, sc[warp * T + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float p = expf(sc[warp * T + j] - mx);
+      sc[warp * T + j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) inv[warp] = 1.0f / sum;
   }
-  sum = warp_sum(sum);
-  const float inv = 1.0f / sum;
-  __syncwarp();
-
-  // pass 2: out = P V
-  float4 acc[FMAXV];
+  __syncthreads();
+  // phase 3: out = P V
+  const int col = 4 * threadIdx.x;
+  if (col < D) {
+    float4 acc[FQ];
 #pragma unroll
-  for (int c = 0; c < FMAXV; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = 0; j0 < T; j0 += FK) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < FK * (D >> 2); e += blockDim.x) {
-      const int jj = e / (D >> 2), c = (e % (D >> 2)) * 4;
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j0 + jj < T) t = *reinterpret_cast<const float4*>(vb + int64_t(j0 + jj) * D + c);
-      *reinterpret_cast<float4*>(tile + jj * D + c) = t;
+    for (int r = 0; r < FQ; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+    for (int j = 0; j < T; ++j) {
+      const float4 vv = *reinterpret_cast<const float4*>(vb + int64_t(j) * D + col);
+#pragma unroll
+      for (int r = 0; r < FQ; ++r) {
+        const float p = sc[r * T + j];
+        acc[r].x = fmaf(p, vv.x, acc[r].x), acc[r].y = fmaf(p, vv.y, acc[r].y);
+        acc[r].z = fmaf(p, vv.z, acc[r].z), acc[r].w = fmaf(p, vv.w, acc[r].w);
+      }
     }
-    __syncthreads();
 #pragma unroll
-    for (int jj = 0; jj < FK; ++jj) {
-      const float p = (j0 + jj < T) ? sc[warp * T + j0 + jj] : 0.f;
-#pragma unroll
-      for (int c = 0; c < FMAXV; ++c)
-        if (c < nv) {
-          const float4 vv = *reinterpret_cast<const float4*>(tile + jj * D + 4 * (lane + 32 * c));
-          acc[c].x = fmaf(p, vv.x, acc[c].x), acc[c].y = fmaf(p, vv.y, acc[c].y);
-          acc[c].z = fmaf(p, vv.z, acc[c].z), acc[c].w = fmaf(p, vv.w, acc[c].w);
-        }
-    }
+    for (int r = 0; r < FQ; ++r)
+      if (r < nq) {
+        const float f = inv[r];
+        const float4 o = make_float4(acc[r].x * f, acc[r].y * f, acc[r].z * f, acc[r].w * f);
+        const int64_t row = int64_t(b) * T + i0 + r;
+        if (out) *reinterpret_cast<float4*>(out + row * D + col) = o;
+        if (planes) store_planes4(planes, int64_t(B) * T * D, row * D + col, o, fmt);
+      }
   }
-  if (!live) return;
-  const int64_t row = int64_t(b) * T + i;
-#pragma unroll
-  for (int c = 0; c < FMAXV; ++c)
-    if (c < nv) {
-      const float4 o = make_float4(acc[c].x * inv, acc[c].y * inv, acc[c].z * inv, acc[c].w * inv);
-      const int col = 4 * (lane + 32 * c);
-      if (out) *reinterpret_cast<float4*>(out + row * D + col) = o;
-      if (planes) store_planes4(planes, int64_t(B) * T * D, row * D + col, o, fmt);
-    }
 }
 
 }  // namespace
@@ -229,7 +230,7 @@ int launch_fusion_attention(const float* q, const float* k, const float* v, int 
   SCATT_REQUIRE(D % 128 == 0 && D <= 1024, "fusion_attention: D=%d must be a multiple of 128, <= 1024", D);
   SCATT_REQUIRE(B <= 65535, "fusion_attention: batch too large for one launch");
   if (B == 0 || T == 0) return SCATT_OK;
-  const size_t smem = (size_t(FK) * D + size_t(FQ) * T) * sizeof(float);
+  const size_t smem = (size_t(FQ) * D + size_t(FQ) * T + FQ) * sizeof(float);
   SCATT_REQUIRE(smem <= 200 * 1024, "fusion_attention: T=%d too long", T);
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {

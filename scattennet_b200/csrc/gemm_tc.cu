@@ -709,7 +709,20 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   // memory traffic of the launch.
   const int64_t row_tiles = ((M + BM - 1) / BM) * group;
   const bool narrow = N == 256 && row_tiles <= 74;
-  const int BN = ((fused_ln || N % 256 == 0) && !narrow) ? 256 : 128;
+  // Tile width: the candidate whose grid comes closest to one full wave of the 148 SMs without exceeding
+  // it (few row tiles -> narrow tiles -> more CTAs sharing the K loop's memory traffic); the widest tile
+  // when even that overflows one wave (large batches: fewer re-reads of A).
+  int BN = 256;
+  if (fused_ln) {
+    BN = narrow ? 128 : 256;
+  } else {
+    int64_t best = -1;
+    for (int cand : {256, 128, 64}) {
+      const int64_t ctas = ((N + cand - 1) / cand) * row_tiles;
+      if (ctas <= 148 && ctas > best) best = ctas, BN = cand;
+    }
+    if (best < 0) BN = N % 256 == 0 ? 256 : 128;
+  }
 
   TcParams P{};
   P.ep = ep;
@@ -741,7 +754,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   }
   int rc;
   if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
-  else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : launch_bn<128, 0>(P, group, s);
+  else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));
   if (rc != SCATT_OK || !split_ln) return rc;
   return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);
 }
