@@ -97,7 +97,7 @@ typedef struct scatt_frontend_stream {
   const int32_t* joint_idx; /* [n_joints] indices into K */
   int32_t n_joints;         /* <= 32 */
   int32_t coord[2];
-  const float* map_w[2];    /* [D, n_joints] mapping weight of the coordinate feeding branch br */
+  const float* map_wt[2];   /* [n_joints, D]: TRANSPOSED mapping weight (nn.Linear.weight^T) of the coordinate feeding branch br */
   const float* map_b[2];    /* [D] */
   const float* pos[2];      /* [max_pos + 2, D] position tables (self, causal) */
   const float* ln_g[2];     /* [D] */
@@ -224,6 +224,10 @@ int scatt_fusion_attention(const float* q, const float* k, const float* v, int B
 /* MaxPool1d(2,2) over time of x[B,T,C] -> y[B,floor(T/2),C] (model/residual.py:40-43),
  * with optional split-plane export of the pooled rows. */
 int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_planes, int plane_fmt, void* stream);
+/* Same for `group` same-shaped tensors (the anatomical streams) in one launch; the three arrays are host
+ * arrays of device pointers (`planes_host` or its entries may be NULL). */
+int scatt_pool_pairs_group(const float* const* xs_host, float* const* ys_host, void* const* planes_host, int group, int B,
+                           int T, int C, int plane_fmt, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ SYMBOLS = (
     "scatt_debug_set_trace",
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
     "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
+    "scatt_pool_pairs_group",
 )
 
 
@@ -68,7 +69,7 @@ class AttentionPlanesProblem(C.Structure):
 
 class FrontendStream(C.Structure):
     _fields_ = [
-        ("joint_idx", C.c_void_p), ("n_joints", C.c_int32), ("coord", C.c_int32 * 2), ("map_w", C.c_void_p * 2),
+        ("joint_idx", C.c_void_p), ("n_joints", C.c_int32), ("coord", C.c_int32 * 2), ("map_wt", C.c_void_p * 2),
         ("map_b", C.c_void_p * 2), ("pos", C.c_void_p * 2), ("ln_g", C.c_void_p * 2), ("ln_b", C.c_void_p * 2),
         ("out", C.c_void_p * 2), ("out_planes", C.c_void_p * 2), ("gathered", C.c_void_p),
     ]
@@ -99,6 +100,8 @@ def _declare(lib):
     lib.scatt_attention_planes.restype = i32
     lib.scatt_fusion_attention.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]
     lib.scatt_pool_pairs.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
+    lib.scatt_pool_pairs_group.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i32, i32, i32, i32, vp]
+    lib.scatt_pool_pairs_group.restype = i32
     for name in ("scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
                  "scatt_attention", "scatt_fusion_attention", "scatt_pool_pairs"):
         getattr(lib, name).restype = i32

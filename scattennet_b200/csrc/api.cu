@@ -133,4 +133,10 @@ int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_plan
   return launch_pool_pairs(x, B, T, C, y, y_planes, plane_fmt, as_stream(stream));
 }
 
+int scatt_pool_pairs_group(const float* const* xs_host, float* const* ys_host, void* const* planes_host, int group, int B, int T,
+                           int C, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(xs_host && ys_host && fmt_ok(plane_fmt), "pool_pairs_group: bad argument");
+  return launch_pool_pairs_group(xs_host, ys_host, planes_host, group, B, T, C, plane_fmt, as_stream(stream));
+}
+
 }  // extern "C"

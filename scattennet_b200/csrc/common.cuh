@@ -163,6 +163,8 @@ int launch_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* r
 int launch_rowwise_linear_tail(const scatt_linear_problem* p, int group, int64_t M, int N, int64_t ldres, int64_t ldy,
                                const scatt_epilogue& ep, int fmt, cudaStream_t s);
 int launch_pool_pairs(const float* x, int B, int T, int C, float* y, void* planes, int fmt, cudaStream_t s);
+int launch_pool_pairs_group(const float* const* xs, float* const* ys, void* const* planes, int group, int B, int T, int C,
+                            int fmt, cudaStream_t s);
 int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
                        int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s);
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,

@@ -153,11 +153,9 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__
   const scatt_frontend_stream& S = prm.s[blockIdx.y];
   const int nj = S.n_joints;
   float* wt[2] = {smem, smem + wt_stride};  // [nj][D] transposed mapping weights per branch
-  for (int br = 0; br < 2; ++br)
-    for (int i = threadIdx.x; i < nj * D; i += blockDim.x) {
-      const int j = i / D, d = i % D;
-      wt[br][i] = S.map_w[br][d * nj + j];
-    }
+  for (int br = 0; br < 2; ++br)  // the host passes W^T [nj][D]: a straight, coalesced copy
+    for (int i = threadIdx.x * 4; i < nj * D; i += blockDim.x * 4)
+      *reinterpret_cast<float4*>(wt[br] + i) = *reinterpret_cast<const float4*>(S.map_wt[br] + i);
   pdl_launch_dependents();
   pdl_wait();  // weights above are static; keypoints / outputs below follow stream order
   __syncthreads();
@@ -209,8 +207,16 @@ __global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------- K4 temporal max-pool
-__global__ void __launch_bounds__(256) pool_pairs_kernel(const float* __restrict__ x, int B, int T, int C,
-                                                         float* __restrict__ y, uint16_t* __restrict__ planes, int fmt) {
+struct PoolGroup {  // one entry per problem of a grouped launch (blockIdx.y)
+  const float* x[SCATT_MAX_GROUP];
+  float* y[SCATT_MAX_GROUP];
+  uint16_t* planes[SCATT_MAX_GROUP];
+};
+
+__global__ void __launch_bounds__(256) pool_pairs_kernel(PoolGroup grp, int B, int T, int C, int fmt) {
+  const float* __restrict__ x = grp.x[blockIdx.y];
+  float* __restrict__ y = grp.y[blockIdx.y];
+  uint16_t* __restrict__ planes = grp.planes[blockIdx.y];
   pdl_launch_dependents();
   pdl_wait();
   const int To = T >> 1, cv = C >> 2;
@@ -320,9 +326,25 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
 int launch_pool_pairs(const float* x, int B, int T, int C, float* y, void* planes, int fmt, cudaStream_t s) {
   SCATT_REQUIRE(C % 4 == 0, "pool_pairs: C must be a multiple of 4");
   SCATT_REQUIRE(T >= 2, "pool_pairs: T=%d gives an empty output (the reference raises too)", T);
+  const float* xs[1] = {x};
+  float* ys[1] = {y};
+  void* ps[1] = {planes};
+  return launch_pool_pairs_group(xs, ys, ps, 1, B, T, C, fmt, s);
+}
+
+int launch_pool_pairs_group(const float* const* xs, float* const* ys, void* const* planes, int group, int B, int T, int C,
+                            int fmt, cudaStream_t s) {
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "pool_pairs: group 1..%d", SCATT_MAX_GROUP);
+  SCATT_REQUIRE(C % 4 == 0, "pool_pairs: C must be a multiple of 4");
+  SCATT_REQUIRE(T >= 2, "pool_pairs: T=%d gives an empty output (the reference raises too)", T);
   const int64_t total = int64_t(B) * (T / 2) * (C / 4);
   if (total == 0) return SCATT_OK;
-  (void)launch_kernel(pool_pairs_kernel, dim3(grid_for(total, 256)), dim3(256), 0, s, x, B, T, C, y, reinterpret_cast<uint16_t*>(planes), fmt);
+  PoolGroup grp{};
+  for (int i = 0; i < group; ++i) {
+    SCATT_REQUIRE(xs[i] && (ys[i] || (planes && planes[i])), "pool_pairs: null pointer in problem %d", i);
+    grp.x[i] = xs[i], grp.y[i] = ys[i], grp.planes[i] = planes ? reinterpret_cast<uint16_t*>(planes[i]) : nullptr;
+  }
+  (void)launch_kernel(pool_pairs_kernel, dim3(grid_for(total, 256, 148 * 8 / group), group), dim3(256), 0, s, grp, B, T, C, fmt);
   return after_launch("pool_pairs_kernel");
 }
 

@@ -360,6 +360,21 @@ def pool_pairs(prec: Precision, x: torch.Tensor, B: int, T: int) -> Act:
     return Act(y, yp)
 
 
+def pool_pairs_group(prec: Precision, xs: Sequence[torch.Tensor], B: int, T: int) -> List[Act]:
+    """:func:`pool_pairs` for the anatomical streams in one launch."""
+    G, Cc = len(xs), xs[0].shape[1]
+    if T < 2:
+        raise RuntimeError("max_pool1d() Invalid computed output size: 0")
+    dev = xs[0].device
+    ys = [torch.empty(B * (T // 2), Cc, dtype=torch.float32, device=dev) for _ in range(G)]
+    yps = [torch.empty(2, B * (T // 2), Cc, dtype=prec.plane_dtype, device=dev) if prec.uses_planes else None for _ in range(G)]
+    arr = lambda ts: (C.c_void_p * G)(*[_ptr(t) for t in ts])
+    with _timed("pool_pairs_kernel", 0.0, G * 1.5 * B * T * Cc * 4):
+        L.check(L.load().scatt_pool_pairs_group(arr(xs), arr(ys), arr(yps), G, B, T, Cc, prec.plane_fmt, _stream()),
+                "scatt_pool_pairs_group")
+    return [Act(y, yp) for y, yp in zip(ys, yps)]
+
+
 def posembed_layernorm(prec: Precision, x: torch.Tensor, table: torch.Tensor, ln: torch.nn.LayerNorm, B: int, T: int) -> Act:
     D = x.shape[-1]
     max_pos = table.shape[0] - 2

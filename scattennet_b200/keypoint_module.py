@@ -211,6 +211,16 @@ class KeypointModule(nn.Module):
         return acts[0].f32.view(b, t_out, -1).to(keypoints.dtype)
 
 
+def _transposed_weight(lin: nn.Linear) -> torch.Tensor:
+    """``lin.weight^T`` ([K_s, D], contiguous) cached on the module; rebuilt when the parameter changes."""
+    key = (lin.weight.data_ptr(), lin.weight._version)
+    ent = lin.__dict__.get("_scatt_wt")
+    if ent is None or ent[0] != key:
+        ent = (key, lin.weight.detach().float().t().contiguous())
+        lin.__dict__["_scatt_wt"] = ent
+    return ent[1]
+
+
 def frontend_forward(prec: Precision, mods: Sequence[KeypointModule], keypoints: torch.Tensor,
                      joint_idx: Sequence[torch.Tensor], B: int, T: int, want_gathered: bool = False):
     """K1: region gather + x/y split + CoordinateMapping + position embedding +
@@ -237,7 +247,7 @@ def frontend_forward(prec: Precision, mods: Sequence[KeypointModule], keypoints:
         acts = []
         for br in range(2):
             st.coord[br] = coords[br]
-            st.map_w[br] = maps[br].weight.data_ptr()
+            st.map_wt[br] = _transposed_weight(maps[br]).data_ptr()
             st.map_b[br] = maps[br].bias.data_ptr()
             st.pos[br] = tables[br].data_ptr()
             st.ln_g[br] = norms[br].weight.data_ptr()

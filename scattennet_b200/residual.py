@@ -73,7 +73,7 @@ def residual_blocks_forward(prec: Precision, blocks: Sequence[ResidualBlock], xs
                     F_.make_epilogue(layer_norm=True, residual_mode=L.RES_AFTER_LN, act_post=L.ACT_RELU), residuals=res,
                     lns=[m.norm2 for m in blocks], out_planes=not blk.downsample)
     if blk.downsample:
-        out = [F_.pool_pairs(prec, o.f32, B, T) for o in out]
+        out = F_.pool_pairs_group(prec, [o.f32 for o in out], B, T)
         T = T // 2
     return out, T
 
