@@ -159,12 +159,41 @@ class SeparativeCoordinateAttention(nn.Module):
         return outputs
 
 
+OVERLAP_BRANCHES = True  # run the first causal layer concurrently with the self branch
+_side_streams = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], s: List[Act], c: List[Act],
                 key_mask: torch.Tensor, B: int, T: int):
     """Layer loops of reference ``model/keypoint_module.py:176-187`` on already
     position-embedded + normalised inputs, for a group of streams."""
     n = len(mods[0].self_attn_layers)
     d = s[0].cols
+    # The first causal layer only needs the causal-branch embedding: run it on a side stream while the
+    # self branch works (inside a captured forward this becomes a parallel graph branch).
+    c_first, join = None, None
+    if OVERLAP_BRANCHES and n > 0:
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            c_first = coordinate_attention_forward(prec, [m.causal_attn_layers[0] for m in mods], c, B, T, key_mask)
+            join = torch.cuda.Event()
+            join.record(side)
+        for a in list(c) + list(c_first):  # tensors that cross streams: keep the allocator honest in eager mode
+            for t in (a.f32, a.planes):
+                if t is not None:
+                    t.record_stream(side)
+                    t.record_stream(main)
     for i in range(n):
         s = coordinate_attention_forward(prec, [m.self_attn_layers[i] for m in mods], s, B, T, key_mask)
     # K / V of every merge layer read the same final self map: one N = n*2*D GEMM per stream
@@ -179,7 +208,11 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
     kv_planes = prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T  # TMA-fed attention takes the planes as they are
     kv_all = F_.linear(prec, s, packs, F_.make_epilogue(), out_f32=not kv_planes, out_planes=kv_planes)
     for i in range(n):
-        c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask)
+        if i == 0 and c_first is not None:
+            torch.cuda.current_stream().wait_event(join)
+            c = c_first
+        else:
+            c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask)
         if kv_planes:
             kv_views = [((kv.planes, 2 * i * d), (kv.planes, (2 * i + 1) * d)) for kv in kv_all]
         else:
