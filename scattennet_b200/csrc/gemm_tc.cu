@@ -37,8 +37,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarps = 8;   // default: two epilogue warps per TMEM lane quadrant (EW template parameter)
 
 struct TcProblem {
   const float* bias;
@@ -70,7 +69,7 @@ __device__ __forceinline__ void trace(int slot) {
 using namespace tc;
 
 __device__ __forceinline__ void epi_bar_sync() {  // the 8 epilogue warps only
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // LayerNorm kernels always run EW = 8
 }
 
 // ------------------------------------------------------------------ epilogue
@@ -256,10 +255,10 @@ __device__ __forceinline__ bool chunk_pre(const TcParams& P, const TcProblem& Q,
 }
 
 // Runs on the epilogue warps while TMA / MMA start: accumulator <- bias + residual.
-template <int BN>
+template <int BN, int EW>
 __device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
                                              int half) {
-  constexpr int kMine = BN / 64;  // 32-column chunks per warp
+  constexpr int kMine = BN / 32 / (EW / 4);  // 32-column chunks per warp
   float4 r[2][8];
   int c = half * kMine;
   if (n0 + c * 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + c * 32, r[0]);
@@ -297,11 +296,12 @@ __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer
 
 // LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 = the row is split
 // over the two CTAs of a cluster (N == 2 BN), which exchange per-row partial statistics through DSMEM.
-template <int BN, int LN, int FMT>
+template <int BN, int LN, int FMT, int EW>
 __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, EpiCtx& E, uint32_t tmem_acc, int n0,
                                               int half, float2* stats, uint32_t xstats_addr, int row_in_tile) {
   const scatt_epilogue& ep = P.ep;
-  constexpr int kMine = BN / 64;
+  constexpr int kMine = BN / 32 / (EW / 4);
+  static_assert(LN == 0 || EW == 8, "the fused LayerNorm combines exactly two column halves per CTA");
   float v[32];
   const bool late_res_any = ep.residual_mode != SCATT_RES_NONE && !P.pre_init;
 
@@ -379,7 +379,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
   }
 }
 
-template <int BN, int LN, int FMT>
+template <int BN, int LN, int FMT, int EW>
 __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, barriers, column parameters, LN partials, staging tiles
@@ -390,7 +390,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t ring_bytes = max(uint32_t(stages) * kStageBytes, uint32_t(kEpiWarps) * 16384u);
+  const uint32_t ring_bytes = max(uint32_t(stages) * kStageBytes, uint32_t(EW) * 16384u);
   const uint32_t bar_base = base + ring_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -418,7 +418,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(tmem_full_bar, 1);
-    mbar_init(acc_init_bar, 32 * kEpiWarps);
+    mbar_init(acc_init_bar, 32 * EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_a[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
@@ -432,7 +432,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   }
   if (warp >= 2) {  // per-column parameters of this CTA's columns -> shared memory
     float* col = reinterpret_cast<float*>(gen(col_base));
-    for (int i = threadIdx.x - 64; i < BN; i += 32 * kEpiWarps) {
+    for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) {
       const bool in = n0 + i < P.N;
       col[i] = (in && Q.bias) ? Q.bias[n0 + i] : 0.f;
       col[BN + i] = (in && Q.ln_g) ? Q.ln_g[n0 + i] : 0.f;
@@ -538,7 +538,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     E.stores = 0;
     const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
     if (P.pre_init) {
-      acc_pre_init<BN>(P, Q, E, my_tmem, n0, half);
+      acc_pre_init<BN, EW>(P, Q, E, my_tmem, n0, half);
       tc_fence_before();
       mbar_arrive(acc_init_bar);
       if (threadIdx.x == 64) trace(9);
@@ -546,7 +546,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 64) trace(5);
     tc_fence_after();
-    epilogue_rows<BN, LN, FMT>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
+    epilogue_rows<BN, LN, FMT, EW>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
                                quad * 32 + lane);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // output boxes fully written before exit
     __syncwarp();
@@ -563,15 +563,24 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
 }
 
 template <int BN, int LN, int FMT>
-__global__ void __launch_bounds__(kThreads, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
-  linear_tc_body<BN, LN, FMT>(P);
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<BN, LN, FMT, kEpiWarps>(P);
+}
+
+// Multi-wave grids (large batches): a 128 x 128 tile per CTA with one epilogue warp per TMEM quadrant and a
+// single-stage operand ring needs < 100 KB of shared memory, 128 TMEM columns and 192 threads, so TWO CTAs are
+// resident per SM and the hardware overlaps one CTA's epilogue with the other's TMA / MMA phase - the
+// overlap a persistent kernel would get from double-buffered accumulators, without the tile scheduler.
+template <int FMT>
+__global__ void __launch_bounds__(64 + 32 * 4, 2) linear_tc_dual_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<128, 0, FMT, 4>(P);
 }
 
 // N = 256 LayerNorm GEMM as 2-CTA clusters (one cluster per 128-row tile, BN = 128 per CTA): twice the
 // CTAs of the single-CTA variant for the small-batch regime, row statistics exchanged through DSMEM.
 template <int FMT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) linear_tc_ln_cluster_kernel(const __grid_constant__ TcParams P) {
-  linear_tc_body<128, 2, FMT>(P);
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_ln_cluster_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<128, 2, FMT, kEpiWarps>(P);
 }
 
 // ------------------------------------------------------------------ host side
@@ -666,16 +675,38 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
       SCATT_CUDA(cudaFuncSetAttribute(linear_tc_ln_cluster_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
-    (void)launch_kernel(linear_tc_ln_cluster_kernel<FMT>, grid, dim3(kThreads), smem, s, P);
+    (void)launch_kernel(linear_tc_ln_cluster_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
     return after_launch("linear_tc_ln_cluster_kernel");
   } else {
     if (!attr_done.load()) {
       SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, LN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
-    (void)launch_kernel(linear_tc_kernel<BN, LN, FMT>, grid, dim3(kThreads), smem, s, P);
+    (void)launch_kernel(linear_tc_kernel<BN, LN, FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
     return after_launch("linear_tc_kernel");
   }
+}
+
+template <int FMT>
+int launch_dual_fmt(TcParams& P, int group, cudaStream_t s) {
+  constexpr int BN = 128, EW = 4;
+  const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
+  int stages = int((64u * 1024u) / kStageBytes);
+  const int num_kb = (P.K + BK - 1) / BK;
+  if (stages > num_kb) stages = num_kb;
+  if (stages < 1) stages = 1;
+  P.stages = stages;
+  size_t ring = size_t(stages) * kStageBytes;
+  if (ring < size_t(EW) * 16384) ring = size_t(EW) * 16384;
+  const size_t smem = ring + 1024 + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 + EW * kEpiWarpBytes;
+  static std::atomic<bool> attr_done{false};
+  if (!attr_done.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_dual_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_done.store(true);
+  }
+  dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
+  (void)launch_kernel(linear_tc_dual_kernel<FMT>, grid, dim3(64 + 32 * EW), smem, s, P);
+  return after_launch("linear_tc_dual_kernel");
 }
 
 template <int BN, int LN>
@@ -721,8 +752,10 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
       const int64_t ctas = ((N + cand - 1) / cand) * row_tiles;
       if (ctas <= 148 && ctas > best) best = ctas, BN = cand;
     }
-    if (best < 0) BN = N % 256 == 0 ? 256 : 128;
+    if (best < 0) BN = 0;  // more than one wave whatever the width: the two-CTAs-per-SM kernel (128-wide tiles)
   }
+  const bool dual = BN == 0;
+  if (dual) BN = 128;
 
   TcParams P{};
   P.ep = ep;
@@ -754,6 +787,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   }
   int rc;
   if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
+  else if (dual) rc = fmt == SCATT_PLANE_F16 ? launch_dual_fmt<SCATT_PLANE_F16>(P, group, s) : launch_dual_fmt<SCATT_PLANE_BF16>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));
   if (rc != SCATT_OK || !split_ln) return rc;
   return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);

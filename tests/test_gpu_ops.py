@@ -117,6 +117,27 @@ def test_linear_n256_large_m_single_cta_path(mode, epi):
     assert float((out.f32.double() - ref).abs().max()) <= MODE_TOL[mode] * 4
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1", "bf16x3"])
+@pytest.mark.parametrize("epi", ["bias", "qscale", "gelu", "clamp"])
+@pytest.mark.parametrize("shape", [(12800 + 5, 768, 256), (19000, 1120, 512)])
+def test_linear_multi_wave_dual_cta_path(mode, epi, shape):
+    """Grids larger than one wave run the 2-CTAs-per-SM kernel (128-wide tiles, 4 epilogue warps)."""
+    M, N, K = shape
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    x = rnd(M, K, seed=1)
+    lin = make_linear(N, K, 2)
+    res = rnd(M, N, seed=4)
+    for with_res in (False, True):  # with a residual the accumulator pre-initialisation runs on 4 warps
+        kw2 = dict(kw, residual_mode=L.RES_BEFORE_LN) if with_res and epi == "bias" else kw
+        out = F_.linear(prec, [Act(x)], [F_.PackedLinear([lin], None, None)], F_.make_epilogue(**kw2),
+                        residuals=[res] if kw2.get("residual_mode") else None)[0]
+        ref = ref_chain(x, lin, kw2, res, None)
+        assert float((out.f32.double() - ref).abs().max()) <= MODE_TOL[mode] * max(1.0, math.sqrt(K / 256))
+        rec = out.planes[0].float() + out.planes[1].float()
+        assert float((rec - out.f32).abs().max()) <= 2.0 ** (-21 if mode.startswith("fp16") else -15) * float(out.f32.abs().max()) + 1e-7
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16x1"])
 def test_linear_grouped_matches_single(mode):
     prec = F_.get_precision(mode)
