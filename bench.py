@@ -305,7 +305,7 @@ def run_ours(args):
         })
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = time_oracle(steps=8, warmup=2, budget_s=25.0)
+            r = time_oracle(steps=40, warmup=2, budget_s=25.0)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
         line = {
             "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
