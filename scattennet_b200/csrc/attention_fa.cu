@@ -156,6 +156,28 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_v[g]) : "memory");
   }
   if (warp == kMmaWarp) {
+    // operands first (they only need the barriers): Q box + nblk K boxes, nblk V boxes (x2 planes) are in
+    // flight while TMEM is allocated and the softmax warps classify the keys
+    __syncwarp();
+    pdl_launch_dependents();
+    pdl_wait();  // q / k / v planes come from the preceding GEMM
+    if (elect_one()) {
+      const int qrow = b * Tq + m0, krow = b * Tk;
+      const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
+      mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + nblk * kbox * 32 * nkpl));
+      tma_load_3d(base + L.qh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
+      if (lo_q) tma_load_3d(base + L.ql, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
+      for (int blk = 0; blk < nblk; ++blk) {
+        tma_load_3d(base + L.kh + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 0);
+        if (lo_k) tma_load_3d(base + L.kl + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 1);
+      }
+      mbar_expect_tx(bar_v, uint32_t(nblk * kbox * 32 * nkpl));
+      for (int blk = 0; blk < nblk; ++blk) {
+        tma_load_3d(base + L.vh + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 0);
+        if (lo_k) tma_load_3d(base + L.vl + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 1);
+      }
+    }
+    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
@@ -174,8 +196,10 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_launch_dependents();
-  pdl_wait();  // q / k / v planes come from the preceding GEMM
+  if (warp != kMmaWarp) {
+    pdl_launch_dependents();
+    pdl_wait();
+  }
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.bar + 48);  // written by tcgen05.alloc
   const uint32_t tmem_s = tmem, tmem_o = tmem + kOCol;
   if (threadIdx.x == 0) trace(1);
@@ -183,24 +207,6 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
 
   if (warp == kMmaWarp) {
     // The whole warp walks this role uniformly; single-thread instructions are issued by an elected lane.
-    const int qrow = b * Tq + m0, krow = b * Tk;
-    const int nq = lo_q ? 2 : 1, nkpl = lo_k ? 2 : 1;
-    if (elect_one()) {
-      // ---- operands: Q box + nblk K boxes, nblk V boxes (x2 planes)
-      mbar_expect_tx(bar_qk, uint32_t(QT * 32 * nq + nblk * kbox * 32 * nkpl));
-      tma_load_3d(base + L.qh, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 0);
-      if (lo_q) tma_load_3d(base + L.ql, &P.map_q[g], bar_qk, A.q_col + h * HD, qrow, 1);
-      for (int blk = 0; blk < nblk; ++blk) {
-        tma_load_3d(base + L.kh + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 0);
-        if (lo_k) tma_load_3d(base + L.kl + blk * kbox * 32, &P.map_k[g], bar_qk, A.k_col + h * HD, krow + blk * kbox, 1);
-      }
-      mbar_expect_tx(bar_v, uint32_t(nblk * kbox * 32 * nkpl));
-      for (int blk = 0; blk < nblk; ++blk) {
-        tma_load_3d(base + L.vh + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 0);
-        if (lo_k) tma_load_3d(base + L.vl + blk * kbox * 32, &P.map_v[g], bar_v, A.v_col + h * HD, krow + blk * kbox, 1);
-      }
-    }
-    __syncwarp();
     if (lane == 0) trace(2);
     mbar_wait(bar_qk, 0);
     if (lane == 0) trace(3);
@@ -248,7 +254,8 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       if (elect_one()) {
         uint64_t vh = vh0 + uint64_t(blk * kbox * 32 >> 4), vl = vl0 + uint64_t(blk * kbox * 32 >> 4);
         uint32_t p_hi = tmem_s;  // P of keys [16 ks, 16 ks + 16): hi in 8 columns, lo 16 columns further
-        for (int ks = 0; ks < kbox / 16; ++ks) {
+        const int ksteps = (min(kbox, nk - blk * kbox) + 15) >> 4;  // causal tiles stop at the diagonal
+        for (int ks = 0; ks < ksteps; ++ks) {
           if (lo_k) {
             tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc_o);
             acc_o = 1;
@@ -287,8 +294,9 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       mbar_wait(bar_s, s_uses++ & 1);
       if (threadIdx.x == 0 && blk == 0) trace(4);
       tc_fence_after();
+      const int nch = (min(kbox, nk - blk * kbox) + 31) >> 5;  // chunks holding a key this tile may see
 #pragma unroll 1
-      for (int c = half; c < nchunk; c += 2) {
+      for (int c = half; c < nch; c += 2) {
         tc_ld32(tmem_s + lane_addr + c * 32, v);
         const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
         // fast path: every key of the chunk is valid and visible to every row of this warp
@@ -319,8 +327,9 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     for (int blk = 0; blk < nblk; ++blk) {
       mbar_wait(bar_s, s_uses++ & 1);
       tc_fence_after();
+      const int nch = (min(kbox, nk - blk * kbox) + 31) >> 5;
 #pragma unroll 1
-      for (int c = half; c < nchunk; c += 2) {
+      for (int c = half; c < nch; c += 2) {
         tc_ld32(tmem_s + lane_addr + c * 32, v);
         const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
         const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
