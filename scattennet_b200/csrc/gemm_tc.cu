@@ -548,7 +548,9 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     tc_fence_after();
     epilogue_rows<BN, LN, FMT, EW>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
                                quad * 32 + lane);
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // output boxes fully written before exit
+    // the boxes must have been READ out of shared memory before the CTA exits; the global writes drain behind it
+    // (they are part of the grid's memory operations: the next kernel's griddepcontrol.wait / stream order covers them)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
     if (threadIdx.x == 64) trace(7);
   }
