@@ -38,6 +38,7 @@ extern "C" {
 
 #define SCATT_ABI_VERSION 1
 #define SCATT_MAX_GROUP 4 /* problems per grouped launch (the 3 anatomical streams + spare) */
+#define SCATT_MAX_FINITE 16 /* tensors per scatt_finite_check call */
 
 enum scatt_error {
   SCATT_OK = 0,
@@ -228,6 +229,35 @@ int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_plan
  * arrays of device pointers (`planes_host` or its entries may be NULL). */
 int scatt_pool_pairs_group(const float* const* xs_host, float* const* ys_host, void* const* planes_host, int group, int B,
                            int T, int C, int plane_fmt, void* stream);
+
+/* ------------------------------------------------------------------ consumers of the path */
+
+/* Recurrent part of one bidirectional LSTM layer (nn.LSTM of AlignmentModule, model/alignment_module.py:25-33,66-72;
+ * hidden size per direction H = 512, zero initial state, every sequence runs all T steps exactly like the
+ * reference, which does not pack padded sequences).
+ *   gates_x  [B*T, ldg] fp32, row b*T + t, columns dir*4H + gate*H + unit in torch's gate order (i, f, g, o):
+ *            the input projection x_t W_ih^T + b_ih + b_hh of both directions (one scatt_linear call, N = 8H);
+ *   w_hh     [2][4H][H] fp32: weight_hh_l{k} then weight_hh_l{k}_reverse;
+ *   y        [B*T, 2H] fp32 (row b*T + t; forward states in columns [0,H), reverse in [H,2H)) and / or
+ *   y_planes [2][B*T][2H] split planes of the same matrix (operand of the next GEMM);
+ *   workspace: scatt_lstm_workspace_bytes(B, H) bytes of device memory owned by the caller (the h exchange
+ *            buffer; zeroed on `stream` by this call).
+ * One persistent co-operative launch of 128 CTAs runs all T steps with W_hh resident in shared memory. */
+size_t scatt_lstm_workspace_bytes(int64_t B, int H);
+int scatt_lstm_bidir(const float* gates_x, int64_t ldg, const float* w_hh, float* y, void* y_planes, void* workspace,
+                     int64_t B, int T, int H, int plane_fmt, void* stream);
+
+/* out = clamp(log_softmax(logits, dim=-1), clamp_min, clamp_max) for logits [B*T, V] (row b*T + t, row stride ld),
+ * written batch-major ([B,T,V]) or, with time_major != 0, as [T,B,V] - the permute + log_softmax + clamp(-100, 0)
+ * that feeds nn.CTCLoss in MSCA_Net.compute_loss (model/__init__.py:243-250). */
+int scatt_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int time_major, float clamp_min,
+                      float clamp_max, float* out, void* stream);
+
+/* *flags_dev = OR over i of (1 << i) for every tensor i (host arrays of `count` device pointers / element counts)
+ * holding a NaN or an infinity: one launch and one 4-byte read-back instead of the 16 host-synchronising
+ * isnan / isinf checks of MSCA_Net.forward (model/__init__.py:130-167). */
+int scatt_finite_check(const float* const* tensors_host, const int64_t* sizes_host, int count, int* flags_dev,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -246,7 +246,8 @@ def linear_heads(sd: SD, p: str, left: Tensor, right: Tensor, fuse: Tensor, body
     }
 
 
-def encoder_forward(sd: SD, cfg: Mapping, keypoints: Tensor, mask: Tensor, dtype=torch.float32, heads: bool = True) -> dict:
+def encoder_forward(sd: SD, cfg: Mapping, keypoints: Tensor, mask: Tensor, dtype=torch.float32, heads: bool = True,
+                    alignment: bool = False) -> dict:
     """model/__init__.py:126-159 restricted to the encoder path: region split,
     three keypoint streams, coordinate fusion and the four linear heads.
     ``sd`` uses the ``MSCA_Net`` key prefixes."""
@@ -257,7 +258,65 @@ def encoder_forward(sd: SD, cfg: Mapping, keypoints: Tensor, mask: Tensor, dtype
     out["fuse_embed"] = coordinates_fusion(sd, "coordinates_fusion", out["left_embed"], out["right_embed"], out["body_embed"])
     if heads:
         out.update(linear_heads(sd, "recognition_head", out["left_embed"], out["right_embed"], out["fuse_embed"], out["body_embed"]))
+    if alignment:
+        out["alignment_gloss_logits"] = alignment_head(sd, "recognition_head", out["fuse_embed"])
     return out
+
+
+# --------------------------------------------------------------------------- consumers of the path
+
+
+def lstm_direction(w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor, x: Tensor, reverse: bool) -> Tensor:
+    """One direction of one ``nn.LSTM`` layer, written out (the arithmetic itself is ATen's, which the
+    reference reaches through ``nn.LSTM`` at model/alignment_module.py:25-31).  ``x [T, B, in]`` ->
+    ``[T, B, H]``; zero initial state; gate rows ordered (input, forget, cell, output)."""
+    t_len, b, _ = x.shape
+    hid = w_hh.shape[1]
+    h = x.new_zeros(b, hid)
+    c = x.new_zeros(b, hid)
+    out = x.new_empty(t_len, b, hid)
+    steps = range(t_len - 1, -1, -1) if reverse else range(t_len)
+    for t in steps:
+        g = x[t] @ w_ih.T + b_ih + h @ w_hh.T + b_hh
+        i, f, gg, o = g.split(hid, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[t] = h
+    return out
+
+
+def alignment_module(sd: SD, p: str, x: Tensor, num_layers: int = 2) -> Tensor:
+    """model/alignment_module.py:66-72 - ``x [T, B, 1024]`` -> stacked bidirectional LSTM (each layer's
+    input is the concatenation forward | reverse of the previous one; inter-layer dropout is identity in
+    eval) -> ``permute(1, 0, 2)`` -> ``gloss_layer``.  Returns ``[B, T, V]`` (unclamped)."""
+    h = x
+    for layer in range(num_layers):
+        outs = []
+        for sfx, rev in ((f"_l{layer}", False), (f"_l{layer}_reverse", True)):
+            w = lambda n: _w(sd, f"{p}.rnn.{n}{sfx}", h.dtype)
+            outs.append(lstm_direction(w("weight_ih"), w("weight_hh"), w("bias_ih"), w("bias_hh"), h, rev))
+        h = torch.cat(outs, dim=2)
+    return linear(sd, p + ".gloss_layer", h.permute(1, 0, 2))
+
+
+def alignment_head(sd: SD, p: str, fuse: Tensor) -> Tensor:
+    """model/__init__.py:51,56 - ``fuse_alignment_head(fuse.permute(1, 0, 2))`` clamped to +-50."""
+    return torch.clamp(alignment_module(sd, p + ".fuse_alignment_head", fuse.permute(1, 0, 2)), min=-50, max=50)
+
+
+def ctc_log_probs(logits: Tensor) -> Tensor:
+    """model/__init__.py:243-250 (``compute_loss``) - ``[B,T,V]`` logits -> time-major ``[T,B,V]``
+    ``clamp(log_softmax, -100, 0)``, the tensor handed to ``nn.CTCLoss``."""
+    return torch.clamp(F.log_softmax(logits.permute(1, 0, 2), dim=-1), min=-100, max=0)
+
+
+def non_finite_mask(tensors: Sequence[Tensor]) -> int:
+    """model/__init__.py:130-167 - the ``isnan(...).any() or isinf(...).any()`` checks, as a bit set."""
+    bits = 0
+    for i, t in enumerate(tensors):
+        if bool(torch.isnan(t).any()) or bool(torch.isinf(t).any()):
+            bits |= 1 << i
+    return bits
 
 
 def generic_encoder(sd: SD, p: str, x_embed: Tensor, mask: Tensor, cfg: Mapping) -> Tensor:

@@ -8,6 +8,7 @@ CUDA kernels (``csrc/``) reached through the C ABI of ``libscatt.so``
 (``include/scatt.h``).  There is no CPU fallback.
 """
 
+from .alignment_module import AlignmentModule  # noqa: F401
 from .attention import BaseAttention, CrossAttention, SelfAttention, SelfCausalAttention  # noqa: F401
 from .config import PHOENIX_2014, PHOENIX_2014T, model_config  # noqa: F401
 from .encoder import Encoder, EncoderLayer  # noqa: F401

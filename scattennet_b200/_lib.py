@@ -30,6 +30,7 @@ SYMBOLS = (
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
     "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
     "scatt_pool_pairs_group",
+    "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
 )
 
 
@@ -102,6 +103,14 @@ def _declare(lib):
     lib.scatt_pool_pairs.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
     lib.scatt_pool_pairs_group.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i32, i32, i32, i32, vp]
     lib.scatt_pool_pairs_group.restype = i32
+    lib.scatt_lstm_workspace_bytes.argtypes = [i64, i32]
+    lib.scatt_lstm_workspace_bytes.restype = C.c_size_t
+    lib.scatt_lstm_bidir.argtypes = [vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.scatt_lstm_bidir.restype = i32
+    lib.scatt_log_softmax.argtypes = [vp, i64, i32, i32, i32, i32, f32, f32, vp, vp]
+    lib.scatt_log_softmax.restype = i32
+    lib.scatt_finite_check.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, vp, vp]
+    lib.scatt_finite_check.restype = i32
     for name in ("scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
                  "scatt_attention", "scatt_fusion_attention", "scatt_pool_pairs"):
         getattr(lib, name).restype = i32

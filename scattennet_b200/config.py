@@ -27,6 +27,8 @@ _COMMON = {
     "body_idx": list(range(11, 17)),
     "right_idx": list(range(54, 75)),
     "left_idx": list(range(33, 54)),
+    # the BiLSTM alignment head that consumes fuse_embed (configs/phoenix-2014t.yaml:220-225)
+    "alignment_module": {"input_size": 1024, "hidden_size": 1024, "num_layers": 2, "dropout": 0.3, "bidirectional": True},
 }
 
 PHOENIX_2014T = dict(_COMMON, residual_blocks=[256, 256, 512, 512], in_fusion_dim=512)

@@ -139,4 +139,22 @@ int scatt_pool_pairs_group(const float* const* xs_host, float* const* ys_host, v
   return launch_pool_pairs_group(xs_host, ys_host, planes_host, group, B, T, C, plane_fmt, as_stream(stream));
 }
 
+size_t scatt_lstm_workspace_bytes(int64_t B, int H) { return B < 0 || H < 0 ? 0 : lstm_workspace_bytes(B, H); }
+
+int scatt_lstm_bidir(const float* gates_x, int64_t ldg, const float* w_hh, float* y, void* y_planes, void* workspace,
+                     int64_t B, int T, int H, int plane_fmt, void* stream) {
+  SCATT_REQUIRE(fmt_ok(plane_fmt) && T >= 0, "lstm_bidir: bad argument");
+  return launch_lstm_bidir(gates_x, ldg, w_hh, y, y_planes, workspace, B, T, H, plane_fmt, as_stream(stream));
+}
+
+int scatt_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int time_major, float clamp_min, float clamp_max,
+                      float* out, void* stream) {
+  SCATT_REQUIRE(B >= 0 && T >= 0, "log_softmax: bad argument");
+  return launch_log_softmax(logits, ld, V, B, T, time_major, clamp_min, clamp_max, out, as_stream(stream));
+}
+
+int scatt_finite_check(const float* const* tensors_host, const int64_t* sizes_host, int count, int* flags_dev, void* stream) {
+  return launch_finite_check(tensors_host, sizes_host, count, flags_dev, as_stream(stream));
+}
+
 }  // extern "C"

@@ -180,6 +180,12 @@ int launch_attention_tc(const scatt_attention_problem* p, int group, int B, int 
 bool attention_planes_supported(int Tq, int Tk, int hd);
 int launch_attention_planes(const scatt_attention_planes_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int kind,
                             int fmt, int terms, cudaStream_t s);
+size_t lstm_workspace_bytes(int64_t B, int H);
+int launch_lstm_bidir(const float* gates_x, int64_t ldg, const float* w_hh, float* y, void* y_planes, void* workspace,
+                      int64_t B, int T, int H, int fmt, cudaStream_t s);
+int launch_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int time_major, float lo, float hi, float* out,
+                       cudaStream_t s);
+int launch_finite_check(const float* const* tensors, const int64_t* sizes, int count, int* flags, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);
 

@@ -205,6 +205,14 @@ class PackedLinear:
                 self.b32 = (torch.cat(bs, 0) if len(bs) > 1 else bs[0]).contiguous()
             else:
                 self.b32 = None
+            # output widths that are not a multiple of 32 (an arbitrary gloss vocabulary) are zero-padded for
+            # the kernels; `linear` returns the first n_valid columns
+            self.n_valid = self.w32.shape[0]
+            pad = (-self.n_valid) % 32
+            if pad:
+                self.w32 = torch.cat([self.w32, self.w32.new_zeros(pad, self.w32.shape[1])], 0).contiguous()
+                if self.b32 is not None:
+                    self.b32 = torch.cat([self.b32, self.b32.new_zeros(pad)], 0).contiguous()
         self.N, self.K = self.w32.shape
         self.key = key
         self._planes = {}
@@ -279,6 +287,12 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     with _timed(name, 2.0 * G * M * N * K, G * ((M * K + N * K) * esz + M * N * 4.0)):
         L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
                                       max(prec.terms, 1), _stream()), "scatt_linear")
+    for g in range(G):
+        nv = getattr(packs[g], "n_valid", N)
+        if nv != N:  # drop the zero-padded columns (plumbing copy; only for widths that are not a multiple of 32)
+            if want_planes or ep.layer_norm:
+                raise ValueError("grouped linear: a padded output width supports plain fp32 outputs only")
+            outs[g] = Act(outs[g].f32[:, :nv].contiguous())
     return outs
 
 
@@ -403,3 +417,47 @@ def rowwise(prec: Precision, z: torch.Tensor, ep: L.Epilogue, ln: Optional[torch
 def key_mask_u8(mask: torch.Tensor) -> torch.Tensor:
     """``[B, T]`` 0/1 mask of any integer / bool / float dtype -> uint8 (1 = valid key)."""
     return (mask != 0).to(torch.uint8).contiguous()
+
+
+# ----------------------------------------------------------------------------- consumers of the path (SURVEY.md 8f)
+
+
+def lstm_bidir(prec: Precision, gates_x: torch.Tensor, w_hh: torch.Tensor, B: int, T: int, H: int,
+               out_f32: bool = True) -> Act:
+    """Recurrent part of one bidirectional LSTM layer.  ``gates_x [B*T, 8H]`` fp32 (input projections of both
+    directions, biases added), ``w_hh [2, 4H, H]`` fp32; returns ``[B*T, 2H]`` (forward | reverse)."""
+    dev = gates_x.device
+    want_planes = prec.uses_planes
+    y = torch.empty(B * T, 2 * H, dtype=torch.float32, device=dev) if (out_f32 or not want_planes) else None
+    yp = torch.empty(2, B * T, 2 * H, dtype=prec.plane_dtype, device=dev) if want_planes else None
+    lib = L.load()
+    ws = torch.empty(max(int(lib.scatt_lstm_workspace_bytes(B, H)), 16), dtype=torch.uint8, device=dev)
+    # per step and direction: 2 * B * 4H * H recurrent flops; bytes: gates in, states out (W_hh stays on chip)
+    with _timed("lstm_bidir_kernel", 2.0 * 2 * B * T * 4 * H * H, B * T * (8 * H + 2 * H) * 4.0):
+        L.check(lib.scatt_lstm_bidir(gates_x.data_ptr(), gates_x.stride(0), w_hh.data_ptr(), _ptr(y), _ptr(yp), ws.data_ptr(),
+                                     B, T, H, prec.plane_fmt, _stream()), "scatt_lstm_bidir")
+    return Act(y, yp)
+
+
+def log_softmax_clamp(logits: torch.Tensor, time_major: bool = False, clamp_min: float = -100.0,
+                      clamp_max: float = 0.0) -> torch.Tensor:
+    """``clamp(log_softmax(logits [B,T,V], -1), clamp_min, clamp_max)`` as ``[B,T,V]`` or ``[T,B,V]``."""
+    require_cuda(logits)
+    B, T, V = logits.shape
+    x = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+    out = torch.empty((T, B, V) if time_major else (B, T, V), dtype=torch.float32, device=x.device)
+    with _timed("log_softmax_kernel", 0.0, 2.0 * B * T * V * 4):
+        L.check(L.load().scatt_log_softmax(x.data_ptr(), V, V, B, T, 1 if time_major else 0, clamp_min, clamp_max,
+                                           out.data_ptr(), _stream()), "scatt_log_softmax")
+    return out
+
+
+def finite_flags(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Device int32 scalar with bit ``i`` set when ``tensors[i]`` holds a NaN or an infinity (no host sync)."""
+    n = len(tensors)
+    ts = [t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous() for t in tensors]
+    flags = torch.empty(1, dtype=torch.int32, device=ts[0].device)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in ts])
+    sizes = (C.c_int64 * n)(*[t.numel() for t in ts])
+    L.check(L.load().scatt_finite_check(ptrs, sizes, n, flags.data_ptr(), _stream()), "scatt_finite_check")
+    return flags

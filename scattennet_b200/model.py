@@ -3,8 +3,10 @@
 streams (``body_encoder``, ``left_encoder``, ``right_encoder``),
 ``coordinates_fusion`` and the four linear classifiers of ``recognition_head``
 with their +-50 clamp.  Sub-module names equal the reference's, so
-``MSCA_Net.state_dict()`` loads with ``strict=False`` (the BiLSTM alignment head,
-the losses and the tokenizer are outside the path - SURVEY.md section 8f).
+``MSCA_Net.state_dict()`` loads with ``strict=False``.  ``alignment=True`` adds the
+first consumer of the path, the BiLSTM ``fuse_alignment_head`` (``alignment_gloss_logits``,
+reference ``model/__init__.py:27-29,51``); the losses and the
+tokenizer stay outside.
 
 ``forward(keypoints[B,T,K,2], mask[B,T])`` runs ~80 grouped kernel launches;
 ``use_graph=True`` replays them from a CUDA graph captured per ``(B, T)``.
@@ -19,6 +21,7 @@ from torch import nn
 
 from . import _lib as L
 from . import functional as F_
+from .alignment_module import AlignmentModule, alignment_forward
 from .functional import Act
 from .fusion import CoordinatesFusion, coordinates_fusion_forward
 from .keypoint_module import KeypointModule, frontend_forward, streams_forward
@@ -30,24 +33,28 @@ class LinearHeads(nn.Module):
     """The four ``nn.Linear`` classifiers of ``RecognitionHead`` (reference
     ``model/__init__.py:14-25``), same attribute names."""
 
-    def __init__(self, cfg, vocab_size: int):
+    def __init__(self, cfg, vocab_size: int, alignment: bool = False):
         super().__init__()
         c = cfg["residual_blocks"][-1]
         self.left_gloss_classifier = nn.Linear(c, vocab_size)
         self.right_gloss_classifier = nn.Linear(c, vocab_size)
         self.body_gloss_classifier = nn.Linear(c, vocab_size)
         self.fuse_coord_classifier = nn.Linear(cfg["out_fusion_dim"], vocab_size)
+        if alignment:
+            self.fuse_alignment_head = AlignmentModule(**cfg["alignment_module"], cls_num=vocab_size)
 
 
 class MSCAEncoder(nn.Module):
-    def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False, micro_batches: int = 1):
+    def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False, micro_batches: int = 1,
+                 alignment: bool = False):
         super().__init__()
         self.cfg = dict(cfg)
         self.body_encoder = KeypointModule(cfg["body_idx"], num_frame=cfg["num_frame"], cfg=cfg)
         self.left_encoder = KeypointModule(cfg["left_idx"], num_frame=cfg["num_frame"], cfg=cfg)
         self.right_encoder = KeypointModule(cfg["right_idx"], num_frame=cfg["num_frame"], cfg=cfg)
         self.coordinates_fusion = CoordinatesFusion(cfg["in_fusion_dim"], cfg["out_fusion_dim"], 0.2)
-        self.recognition_head = LinearHeads(cfg, vocab_size)
+        self.recognition_head = LinearHeads(cfg, vocab_size, alignment)
+        self.alignment = alignment
         self.precision = precision
         self.use_graph = use_graph
         # > 1: inside the captured graph the batch is cut into this many independent sub-batches that
@@ -111,6 +118,9 @@ class MSCAEncoder(nn.Module):
             fl = F_.linear(prec, [fuse], [F_.pack_of(rh, "fuse", [rh.fuse_coord_classifier])], ep, out_planes=False)[0]
             out.update(left=lg[0].f32.view(b, tp, -1), right=lg[1].f32.view(b, tp, -1), body=lg[2].f32.view(b, tp, -1),
                        fuse_coord_gloss_logits=fl.f32.view(b, tp, -1))
+            if self.alignment:
+                al = alignment_forward(prec, rh.fuse_alignment_head, fuse, b, tp, clamp=50.0)
+                out["alignment_gloss_logits"] = al.f32.view(b, tp, -1)
         return out
 
     def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True) -> Dict[str, torch.Tensor]:

@@ -173,6 +173,49 @@ def module_cases():
     save("mod_encoder", x=xe, mask=me, out=e(xe, me), cfg=json.dumps(ecfg))
 
 
+@torch.no_grad()
+def alignment_cases():
+    """Consumers of the path: the reference's BiLSTM alignment head on the fused features
+    of encoder cases above (same seeds), ``AlignmentModule`` alone, and the CTC log-prob front of ``compute_loss``."""
+    from model.alignment_module import AlignmentModule  # noqa: E402  (reference)
+
+    for name, cfg_name, batch, t, lengths, lstep, over in (
+        ("align_2014t_small", "phoenix-2014t", 2, 16, [16, 11], (1, 1), {}),
+        ("align_2014t_odd", "phoenix-2014t", 3, 37, [37, 20, 1], (1, 1), {}),
+        ("align_2014_small", "phoenix-2014", 2, 18, [18, 7], (1, 1), {}),
+        ("align_2014t_c1", "phoenix-2014t", 8, 200, synth.parity_lengths(8, 200), (1, 8), {}),
+    ):
+        cfg = full_cfg(cfg_name, **over)
+        model = MSCA_Net(copy.deepcopy(cfg), StubTokenizer(), "cpu").eval()
+        synth.load_synth_(model, seed=0)
+        kp, mask = synth.synth_batch(batch, t, seed=1, lengths=lengths)
+        body = model.body_encoder(kp[:, :, cfg["body_idx"], :], mask)
+        left = model.left_encoder(kp[:, :, cfg["left_idx"], :], mask)
+        right = model.right_encoder(kp[:, :, cfg["right_idx"], :], mask)
+        fuse = model.coordinates_fusion(left, right, body)
+        heads = model.recognition_head(left, right, fuse, body)  # the reference's own RecognitionHead.forward
+        al = heads["alignment_gloss_logits"]
+        lf, lv = lstep
+        save(name,
+             meta=json.dumps(dict(cfg=cfg_name, over=over, batch=batch, t=t, lengths=lengths, seed_w=0, seed_in=1,
+                                  frame_step=1, logit_step=[lf, lv], mask_override=None)),
+             alignment_gloss_logits=al[:, ::lf, ::lv],
+             fuse_coord_gloss_logits=heads["fuse_coord_gloss_logits"][:, ::lf, ::lv])
+
+    # AlignmentModule alone, time-major input as the reference passes it, plus compute_loss's log-prob front
+    g = torch.Generator().manual_seed(21)
+    m = AlignmentModule(cls_num=97, input_size=1024, hidden_size=1024).eval()
+    synth.load_synth_(m, seed=16)
+    res = {}
+    for nm, (tt, bb) in (("a", (9, 2)), ("b", (23, 11)), ("c", (1, 3))):
+        x = torch.randn(tt, bb, 1024, generator=g)
+        lg = m(x)
+        res[f"x_{nm}"] = x
+        res[f"logits_{nm}"] = lg
+        res[f"logp_{nm}"] = torch.clamp(torch.nn.functional.log_softmax(lg.permute(1, 0, 2), dim=-1), min=-100, max=0)
+    save("mod_alignment", **res)
+
+
 def state_dict_keys():
     for nm in ("phoenix-2014t", "phoenix-2014"):
         m = MSCA_Net(full_cfg(nm), StubTokenizer(), "cpu")
@@ -184,6 +227,9 @@ def state_dict_keys():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--alignment-only" in sys.argv:  # adds the section-8f fixtures without rewriting the encoder ones
+        alignment_cases()
+        sys.exit(0)
     state_dict_keys()
     module_cases()
     encoder_case("enc_2014t_small", "phoenix-2014t", 2, 16, [16, 11])
@@ -195,3 +241,4 @@ if __name__ == "__main__":
     encoder_case("enc_2014t_c1", "phoenix-2014t", 8, 200, synth.parity_lengths(8, 200), logit_step=(1, 8))
     encoder_case("enc_2014_t400", "phoenix-2014", 2, 400, synth.parity_lengths(2, 400)[::-1], frame_step=4,
                  logit_step=(4, 8), max_position_embeddings=512)
+    alignment_cases()
