@@ -272,6 +272,35 @@ def run_ours(args):
         per_kernel = prof.summary()
         model.use_graph = True
 
+        # ---- the same step with the path's first consumer attached (BiLSTM alignment head):
+        # reported beside the headline, not part of it
+        consumers = None
+        if world == 1 and not args.no_consumers:
+            m2 = MSCAEncoder(cfg, VOCAB, precision=args.precision, use_graph=True, alignment=True).eval()
+            synth.load_synth_(m2, seed=0)
+            m2 = m2.to(dev)
+            for _ in range(3):
+                m2(kp_dev, mask_dev)
+            ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            torch.cuda.synchronize()
+            for e0, e1 in ev3:
+                flush.zero_()
+                e0.record()
+                o2 = m2(kp_dev, mask_dev)
+                e1.record()
+            torch.cuda.synchronize()
+            ms3 = sum(e0.elapsed_time(e1) for e0, e1 in ev3) / args.steps
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                lp = F_.log_softmax_clamp(o2["alignment_gloss_logits"], time_major=True)
+            e1.record()
+            torch.cuda.synchronize()
+            consumers = {"with_alignment_head": {"ms_per_step": ms3, "value": args.batch * T / (ms3 * 1e-3), "unit": UNIT,
+                                                 "launches_per_step": m2.graph_launches(kp_dev.shape, dev)},
+                         "ctc_log_softmax_eager_call_us": 1e3 * e0.elapsed_time(e1) / 20, "log_probs_shape": list(lp.shape)}
+            del m2
+
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -327,6 +356,7 @@ def run_ours(args):
             "clocks": sampler.result(),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "consumers": consumers,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -351,6 +381,7 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--micro-batches", type=int, default=1, help="independent sub-batches run as parallel CUDA-graph branches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-consumers", action="store_true", help="skip the extra timing of the step with the BiLSTM alignment head")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -123,18 +123,31 @@ class MSCAEncoder(nn.Module):
                 out["alignment_gloss_logits"] = al.f32.view(b, tp, -1)
         return out
 
-    def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True) -> Dict[str, torch.Tensor]:
+    def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True,
+                check_finite: bool = False) -> Dict[str, torch.Tensor]:
         """``keypoints [B,T,K,2]`` (the full collated tensor - the region split is
         part of the path), ``mask [B,T]`` 0/1.  Returns the stream / fusion
-        features and the clamped per-frame logits (fp32)."""
+        features and the clamped per-frame logits (fp32).
+
+        ``check_finite=True`` reproduces the NaN / inf guards of ``MSCA_Net.forward`` (reference
+        ``model/__init__.py:130-167``: input, the three stream outputs, the fused features, every head) and
+        raises ``ValueError`` naming the first offender - with one fused kernel and one 4-byte read-back
+        instead of 16 host synchronisations."""
         if self.training:
             raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward")
         F_.require_cuda(keypoints, mask)
         if keypoints.dtype != torch.float32 or not keypoints.is_contiguous():
             keypoints = keypoints.float().contiguous()
         if not self.use_graph:
-            return self._run(keypoints, F_.key_mask_u8(mask), with_heads)
-        return self._run_graph(keypoints, mask, with_heads)
+            out = self._run(keypoints, F_.key_mask_u8(mask), with_heads)
+        else:
+            out = self._run_graph(keypoints, mask, with_heads)
+        if check_finite:
+            names = ["input keypoints"] + list(out)
+            bits = int(F_.finite_flags([keypoints] + [out[k] for k in out]).item())
+            if bits:
+                raise ValueError("NaN or inf in " + names[(bits & -bits).bit_length() - 1])
+        return out
 
     def forward_host(self, keypoints: torch.Tensor, mask: torch.Tensor, heads=("fuse_coord_gloss_logits",), device=None,
                      gather: bool = False):

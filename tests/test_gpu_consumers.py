@@ -166,3 +166,24 @@ def test_encoder_odd_vocabulary():
         assert got[k].shape == want[k].shape == (2, 6, V), k
         assert got[k].is_contiguous()
         assert float((got[k].cpu() - want[k]).abs().max()) <= 1e-4, k
+
+
+def test_forward_check_finite():
+    """The reference's NaN / inf guards (model/__init__.py:130-167) as one flag read-back."""
+    from scattennet_b200.config import model_config
+
+    cfg = model_config("phoenix-2014t")
+    m = S.MSCAEncoder(cfg, 64, precision="fp16x3").eval()
+    synth.load_synth_(m, seed=5)
+    m = m.to(DEV)
+    kp, mask = synth.synth_batch(2, 16, seed=3, lengths=[16, 9])
+    with torch.no_grad():
+        out = m(kp.to(DEV), mask.to(DEV), check_finite=True)
+        assert set(out) >= {"body_embed", "fuse_embed", "fuse_coord_gloss_logits"}
+        bad = kp.clone()
+        bad[1, 2, 40, 0] = float("nan")  # a left-hand joint of a valid frame
+        with pytest.raises(ValueError, match="input keypoints"):
+            m(bad.to(DEV), mask.to(DEV), check_finite=True)
+        m.coordinates_fusion.out_proj.bias[3] = float("inf")  # in-place under no_grad: bumps the version, weights repack
+        with pytest.raises(ValueError, match="fuse_embed"):
+            m(kp.to(DEV), mask.to(DEV), check_finite=True)
