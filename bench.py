@@ -300,6 +300,29 @@ def run_ours(args):
                                                  "launches_per_step": m2.graph_launches(kp_dev.shape, dev)},
                          "ctc_log_softmax_eager_call_us": 1e3 * e0.elapsed_time(e1) / 20, "log_probs_shape": list(lp.shape)}
             del m2
+            # ---- the 16-bit single-product tier of the north star (max-abs 1e-2 class; the headline runs the
+            # fp32-grade 3-term split): same step, same workload
+            tiers = {}
+            for tier in ("fp16x1",):
+                if tier == args.precision:
+                    continue
+                m3 = MSCAEncoder(cfg, VOCAB, precision=tier, use_graph=True).eval()
+                synth.load_synth_(m3, seed=0)
+                m3 = m3.to(dev)
+                for _ in range(3):
+                    m3(kp_dev, mask_dev)
+                ev4 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                torch.cuda.synchronize()
+                for e0, e1 in ev4:
+                    flush.zero_()
+                    e0.record()
+                    m3(kp_dev, mask_dev)
+                    e1.record()
+                torch.cuda.synchronize()
+                ms4 = sum(e0.elapsed_time(e1) for e0, e1 in ev4) / args.steps
+                tiers[tier] = {"ms_per_step": ms4, "value": args.batch * T / (ms4 * 1e-3), "unit": UNIT}
+                del m3
+            consumers["precision_tiers"] = tiers
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
