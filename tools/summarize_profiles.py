@@ -22,13 +22,13 @@ def launches(path, out, skip, count):
             fh.write(f"{r['ID']:>4s} {r['Kernel Name'].split('(')[0].replace('void scatt::<unnamed>::',''):46s} {r['Grid Size']:14s} {r['Metric Value']}\n")
     print(open(out).read().split("\n# per launch")[0])
 
-def raw_metrics(rep, out, want):
+def raw_metrics(rep, out, want, idx=0):
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = r[0], r[1], r[2]
+    hdr, units, vals = r[0], r[1], r[2 + idx]
     got = {}
     with open(out, "w") as fh:
-        fh.write(f"# ncu --set full --clock-control none, one launch; source: {os.path.basename(rep)}\n")
+        fh.write(f"# ncu --set full --clock-control none, one launch (launch #{idx} of the report); source: {os.path.basename(rep)}\n")
         for h, u, v in zip(hdr, units, vals):
             if any(h == w or h.startswith(w) for w in want):
                 fh.write(f"{h} [{u}] = {v}\n")
@@ -52,7 +52,7 @@ def full_step(rep, out, traffic_json=None):
             return 0.0
     recs = []
     for r in rows[2:]:
-        name = g(r, "Kernel Name").split("(")[0].replace("void scatt::<unnamed>::", "").replace("scatt::<unnamed>::", "")
+        name = g(r, "Kernel Name").split("(")[0].replace("void ", "").replace("scatt::<unnamed>::", "").replace("scatt::(anonymous namespace)::", "").replace("<unnamed>::", "").replace("unnamed>::", "")
         recs.append(dict(
             name=name, grid=g(r, "launch__grid_size"), regs=g(r, "launch__registers_per_thread"),
             ns=f(r, "gpu__time_duration.sum"), rd=f(r, "dram__bytes_read.sum"), wr=f(r, "dram__bytes_write.sum"),
@@ -78,12 +78,12 @@ def full_step(rep, out, traffic_json=None):
     with open(out, "w") as fh:
         fh.write(f"# ncu --set full --clock-control none --profile-from-start off, one eager step ({len(recs)} launches, sum {tot/1e3:.1f} us; cold-cache, serialised)\n")
         fh.write(f"# source: {os.path.basename(rep)}; DRAM / L2 bytes are per launch averages; tensor% / sm% are time-weighted pct_of_peak_sustained_elapsed\n")
-        fh.write(f"{'kernel':44s} {'n':>3s} {'total_us':>9s} {'avg_us':>8s} {'share':>6s} {'dram_rd_MB':>10s} {'dram_wr_MB':>10s} {'l2_MB':>8s} {'tensor%':>8s} {'sm%':>6s}\n")
+        fh.write(f"{'kernel':44s} {'n':>3s} {'total_us':>9s} {'avg_us':>8s} {'share':>6s} {'dram_rd_MB':>10s} {'dram_wr_MB':>10s} {'tensor%':>8s} {'sm%':>6s}\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
-            fh.write(f"{k:44s} {a['n']:3d} {a['ns']/1e3:9.1f} {a['ns']/a['n']/1e3:8.2f} {100*a['ns']/tot:5.1f}% {a['rd']/a['n']/1e6:10.3f} {a['wr']/a['n']/1e6:10.3f} {a['l2']/a['n']/1e6:8.2f} {a['tensor']/max(a['ns'],1):8.1f} {a['sm']/max(a['ns'],1):6.1f}\n")
-        fh.write("\n# per launch, in stream order: kernel, grid, regs, us, dram_rd_MB, dram_wr_MB, l2_MB, tensor%, sm%, dram%\n")
+            fh.write(f"{k:44s} {a['n']:3d} {a['ns']/1e3:9.1f} {a['ns']/a['n']/1e3:8.2f} {100*a['ns']/tot:5.1f}% {a['rd']/a['n']/1e6:10.3f} {a['wr']/a['n']/1e6:10.3f} {a['tensor']/max(a['ns'],1):8.1f} {a['sm']/max(a['ns'],1):6.1f}\n")
+        fh.write("\n# per launch, in stream order: kernel, grid, regs, us, dram_rd_MB, dram_wr_MB, tensor%, sm%, dram%\n")
         for r in recs:
-            fh.write(f"{r['name']:44s} {r['grid']:>6s} {r['regs']:>4s} {r['ns']/1e3:8.2f} {r['rd']/1e6:8.3f} {r['wr']/1e6:8.3f} {r['l2']/1e6:8.2f} {r['tensor']:6.1f} {r['sm']:6.1f} {r['dram']:6.1f}\n")
+            fh.write(f"{r['name']:44s} {r['grid']:>6s} {r['regs']:>4s} {r['ns']/1e3:8.2f} {r['rd']/1e6:8.3f} {r['wr']/1e6:8.3f} {r['tensor']:6.1f} {r['sm']:6.1f} {r['dram']:6.1f}\n")
     print(open(out).read().split("\n# per launch")[0])
     if traffic_json:
         tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (average over the launches of that kernel in one eager step) from the ncu --set full capture summarised in " + os.path.basename(out) + " (cold L2 per replay pass)"}
@@ -112,4 +112,4 @@ if __name__ == "__main__":
             skip, count = int(a.split(":")[3]), int(a.split(":")[4])
             launches(src, dst, skip, count)
         else:
-            raw_metrics(src, dst, WANT)
+            raw_metrics(src, dst, WANT, int(a.split(":")[3]) if len(a.split(":")) > 3 else 0)
