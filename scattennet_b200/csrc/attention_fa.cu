@@ -11,6 +11,9 @@
 //   O = P V     tcgen05.mma, A from TMEM, B = V read MN-major (keys x 16 rows as stored: no transpose)
 //
 // One CTA = one (batch, head, 128-query tile); 256 TMEM columns (S/P 224 + O 16) -> two CTAs per SM.
+// A tile of up to 224 keys computes S once (max pass and exp pass both read it from TMEM), and the PV
+// MMAs of a 64-key slice are issued as soon as the softmax warps have written that slice of P, so all
+// but the last slice of O = P V overlaps the exponentials.
 // Longer key sequences are walked in blocks of 224 keys with an exact two-pass softmax: pass A
 // recomputes S block by block for the row maxima, pass B recomputes it again, exponentiates and
 // accumulates O = sum_blocks P_blk V_blk (QK^T is one K=16 MMA per term, so recomputing it is free;
@@ -68,8 +71,8 @@ __host__ __device__ inline FaSmem fa_smem_map(int nblk, int kbox) {
   m.cls = m.vl + kv;                              // float[nblk * 224 + 32] key class: 0 valid / -FLT_MAX padded / -inf absent
   m.xch = m.cls + (uint32_t(nblk) * KBLK + 32) * 4;   // float[2][128] row max, float[2][128] row sum (pair exchange)
   m.flag = m.xch + 4 * 128 * 4;                   // uint32[nblk * 7]: chunk has only valid keys
-  m.bar = (m.flag + uint32_t(nblk) * 7 * 4 + 15u) & ~15u;  // 6 mbarriers + tmem pointer
-  m.total = m.bar + 64 + 1024;
+  m.bar = (m.flag + uint32_t(nblk) * 7 * 4 + 15u) & ~15u;  // 6 mbarriers + tmem pointer + 3 more P-slice mbarriers
+  m.total = m.bar + 96 + 1024;
   return m;
 }
 
@@ -126,6 +129,9 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   const FaSmem L = fa_smem_map(P.nblk, P.kbox);
   const uint32_t bar_qk = base + L.bar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_p = bar_qk + 24, bar_o = bar_qk + 32;
   const uint32_t bar_sf = bar_qk + 40, tmem_ptr_addr = bar_qk + 48;
+  // P is handed to the MMA warp in slices of 64 keys (one chunk per thread of a row pair): slice 0 on bar_p,
+  // slices 1..3 on the barriers behind the TMEM pointer
+  auto bar_pk = [&](int it) -> uint32_t { return it == 0 ? bar_p : bar_qk + 48 + 8 * it; };
   float* cls = reinterpret_cast<float*>(sm + L.cls);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,6 +156,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     mbar_init(bar_p, 32 * kSoftmaxWarps);
     mbar_init(bar_o, 1);
     mbar_init(bar_sf, 32 * kSoftmaxWarps);
+    for (int it = 1; it < 4; ++it) mbar_init(bar_pk(it), 32 * kSoftmaxWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_q[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_k[g]) : "memory");
@@ -248,30 +255,34 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     mbar_wait(bar_v, 0);
     uint32_t acc_o = 0;
     for (int blk = 0; blk < nblk; ++blk) {
-      issue_s(blk);
-      mbar_wait(bar_p, blk & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        uint64_t vh = vh0 + uint64_t(blk * kbox * 32 >> 4), vl = vl0 + uint64_t(blk * kbox * 32 >> 4);
-        uint32_t p_hi = tmem_s;  // P of keys [16 ks, 16 ks + 16): hi in 8 columns, lo 16 columns further
-        const int ksteps = (min(kbox, nk - blk * kbox) + 15) >> 4;  // causal tiles stop at the diagonal
-        for (int ks = 0; ks < ksteps; ++ks) {
-          if (lo_k) {
-            tc_mma_ts(tmem_o, p_hi, vl, idesc_o, acc_o);
+      if (nblk > 1) issue_s(blk);  // a single block still holds the S of pass A
+      const int nkeys = min(kbox, nk - blk * kbox);  // causal tiles stop at the diagonal
+      const int ksteps = (nkeys + 15) >> 4, niter = (((nkeys + 31) >> 5) + 1) >> 1;
+      const uint64_t vh = vh0 + uint64_t(blk * kbox * 32 >> 4), vl = vl0 + uint64_t(blk * kbox * 32 >> 4);
+      for (int it = 0; it < niter; ++it) {
+        mbar_wait(bar_pk(it), blk & 1);  // P of keys [64 it, 64 it + 64) is in TMEM
+        tc_fence_after();
+        if (elect_one()) {
+          const int ks1 = min(4 * it + 4, ksteps);
+          for (int ks = 4 * it; ks < ks1; ++ks) {
+            // P of keys [16 ks, 16 ks + 16): hi in 8 columns of the 32-key chunk, lo 16 columns further
+            const uint32_t p_hi = tmem_s + uint32_t(ks >> 1) * 32 + uint32_t(ks & 1) * 8;
+            const uint64_t voff = uint64_t(ks) * 32;  // 16 keys x 32 bytes
+            if (lo_k) {
+              tc_mma_ts(tmem_o, p_hi, vl + voff, idesc_o, acc_o);
+              acc_o = 1;
+            }
+            if (lo_q) {
+              tc_mma_ts(tmem_o, p_hi + 16, vh + voff, idesc_o, acc_o);
+              acc_o = 1;
+            }
+            tc_mma_ts(tmem_o, p_hi, vh + voff, idesc_o, acc_o);
             acc_o = 1;
           }
-          if (lo_q) {
-            tc_mma_ts(tmem_o, p_hi + 16, vh, idesc_o, acc_o);
-            acc_o = 1;
-          }
-          tc_mma_ts(tmem_o, p_hi, vh, idesc_o, acc_o);
-          acc_o = 1;
-          vh += 32, vl += 32;            // 16 keys x 32 bytes
-          p_hi += (ks & 1) ? 24 : 8;     // next 16 keys: +8 columns inside a 32-key chunk, +24 to the next chunk
         }
+        __syncwarp();
+        acc_o = 1;
       }
-      __syncwarp();
-      acc_o = 1;
     }
     if (elect_one()) tc_commit(bar_o);
     __syncwarp();
@@ -325,60 +336,75 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     float l = 0.f;
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
-      mbar_wait(bar_s, s_uses++ & 1);
-      tc_fence_after();
-      const int nch = (min(kbox, nk - blk * kbox) + 31) >> 5;
-#pragma unroll 1
-      for (int c = half; c < nch; c += 2) {
-        tc_ld32(tmem_s + lane_addr + c * 32, v);
-        const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
-        const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
-        if (fast) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float p = ex2(fmaf(v[j], kLog2e, mneg));
-            l += p;
-            v[j] = p;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float kc = cls[cc * 32 + j];
-            float s = kc == 0.f ? v[j] : kc;
-            if (key0 + j > jmax) s = -INFINITY;
-            const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
-            l += p;
-            v[j] = p;
-          }
-        }
-        float w[32];
-        uint32_t* wp = reinterpret_cast<uint32_t*>(w);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
-        tc_st32(tmem_s + lane_addr + c * 32, w);
+      if (nblk > 1) {  // S of this block was recomputed; a single block is still there from pass A
+        mbar_wait(bar_s, s_uses++ & 1);
+        tc_fence_after();
       }
-      tc_fence_before();
-      mbar_arrive(bar_p);
+      const int nch = (min(kbox, nk - blk * kbox) + 31) >> 5;
+      const int niter = (nch + 1) >> 1;
+#pragma unroll 1
+      for (int it = 0; it < niter; ++it) {
+        const int c = 2 * it + half;
+        if (c < nch) {
+          tc_ld32(tmem_s + lane_addr + c * 32, v);
+          const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
+          const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
+          if (fast) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float p = ex2(fmaf(v[j], kLog2e, mneg));
+              l += p;
+              v[j] = p;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float kc = cls[cc * 32 + j];
+              float s = kc == 0.f ? v[j] : kc;
+              if (key0 + j > jmax) s = -INFINITY;
+              const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
+              l += p;
+              v[j] = p;
+            }
+          }
+          float w[32];
+          uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) split2<FMT>(v[2 * q], v[2 * q + 1], wp[q], wp[16 + q]);
+          tc_st32(tmem_s + lane_addr + c * 32, w);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_pk(it));  // this 64-key slice of P may be multiplied
+      }
     }
     if (threadIdx.x == 0) trace(6);
     xch[256 + half * 128 + r] = l;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
 
-    if (half == 0) {  // one thread of the pair scales and stores the row
-      l += xch[256 + 128 + r];
+    {  // each thread of the pair scales and stores 8 of the row's 16 columns
+      l += xch[256 + (half ^ 1) * 128 + r];
       mbar_wait(bar_o, 0);
       if (threadIdx.x == 0) trace(7);
       tc_fence_after();
-      float o[16];
-      tc_ld16(tmem_o + lane_addr, o);
+      float o[8];
+      tc_ld8(tmem_o + lane_addr + 8 * half, o);
       const float inv = 1.0f / l;
       if (i < Tq) {
-        const int64_t row = int64_t(b) * Tq + i;
+        const int64_t off = (int64_t(b) * Tq + i) * D + h * HD + 8 * half;
 #pragma unroll
-        for (int c = 0; c < HD; c += 4) {
-          const float4 ov = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
-          if (A.out) *reinterpret_cast<float4*>(A.out + row * D + h * HD + c) = ov;
-          if (A.out_planes) store_planes4(A.out_planes, int64_t(P.B) * Tq * D, row * D + h * HD + c, ov, FMT);
+        for (int c = 0; c < 8; ++c) o[c] *= inv;
+        if (A.out) {
+          *reinterpret_cast<float4*>(A.out + off) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(A.out + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (A.out_planes) {
+          uint4 ph, pl;
+          split2<FMT>(o[0], o[1], ph.x, pl.x);
+          split2<FMT>(o[2], o[3], ph.y, pl.y);
+          split2<FMT>(o[4], o[5], ph.z, pl.z);
+          split2<FMT>(o[6], o[7], ph.w, pl.w);
+          *reinterpret_cast<uint4*>(A.out_planes + off) = ph;
+          *reinterpret_cast<uint4*>(A.out_planes + int64_t(P.B) * Tq * D + off) = pl;
         }
       }
     }

@@ -7,7 +7,7 @@ dev = "cuda"
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
 lib = L.load()
 NAMES = ["start", "setup done", "TMA issued", "Q/K landed", "S ready", "row max done", "P written", "O ready", "row stored", "all done"]
-B, T, H, D = 8, 200, 16, 256
+B, T, H, D = (int(sys.argv[1]) if len(sys.argv) > 1 else 8), 200, 16, 256
 g = torch.Generator().manual_seed(0)
 qkv = [torch.randn(B * T, 3 * D, generator=g).to(dev) for _ in range(3)]
 km = torch.ones(B, T, dtype=torch.uint8, device=dev)
