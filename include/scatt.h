@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SCATT_ABI_VERSION 1
+#define SCATT_ABI_VERSION 2
 #define SCATT_MAX_GROUP 4 /* problems per grouped launch (the 3 anatomical streams + spare) */
 #define SCATT_MAX_FINITE 16 /* tensors per scatt_finite_check call */
 
@@ -149,6 +149,10 @@ typedef struct scatt_linear_problem {
   const float* ln_b;     /* [N] */
   float* y;              /* [M, N] fp32, row stride ldy; may be NULL if y_planes is given and no LayerNorm scratch is needed */
   void* y_planes;        /* [2][M][N] split planes or NULL */
+  const void* residual_planes; /* the residual as [2][M][N] split planes (hi + lo is added) when `residual` is NULL:
+                                * lets a residual stream live in planes only.  Large-batch LayerNorm GEMM of the
+                                * tcgen05 engine only: N = 256, M > 74 * 128 rows, RES_BEFORE_LN, no
+                                * pre-activation / column scaling */
 } scatt_linear_problem;
 
 int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx,

@@ -48,7 +48,7 @@ class Epilogue(C.Structure):
 class LinearProblem(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_planes", C.c_void_p), ("w", C.c_void_p), ("w_planes", C.c_void_p), ("bias", C.c_void_p),
-        ("residual", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("y", C.c_void_p), ("y_planes", C.c_void_p),
+        ("residual", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("y", C.c_void_p), ("y_planes", C.c_void_p), ("residual_planes", C.c_void_p),
     ]
 
 
@@ -133,7 +133,7 @@ def load(build_if_missing: bool = True):
         if missing:
             raise ScattError(f"{LIB_PATH} lacks symbols {missing}")
         _declare(lib)
-        if lib.scatt_abi_version() != 1:
+        if lib.scatt_abi_version() != 2:
             raise ScattError("libscatt ABI version mismatch; rebuild with python -m scattennet_b200.build --force")
         _lib = lib
         return lib

@@ -46,6 +46,7 @@ struct TcProblem {
   const float* ln_b;
   float* y;
   uint16_t* y_planes;
+  const uint16_t* res_planes;  // residual as [2][M][N] split planes (used when `residual` is null)
 };
 
 struct alignas(64) TcParams {
@@ -113,6 +114,59 @@ __device__ __forceinline__ void tile_add(const EpiCtx& E, const float4 (&r)[8], 
   for (int h = 0; h < 2; ++h) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(E.stage + (8 * i + sub) * kEpiLd + c4) = r[h * 4 + i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(E.stage + E.lane * kEpiLd + j);
+      v[h * 16 + j] += t.x, v[h * 16 + j + 1] += t.y, v[h * 16 + j + 2] += t.z, v[h * 16 + j + 3] += t.w;
+    }
+    __syncwarp();
+  }
+}
+
+// The same for a residual kept as 16-bit split planes [2][M][N]: r[i] <- 8 hi halves, r[4 + i] <- 8 lo halves
+// of row 8 i + lane / 4, columns c0 + 8 (lane % 4) ... (raw bits in the float4 registers).
+__device__ __forceinline__ void tile_fetch_planes(const EpiCtx& E, const uint16_t* __restrict__ g, int64_t plane_stride, int64_t ld,
+                                                  int c0, float4 (&r)[8]) {
+  const int sub = E.lane >> 2, q = E.lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 8 * i + sub;
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f), r[4 + i] = r[i];
+    if (row < E.rows_valid) {
+      const uint16_t* p = g + (E.row0 + row) * ld + c0 + q * 8;
+      r[i] = *reinterpret_cast<const float4*>(p);
+      r[4 + i] = *reinterpret_cast<const float4*>(p + plane_stride);
+    }
+  }
+}
+__device__ __forceinline__ float2 unpack_pair(float hi_bits, float lo_bits, int fmt) {
+  const uint32_t h = __float_as_uint(hi_bits), l = __float_as_uint(lo_bits);
+  float2 a, b;
+  if (fmt == SCATT_PLANE_F16) {
+    a = __half22float2(*reinterpret_cast<const __half2*>(&h));
+    b = __half22float2(*reinterpret_cast<const __half2*>(&l));
+  } else {
+    a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h));
+    b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l));
+  }
+  return make_float2(a.x + b.x, a.y + b.y);
+}
+// v[32] (thread-per-row) += hi + lo of the fetched plane tile, transposed through the staging tile
+__device__ __forceinline__ void tile_add_planes(const EpiCtx& E, const float4 (&r)[8], float* v, int fmt) {
+  const int sub = E.lane >> 2, q = E.lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if ((q >> 1) == h) {  // this lane's 8 columns belong to the 16-column half being transposed
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 p0 = unpack_pair(r[i].x, r[4 + i].x, fmt), p1 = unpack_pair(r[i].y, r[4 + i].y, fmt);
+        const float2 p2 = unpack_pair(r[i].z, r[4 + i].z, fmt), p3 = unpack_pair(r[i].w, r[4 + i].w, fmt);
+        float* dst = E.stage + (8 * i + sub) * kEpiLd + (q & 1) * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(p0.x, p0.y, p1.x, p1.y);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(p2.x, p2.y, p3.x, p3.y);
+      }
+    }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -255,25 +309,45 @@ __device__ __forceinline__ bool chunk_pre(const TcParams& P, const TcProblem& Q,
 }
 
 // Runs on the epilogue warps while TMA / MMA start: accumulator <- bias + residual.
-template <int BN, int EW>
-__device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
-                                             int half) {
+// PL: the residual stream lives in split planes only (two straight-line copies of the routine, picked once).
+template <int BN, int EW, bool PL>
+__device__ __forceinline__ void acc_pre_init_impl(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
+                                                  int half) {
   constexpr int kMine = BN / 32 / (EW / 4);  // 32-column chunks per warp
   float4 r[2][8];
+  const int64_t ps = P.M * int64_t(P.N);
+  auto fetch = [&](int c0, float4 (&dst)[8]) {
+    if constexpr (PL) tile_fetch_planes(E, Q.res_planes, ps, P.N, c0, dst);
+    else tile_fetch(E, Q.residual, P.ldres, c0, dst);
+  };
   int c = half * kMine;
-  if (n0 + c * 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + c * 32, r[0]);
+  if (n0 + c * 32 < P.N) fetch(n0 + c * 32, r[0]);
 #pragma unroll 2
   for (int i = 0; i < kMine; ++i) {
     const int cl = (half * kMine + i) * 32;
     if (n0 + cl >= P.N) break;
-    if (i + 1 < kMine && n0 + cl + 32 < P.N) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
+    if (i + 1 < kMine && n0 + cl + 32 < P.N) fetch(n0 + cl + 32, r[(i + 1) & 1]);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
     if (Q.bias) add_cols(v, E.col_bias + cl);
-    tile_add(E, r[i & 1], v);
+    if constexpr (PL) tile_add_planes(E, r[i & 1], v, P.fmt);
+    else tile_add(E, r[i & 1], v);
     tc_st32(tmem_acc + cl, v);
   }
+}
+// Only the large-batch LayerNorm kernel (one CTA per 128-row tile, LN == 1) carries the plane-residual copy: the
+// small-batch kernels are latency-bound and measurably slower with the extra code in them (B=8 step +3 %).
+template <int BN, int EW, bool ALLOW_PL>
+__device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem& Q, const EpiCtx& E, uint32_t tmem_acc, int n0,
+                                             int half) {
+  if constexpr (ALLOW_PL) {
+    if (Q.residual == nullptr) {
+      acc_pre_init_impl<BN, EW, true>(P, Q, E, tmem_acc, n0, half);
+      return;
+    }
+  }
+  acc_pre_init_impl<BN, EW, false>(P, Q, E, tmem_acc, n0, half);
 }
 
 // cluster helpers (LN == 2: the row's 256 columns live in two CTAs of a cluster)
@@ -538,7 +612,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     E.stores = 0;
     const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
     if (P.pre_init) {
-      acc_pre_init<BN, EW>(P, Q, E, my_tmem, n0, half);
+      acc_pre_init<BN, EW, LN == 1>(P, Q, E, my_tmem, n0, half);
       tc_fence_before();
       mbar_arrive(acc_init_bar);
       if (threadIdx.x == 64) trace(9);
@@ -774,7 +848,11 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   P.pre_init = (res_early && P.ep.act_pre == SCATT_ACT_NONE && P.ep.scale_cols == 0) ? 1 : 0;
   for (int i = 0; i < group; ++i) {
     SCATT_REQUIRE(p[i].x_planes && p[i].w_planes, "linear(tcgen05): problem %d lacks split planes", i);
-    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual, "linear(tcgen05): residual missing");
+    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || p[i].residual_planes, "linear(tcgen05): residual missing");
+    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || (P.pre_init && fused_ln && !narrow),
+                  "linear(tcgen05): a residual given as split planes is taken by the large-batch LayerNorm kernel only "
+                  "(N = 256, more than 74 row tiles, foldable into the accumulator: residual before LayerNorm, no "
+                  "pre-activation, no column scaling)");
     SCATT_REQUIRE(!ep.layer_norm || (p[i].ln_g && p[i].ln_b), "linear(tcgen05): LayerNorm needs gamma and beta");
     SCATT_REQUIRE(!split_ln || p[i].y, "linear(tcgen05): LayerNorm with N != 256 needs y as scratch");
     SCATT_REQUIRE(p[i].y || p[i].y_planes, "linear(tcgen05): no output");
@@ -783,7 +861,8 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     rc = encode_planes_map(&P.map_b[i], p[i].w_planes, N, K, BN, fmt);
     if (rc != SCATT_OK) return rc;
     P.prob[i] = TcProblem{p[i].bias, p[i].residual, p[i].ln_g, p[i].ln_b, p[i].y,
-                          split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes)};
+                          split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes),
+                          reinterpret_cast<const uint16_t*>(p[i].residual_planes)};
     rc = encode_out_maps(&P.map_y[i], &P.map_p[i], P.prob[i].y, ldy, P.prob[i].y_planes, M, N, fmt);
     if (rc != SCATT_OK) return rc;
   }

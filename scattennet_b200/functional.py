@@ -274,14 +274,26 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
             p.x, p.w = x.f32.data_ptr(), pk.w32.data_ptr()
         p.bias = _ptr(pk.b32)
         if residuals is not None:
-            p.residual = residuals[g].data_ptr()
+            r = residuals[g]
+            if isinstance(r, Act):  # fp32 if the activation has it, else its split planes (tcgen05 engine only)
+                if r.f32 is not None:
+                    p.residual = r.f32.data_ptr()
+                elif prec.uses_planes:
+                    p.residual_planes = r.planes.data_ptr()
+                else:
+                    raise ValueError("the fp32 engine needs an fp32 residual")
+            else:
+                p.residual = r.data_ptr()
         if lns is not None:
             p.ln_g, p.ln_b = lns[g].weight.data_ptr(), lns[g].bias.data_ptr()
         p.y, p.y_planes = _ptr(y), _ptr(yp)
         outs.append(Act(y, yp))
         keep.append((x, pk))
     ldx = xs[0].f32.stride(0) if xs[0].f32 is not None else K
-    ldres = residuals[0].stride(0) if residuals is not None else N
+    r0 = residuals[0] if residuals is not None else None
+    if isinstance(r0, Act):
+        r0 = r0.f32
+    ldres = r0.stride(0) if r0 is not None else N
     esz = 2 if prec.uses_planes else 4
     name = "linear_tc_kernel" if prec.uses_planes else "linear_simt_kernel"
     with _timed(name, 2.0 * G * M * N * K, G * ((M * K + N * K) * esz + M * N * 4.0)):

@@ -73,27 +73,46 @@ class CoordinateAttention(nn.Module):
         return out[0].f32.view_as(coord_embed).to(coord_embed.dtype)
 
 
-def _attn_out_ln(prec, attns, ctx, norms, residuals: List[Act]) -> List[Act]:
+# On the tensor-core engine the residual stream between the layers of a ladder lives in split planes only:
+# an activation that is just the next GEMM's operand and the next LayerNorm's residual is written once (planes),
+# not twice (planes + fp32) - the outbound store path is what bounds these launches.  `keep_f32` asks for the
+# fp32 copy as well (module-level calls, final outputs, anything a non-GEMM consumer reads).
+
+
+# Measured: +4 % frames/s at B = 256, but -1.5 % at B = 8 (there the launches are latency-bound and the plane
+# residual's conversion sits on the critical path), so only the large-batch LayerNorm kernel implements it.
+def _keep_f32(prec, acts: List[Act], keep_f32: bool) -> bool:
+    # scatt_linear runs an N = 256 LayerNorm GEMM one CTA per 128-row tile once the row tiles of the group exceed 74
+    large = ((acts[0].rows + 127) // 128) * len(acts) > 74
+    return keep_f32 or not prec.uses_planes or not large
+
+
+def _attn_out_ln(prec, attns, ctx, norms, residuals: List[Act], keep_f32: bool = True) -> List[Act]:
+    keep_f32 = _keep_f32(prec, ctx, keep_f32)
     return F_.linear(prec, ctx, [F_.pack_of(a, "out", [a.out_proj]) for a in attns],
-                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[r.f32 for r in residuals],
-                     lns=norms)
+                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=residuals,
+                     lns=norms, out_f32=keep_f32 or not prec.uses_planes)
 
 
-def _ffn_ln(prec, mlps: Sequence[FeedForward], norms, h: List[Act]) -> List[Act]:
+def _ffn_ln(prec, mlps: Sequence[FeedForward], norms, h: List[Act], keep_f32: bool = True) -> List[Act]:
+    keep_f32 = _keep_f32(prec, h, keep_f32)
     f = F_.linear(prec, h, [F_.pack_of(m, "fc1", [m.fc1]) for m in mlps], F_.make_epilogue(act_pre=L.ACT_GELU),
                   out_f32=not prec.uses_planes)
     return F_.linear(prec, f, [F_.pack_of(m, "fc2", [m.fc2]) for m in mlps],
-                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[x.f32 for x in h], lns=norms)
+                     F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=h, lns=norms,
+                     out_f32=keep_f32 or not prec.uses_planes)
 
 
 def coordinate_attention_forward(prec: Precision, mods: Sequence[CoordinateAttention], xs: List[Act], B: int, T: int,
-                                 key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None) -> List[Act]:
+                                 key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None,
+                                 keep_f32: bool = True) -> List[Act]:
     """reference ``model/keypoint_module.py:61-80`` for a group of streams."""
     kind = L.ATTN_SELF if mods[0].attn_type == "self_attn" else L.ATTN_CAUSAL
+    is_self = mods[0].attn_type == "self_attn"
     ctx = attention_core(prec, [m.attn for m in mods], xs, None, B, T, T, kind, key_mask, additive)
-    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], xs)
-    if mods[0].attn_type == "self_attn":
-        h = _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h)
+    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], xs, keep_f32 and not is_self)
+    if is_self:
+        h = _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h, keep_f32)
     return h
 
 
@@ -120,11 +139,11 @@ class CoordinatesMerge(nn.Module):
 
 def coordinates_merge_forward(prec: Precision, mods: Sequence[CoordinatesMerge], ys: List[Act], xs: Optional[List[Act]],
                               kv_views, B: int, Tq: int, Tk: int, key_mask: Optional[torch.Tensor],
-                              additive: Optional[torch.Tensor] = None) -> List[Act]:
+                              additive: Optional[torch.Tensor] = None, keep_f32: bool = True) -> List[Act]:
     """reference ``model/keypoint_module.py:97-115`` for a group of streams."""
     ctx = attention_core(prec, [m.attn for m in mods], ys, xs, B, Tq, Tk, L.ATTN_CROSS, key_mask, additive, kv_views)
-    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], ys)
-    return _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h)
+    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], ys, False)
+    return _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h, keep_f32)
 
 
 class SeparativeCoordinateAttention(nn.Module):
@@ -151,7 +170,7 @@ class SeparativeCoordinateAttention(nn.Module):
         s = F_.posembed_layernorm(prec, s_in, self.self_pos_embed.weight, self.first_self_norm, b, t)
         c = F_.posembed_layernorm(prec, c_in, self.causal_pos_embed.weight, self.first_causal_norm, b, t)
         km = F_.key_mask_u8(attention_mask)  # the reference requires a [B,T] mask here too (model/utils.py:5)
-        outs, selfs = sca_forward(prec, [self], [s], [c], km, b, t)
+        outs, selfs = sca_forward(prec, [self], [s], [c], km, b, t, need_self_f32=return_attn_map)
         outputs = outs[0].f32.view(b, t, d).to(x_embed.dtype)
         if return_attn_map:
             return {"outputs": outputs, "self_attn_map": selfs[0].f32.view(b, t, d).to(x_embed.dtype),
@@ -171,7 +190,7 @@ def _side_stream(device) -> torch.cuda.Stream:
 
 
 def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], s: List[Act], c: List[Act],
-                key_mask: torch.Tensor, B: int, T: int):
+                key_mask: torch.Tensor, B: int, T: int, need_self_f32: bool = False):
     """Layer loops of reference ``model/keypoint_module.py:176-187`` on already
     position-embedded + normalised inputs, for a group of streams."""
     n = len(mods[0].self_attn_layers)
@@ -186,7 +205,7 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
-            c_first = coordinate_attention_forward(prec, [m.causal_attn_layers[0] for m in mods], c, B, T, key_mask)
+            c_first = coordinate_attention_forward(prec, [m.causal_attn_layers[0] for m in mods], c, B, T, key_mask, keep_f32=False)
             join = torch.cuda.Event()
             join.record(side)
         for a in list(c) + list(c_first):  # tensors that cross streams: keep the allocator honest in eager mode
@@ -195,7 +214,8 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
                     t.record_stream(side)
                     t.record_stream(main)
     for i in range(n):
-        s = coordinate_attention_forward(prec, [m.self_attn_layers[i] for m in mods], s, B, T, key_mask)
+        s = coordinate_attention_forward(prec, [m.self_attn_layers[i] for m in mods], s, B, T, key_mask,
+                                         keep_f32=need_self_f32 and i == n - 1)
     # K / V of every merge layer read the same final self map: one N = n*2*D GEMM per stream
     packs = []
     for m in mods:
@@ -212,12 +232,13 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
             torch.cuda.current_stream().wait_event(join)
             c = c_first
         else:
-            c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask)
+            c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask, keep_f32=False)
         if kv_planes:
             kv_views = [((kv.planes, 2 * i * d), (kv.planes, (2 * i + 1) * d)) for kv in kv_all]
         else:
             kv_views = [(kv.f32[:, 2 * i * d : (2 * i + 1) * d], kv.f32[:, (2 * i + 1) * d : (2 * i + 2) * d]) for kv in kv_all]
-        c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask)
+        c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask,
+                                      keep_f32=i == n - 1)  # the ladder's result feeds the residual network in fp32
     return c, s
 
 

@@ -138,6 +138,38 @@ def test_linear_multi_wave_dual_cta_path(mode, epi, shape):
         assert float((rec - out.f32).abs().max()) <= 2.0 ** (-21 if mode.startswith("fp16") else -15) * float(out.f32.abs().max()) + 1e-7
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
+@pytest.mark.parametrize("shape", [(128 * 80 + 17, 256, 256), (128 * 75, 256, 768)])
+def test_linear_residual_from_planes(mode, shape):
+    """A residual stream that lives in split planes only (no fp32 copy): `residual_planes` must give the result of
+    the fp32 residual it was split from (large-batch LayerNorm kernel), and the output may be planes only as well."""
+    M, N, K = shape
+    prec = F_.get_precision(mode)
+    x = rnd(M, K, seed=1)
+    lin = make_linear(N, K, 2)
+    ln = torch.nn.LayerNorm(N).to(DEV)
+    res = rnd(M, N, seed=4)
+    res_planes = F_.split_planes(res, prec)
+    res_rec = res_planes[0].float() + res_planes[1].float()  # what the planes hold (== res to 2^-21 / 2^-15 relative)
+    for layer_norm in (True,):
+        ep = F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=layer_norm)
+        kw = dict(lns=[ln] if layer_norm else None)
+        want = F_.linear(prec, [Act(x)], [F_.PackedLinear([lin], None, None)], ep, residuals=[res_rec], **kw)[0]
+        got = F_.linear(prec, [Act(x)], [F_.PackedLinear([lin], None, None)], ep, residuals=[Act(None, res_planes)],
+                        out_f32=False, **kw)[0]
+        assert got.f32 is None and got.planes is not None
+        assert torch.equal(got.planes, want.planes), (mode, shape, layer_norm)
+
+
+def test_linear_residual_from_planes_rejected_when_not_foldable():
+    prec = F_.get_precision("fp16x3")
+    x, res = rnd(64, 256, seed=1), rnd(64, 256, seed=2)
+    with pytest.raises(Exception, match="large-batch LayerNorm kernel"):  # 64 rows: the 2-CTA cluster kernel would run
+        F_.linear(prec, [Act(x)], [F_.PackedLinear([make_linear(256, 256, 2)], None, None)],
+                  F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[Act(None, F_.split_planes(res, prec))],
+                  lns=[torch.nn.LayerNorm(256).to(DEV)])
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16x1"])
 def test_linear_grouped_matches_single(mode):
     prec = F_.get_precision(mode)

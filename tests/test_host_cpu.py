@@ -25,7 +25,7 @@ def test_library_exports_header_symbols():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.scatt_abi_version() == 1
+    assert lib.scatt_abi_version() == 2
     assert b"sm_100a" in lib.scatt_version()
 
 
@@ -33,7 +33,7 @@ def test_ctypes_structs_match_header_sizes():
     import ctypes as C
 
     assert C.sizeof(_lib.Epilogue) == 32
-    assert C.sizeof(_lib.LinearProblem) == 80
+    assert C.sizeof(_lib.LinearProblem) == 88
     assert C.sizeof(_lib.AttentionProblem) == 56
     assert C.sizeof(_lib.FrontendStream) == 8 + 4 + 8 + 4 + 7 * 16 + 8  # idx, n, coord[2], pad, 7 ptr pairs, gathered
 
