@@ -323,6 +323,33 @@ def run_ours(args):
                 tiers[tier] = {"ms_per_step": ms4, "value": args.batch * T / (ms4 * 1e-3), "unit": UNIT}
                 del m3
             consumers["precision_tiers"] = tiers
+            # ---- CTC beam decode (beam 5, the reference's utils.ctc_decode) on the device: kernel time, and the
+            # end-to-end step that returns gloss ids instead of logits (host tensors in, token ids out)
+            lens = torch.full((args.batch,), out["fuse_coord_gloss_logits"].shape[1], dtype=torch.int32, device=dev)
+            for _ in range(3):
+                F_.ctc_beam_decode(out["fuse_coord_gloss_logits"], lens, 5)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(10):
+                F_.ctc_beam_decode(out["fuse_coord_gloss_logits"], lens, 5)
+            e1.record()
+            torch.cuda.synchronize()
+            lens_host = lens.cpu()
+            for _ in range(3):
+                model.forward_host(kp_pin, mask_pin, device=dev, decode_beam=5, input_lengths=lens_host)
+            ev5 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            torch.cuda.synchronize()
+            for a0, a1 in ev5:
+                flush.zero_()
+                a0.record()
+                model.forward_host(kp_pin, mask_pin, device=dev, decode_beam=5, input_lengths=lens_host)
+                a1.record()
+            torch.cuda.synchronize()
+            ms5 = sum(a0.elapsed_time(a1) for a0, a1 in ev5) / args.steps
+            consumers["ctc_beam_decode"] = {"kernel_us": 1e3 * e0.elapsed_time(e1) / 10, "beam": 5,
+                                            "e2e_gloss_ids_ms_per_step": ms5, "e2e_gloss_ids_value": args.batch * T / (ms5 * 1e-3),
+                                            "d2h_bytes_per_step": int(args.batch * (out["fuse_coord_gloss_logits"].shape[1] + 1) * 4)}
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)

@@ -263,6 +263,17 @@ int scatt_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int 
 int scatt_finite_check(const float* const* tensors_host, const int64_t* sizes_host, int count, int* flags_dev,
                        void* stream);
 
+/* CTC prefix beam search, top path, on logits [B, T, V] fp32 (contiguous; class 0 = blank, as nn.CTCLoss(blank=0)
+ * and the reference's logits have it): the device-side form of utils.py:164-189 ctc_decode - rotation of the blank
+ * to TensorFlow's position, tf.nn.ctc_beam_search_decoder(beam_width = beam, top_paths = 1), + 1, and the
+ * groupby that collapses consecutive duplicates - so that only gloss ids leave the GPU instead of the logits.
+ *   lengths  [B] int32 valid frames per sequence (NULL = T for all);
+ *   out_ids  [B, T] int32: the decoded gloss ids (original class numbering, 1..V-1), padded with -1;
+ *   out_len  [B] int32 number of ids; out_score [B] log-probability of the winning prefix (may be NULL).
+ * beam <= 16; shared memory grows with V, T and beam (V = 1120, T = 512, beam = 5: ~75 KB). */
+int scatt_ctc_beam_decode(const float* logits, int B, int T, int V, const int32_t* lengths, int beam, int32_t* out_ids,
+                          int32_t* out_len, float* out_score, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ CUDA kernels (``csrc/``) reached through the C ABI of ``libscatt.so``
 
 from .alignment_module import AlignmentModule  # noqa: F401
 from .attention import BaseAttention, CrossAttention, SelfAttention, SelfCausalAttention  # noqa: F401
+from .decode import ctc_decode  # noqa: F401
 from .config import PHOENIX_2014, PHOENIX_2014T, model_config  # noqa: F401
 from .encoder import Encoder, EncoderLayer  # noqa: F401
 from .functional import PRECISIONS, get_precision, set_default_precision  # noqa: F401

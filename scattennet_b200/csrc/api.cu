@@ -157,4 +157,9 @@ int scatt_finite_check(const float* const* tensors_host, const int64_t* sizes_ho
   return launch_finite_check(tensors_host, sizes_host, count, flags_dev, as_stream(stream));
 }
 
+int scatt_ctc_beam_decode(const float* logits, int B, int T, int V, const int32_t* lengths, int beam, int32_t* out_ids,
+                          int32_t* out_len, float* out_score, void* stream) {
+  return launch_ctc_beam(logits, B, T, V, lengths, beam, out_ids, out_len, out_score, as_stream(stream));
+}
+
 }  // extern "C"

@@ -185,6 +185,8 @@ int launch_lstm_bidir(const float* gates_x, int64_t ldg, const float* w_hh, floa
                       int64_t B, int T, int H, int fmt, cudaStream_t s);
 int launch_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int time_major, float lo, float hi, float* out,
                        cudaStream_t s);
+int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths, int beam, int* out_ids, int* out_len,
+                    float* out_score, cudaStream_t s);
 int launch_finite_check(const float* const* tensors, const int64_t* sizes, int count, int* flags, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);

@@ -473,3 +473,20 @@ def finite_flags(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     sizes = (C.c_int64 * n)(*[t.numel() for t in ts])
     L.check(L.load().scatt_finite_check(ptrs, sizes, n, flags.data_ptr(), _stream()), "scatt_finite_check")
     return flags
+
+
+def ctc_beam_decode(logits: torch.Tensor, lengths: Optional[torch.Tensor] = None, beam: int = 5):
+    """CTC prefix beam search (top path) on ``logits [B,T,V]`` (class 0 = blank).  Returns device tensors
+    ``(ids [B,T] int32 padded with -1, n_ids [B] int32, log-probability [B] fp32)`` - no host sync."""
+    require_cuda(logits)
+    B, T, V = logits.shape
+    x = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+    dev = x.device
+    ids = torch.empty(B, T, dtype=torch.int32, device=dev)
+    n_ids = torch.empty(B, dtype=torch.int32, device=dev)
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    lens = None if lengths is None else lengths.to(device=dev, dtype=torch.int32).contiguous()
+    with _timed("ctc_beam_kernel", 0.0, float(B) * T * V * 4):
+        L.check(L.load().scatt_ctc_beam_decode(x.data_ptr(), B, T, V, _ptr(lens), beam, ids.data_ptr(), n_ids.data_ptr(),
+                                               score.data_ptr(), _stream()), "scatt_ctc_beam_decode")
+    return ids, n_ids, score

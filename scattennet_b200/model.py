@@ -150,7 +150,7 @@ class MSCAEncoder(nn.Module):
         return out
 
     def forward_host(self, keypoints: torch.Tensor, mask: torch.Tensor, heads=("fuse_coord_gloss_logits",), device=None,
-                     gather: bool = False):
+                     gather: bool = False, decode_beam: int = 0, input_lengths: Optional[torch.Tensor] = None):
         """End-to-end call for host-resident batches (the collator -> device path).
 
         ``keypoints [B,T,K,2]`` / ``mask [B,T]`` are CPU tensors.  Only the joints the three streams read
@@ -159,7 +159,10 @@ class MSCAEncoder(nn.Module):
         tensors.  Returns ``{name: host tensor}``; call ``torch.cuda.current_stream().synchronize()`` (or use
         the tensors after any sync) before reading them.  ``gather=True`` (inside an initialised
         ``torch.distributed`` job): the first head is all-gathered over NVLink before the read-back, and only
-        rank 0 reads the gathered ``[world*B, T', V]`` logits (the others read their own shard)."""
+        rank 0 reads the gathered ``[world*B, T', V]`` logits (the others read their own shard).
+        ``decode_beam > 0``: the first head is CTC-decoded on the device (prefix beam search, the reference's
+        ``utils.ctc_decode``; ``input_lengths [B]`` = valid pooled frames per sequence) and only
+        ``gloss_ids [B,T'] int32`` (padded with -1) and ``gloss_len [B]`` come back instead of logits."""
         if self.training:
             raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward")
         dev = device or next(self.parameters()).device
@@ -191,6 +194,15 @@ class MSCAEncoder(nn.Module):
             if dist.get_rank() == 0:
                 out = dict(out)
                 out[heads[0]] = full
+        if decode_beam > 0:
+            lens = st.get("len_dev")
+            if input_lengths is not None:
+                if lens is None:
+                    lens = st["len_dev"] = torch.empty(b, dtype=torch.int32, device=dev)
+                lens.copy_(input_lengths.to(torch.int32), non_blocking=True)
+            ids, n_ids, _ = F_.ctc_beam_decode(out[heads[0]], lens if input_lengths is not None else None, decode_beam)
+            out = {"gloss_ids": ids, "gloss_len": n_ids}
+            heads = ("gloss_ids", "gloss_len")
         res = {}
         for k in heads:
             pin = st["out_pin"].get(k)

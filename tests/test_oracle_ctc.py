@@ -1,0 +1,63 @@
+"""Known-answer checks of the CTC beam-search restatement (oracle/ctc_oracle.py).  TensorFlow - where the
+reference's decode lives (utils.py:173-178) - is absent here, so the pin is the mathematics: with a beam that
+holds every prefix the search is exact and must reproduce a brute-force enumeration of all alignments."""
+
+import itertools
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ctc_oracle as C
+
+
+@pytest.mark.parametrize("t_len,v,seed", [(1, 3, 0), (2, 3, 1), (3, 3, 2), (4, 3, 3), (5, 3, 4), (4, 4, 5), (5, 4, 6), (6, 3, 7)])
+def test_exhaustive_beam_equals_brute_force(t_len, v, seed):
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal((t_len, v)) * 2.0).astype(np.float32)
+    want_lab, want_lp = C.brute_force_best(logits)
+    got_lab, got_lp = C.beam_search(logits, beam_width=4096)
+    assert got_lab == want_lab
+    assert abs(got_lp - want_lp) <= 1e-5
+
+
+def test_hand_computed_two_steps():
+    # V = 2 (label 0, blank 1), T = 2, uniform: P("") = 1/4 (bb), P("0") = 3/4 (0b, b0, 00)
+    logits = np.zeros((2, 2), dtype=np.float32)
+    lab, lp = C.beam_search(logits, beam_width=5)
+    assert lab == [0] and abs(lp - math.log(0.75)) <= 1e-6
+    # strongly peaked on "label, blank, label": the repeated label survives as two tokens in the raw path
+    logits = np.array([[9.0, 0.0], [0.0, 9.0], [9.0, 0.0]], dtype=np.float32)
+    lab, _ = C.beam_search(logits, beam_width=5)
+    assert lab == [0, 0]
+
+
+def test_narrow_beam_is_a_lower_bound_and_usually_exact():
+    rng = np.random.default_rng(11)
+    exact = 0
+    for _ in range(20):
+        logits = (rng.standard_normal((5, 4)) * 3.0).astype(np.float32)
+        want_lab, want_lp = C.brute_force_best(logits)
+        lab, lp = C.beam_search(logits, beam_width=5)
+        assert lp <= want_lp + 1e-5
+        exact += lab == want_lab
+    assert exact >= 18
+
+
+def test_ctc_decode_wrapper_matches_reference_post_processing():
+    """utils.py:166-188: blank 0 rotated to last, +1 afterwards, consecutive duplicates collapsed, per-sequence
+    lengths respected."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((3, 6, 5)) * 3.0).astype(np.float32)
+    lens = [6, 4, 0]
+    out = C.ctc_decode(x, 5, lens)
+    assert out[2] == []
+    for b in range(2):
+        tf_logits = np.concatenate([x[b, : lens[b], 1:], x[b, : lens[b], 0:1]], -1)
+        lab, _ = C.beam_search(tf_logits, 5)
+        assert out[b] == [k for k, _ in itertools.groupby([l + 1 for l in lab])]
+        assert all(1 <= g < 5 for g in out[b])
+    # a sequence that repeats one gloss across a blank comes back as a single gloss (the reference's groupby quirk)
+    peaked = np.full((1, 3, 3), -9.0, dtype=np.float32)
+    peaked[0, 0, 2] = peaked[0, 1, 0] = peaked[0, 2, 2] = 9.0
+    assert C.ctc_decode(peaked, 5, [3]) == [[2]]
