@@ -159,6 +159,11 @@ int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M
                  int64_t ldres, int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms,
                  void* stream);
 
+/* 1 when scatt_linear with a LayerNorm epilogue normalises inside the GEMM kernel for this shape (tcgen05
+ * engine: N = 256 always; N = 512 / 1024 by 4- / 8-CTA clusters while ceil(M / 128) * group * N / 128 <= 148),
+ * 0 when it runs the GEMM and then the row-wise tail in place on y - y is then required as scratch. */
+int scatt_linear_ln_fused(int64_t M, int N, int group, int engine);
+
 /* Row-wise tail on an fp32 [M, N] matrix: optional LayerNorm, residual after,
  * activation, clamp, split-plane export.  In-place (y == z) is allowed. */
 int scatt_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* residual, int64_t ldres,

@@ -95,6 +95,11 @@ int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M
   return SCATT_ERR_INVALID;
 }
 
+int scatt_linear_ln_fused(int64_t M, int N, int group, int engine) {
+  if (engine != SCATT_ENGINE_TCGEN05 || M < 0 || N < 1 || group < 1) return 0;
+  return linear_tc_ln_cluster(M, N, group, 1) > 0 ? 1 : 0;
+}
+
 int scatt_rowwise(const float* z, int64_t M, int N, int64_t ldz, const float* residual, int64_t ldres, const float* ln_g,
                   const float* ln_b, const scatt_epilogue* epilogue_host, float* y, int64_t ldy, void* y_planes,
                   int plane_fmt, void* stream) {

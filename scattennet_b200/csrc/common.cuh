@@ -67,6 +67,21 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// Same, as thread-block clusters of `cluster_x` CTAs along grid.x.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 // ---------------------------------------------------------------- device helpers
@@ -132,18 +147,28 @@ __device__ __forceinline__ void split16_rt(float x, int fmt, uint16_t& hi, uint1
   else split16<SCATT_PLANE_BF16>(x, hi, lo);
 }
 
+// hi/lo split of two fp32 values with the packed conversions (same roundings as split16, half the instructions).
+__device__ __forceinline__ void split_pair_rt(float a, float b, int fmt, uint32_t& hi, uint32_t& lo) {
+  if (fmt == SCATT_PLANE_F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 back = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
 // Store 4 consecutive fp32 values as split planes (8-byte stores).
 __device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t plane_stride, int64_t off, float4 v, int fmt) {
-  uint16_t h[4], l[4];
-  split16_rt(v.x, fmt, h[0], l[0]);
-  split16_rt(v.y, fmt, h[1], l[1]);
-  split16_rt(v.z, fmt, h[2], l[2]);
-  split16_rt(v.w, fmt, h[3], l[3]);
   uint2 ph, pl;
-  ph.x = h[0] | (uint32_t(h[1]) << 16);
-  ph.y = h[2] | (uint32_t(h[3]) << 16);
-  pl.x = l[0] | (uint32_t(l[1]) << 16);
-  pl.y = l[2] | (uint32_t(l[3]) << 16);
+  split_pair_rt(v.x, v.y, fmt, ph.x, pl.x);
+  split_pair_rt(v.z, v.w, fmt, ph.y, pl.y);
   *reinterpret_cast<uint2*>(planes + off) = ph;
   *reinterpret_cast<uint2*>(planes + plane_stride + off) = pl;
 }
@@ -169,6 +194,7 @@ int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int 
                        int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s);
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
                      const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s);
+int linear_tc_ln_cluster(int64_t M, int N, int group, int layer_norm);
 int debug_set_trace(void* dev_buf);
 int debug_set_trace_attention(void* dev_buf);
 int debug_set_trace_fa(void* dev_buf);

@@ -350,7 +350,7 @@ __device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem&
   acc_pre_init_impl<BN, EW, false>(P, Q, E, tmem_acc, n0, half);
 }
 
-// cluster helpers (LN == 2: the row's 256 columns live in two CTAs of a cluster)
+// cluster helpers (LN >= 2: the row's columns live in the LN CTAs of a cluster)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -368,8 +368,8 @@ __device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 
-// LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 = the row is split
-// over the two CTAs of a cluster (N == 2 BN), which exchange per-row partial statistics through DSMEM.
+// LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 / 4 / 8 = the row is split
+// over the LN CTAs of a cluster (N == LN * BN), which exchange per-row partial statistics through DSMEM.
 template <int BN, int LN, int FMT, int EW>
 __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem& Q, EpiCtx& E, uint32_t tmem_acc, int n0,
                                               int half, float2* stats, uint32_t xstats_addr, int row_in_tile) {
@@ -417,18 +417,35 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     float mean = 0.5f * (my_mean + other.x);
     const float da = my_mean - mean, db = other.x - mean;
     float m2 = my_m2 + other.y + kHalfN * (da * da + db * db);
-    if constexpr (LN == 2) {
-      cluster_wait();  // phase 1 (armed at kernel start): the peer CTA is running
-      if (half == 0) st_peer_f32x2(xstats_addr + 8u * row_in_tile, cluster_ctarank() ^ 1u, mean, m2);
-      cluster_sync_all();  // phase 2: every thread of both CTAs takes part (warps 0 / 1 after their roles)
-      float2 peer;
-      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(peer.x), "=f"(peer.y) : "r"(xstats_addr + 8u * row_in_tile) : "memory");
-      const float mc = mean;
-      mean = 0.5f * (mc + peer.x);
-      const float d1 = mc - mean, d2 = peer.x - mean;
-      m2 = m2 + peer.y + float(BN) * (d1 * d1 + d2 * d2);
+    if constexpr (LN >= 2) {
+      // the row's LN * BN columns live in the LN CTAs of the cluster: every CTA sends its (mean, m2) to every
+      // peer (both column halves hold the CTA's statistics; half h serves the peers of parity h)
+      const uint32_t rank = cluster_ctarank();
+      cluster_wait();  // phase 1 (armed at kernel start): the peer CTAs are running
+#pragma unroll
+      for (uint32_t p = 0; p < uint32_t(LN); ++p)
+        if ((p & 1u) == uint32_t(half) && p != rank) st_peer_f32x2(xstats_addr + 8u * (rank * BM + row_in_tile), p, mean, m2);
+      cluster_sync_all();  // phase 2: every thread of every CTA takes part (warps 0 / 1 after their roles)
+      float2 part[LN];
+#pragma unroll
+      for (uint32_t p = 0; p < uint32_t(LN); ++p) {
+        part[p] = make_float2(mean, m2);
+        if (p != rank)
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(part[p].x), "=f"(part[p].y) : "r"(xstats_addr + 8u * (p * BM + row_in_tile)) : "memory");
+      }
+      float msum = part[0].x, qsum = part[0].y;
+#pragma unroll
+      for (int p = 1; p < LN; ++p) msum += part[p].x, qsum += part[p].y;
+      mean = msum * (1.0f / float(LN));
+      float dsum = 0.f;
+#pragma unroll
+      for (int p = 0; p < LN; ++p) {
+        const float d = part[p].x - mean;
+        dsum = fmaf(d, d, dsum);
+      }
+      m2 = qsum + float(BN) * dsum;
     }
-    const float var = m2 / float(LN == 2 ? 2 * BN : BN);
+    const float var = m2 / float(LN >= 2 ? LN * BN : BN);
     const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
     float4 r[2][8];
@@ -473,8 +490,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t tmem_ptr_addr = acc_init_bar + 8u;
   const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][BN]
   const uint32_t stats_base = col_base + 3u * BN * 4u;               // float2[2][BM]
-  const uint32_t xstats_base = stats_base + 2u * BM * 8u;            // float2[BM] written by the peer CTA (LN == 2)
-  const uint32_t stage_base = xstats_base + BM * 8u;                 // kEpiWarps staging tiles
+  const uint32_t xstats_base = stats_base + 2u * BM * 8u;            // float2[LN][BM], slot p written by peer CTA p (LN >= 2)
+  const uint32_t stage_base = xstats_base + BM * 8u * uint32_t(LN >= 2 ? LN : 1);  // kEpiWarps staging tiles
   auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
 
@@ -516,9 +533,9 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // LN == 2: the peer CTA must be resident before anybody writes into its smem.  Only arrive here; the
+  // LN >= 2: the peer CTAs must be resident before anybody writes into their smem.  Only arrive here; the
   // matching wait sits right before the remote store, so nobody stalls on the peer's start-up.
-  if constexpr (LN == 2) cluster_arrive();
+  if constexpr (LN >= 2) cluster_arrive();
   // Everything above touched only this CTA's resources and static weights; activations follow stream order.
   pdl_launch_dependents();
   pdl_wait();
@@ -543,7 +560,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       __syncwarp();
       if (kb == 0 && lane == 0) trace(2);
     }
-    if constexpr (LN == 2) {
+    if constexpr (LN >= 2) {
       __syncwarp();
       cluster_wait();      // phase 1
       cluster_sync_all();  // phase 2: statistics exchange point of the epilogue warps
@@ -589,7 +606,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       accumulate = 1;
     }
     if (lane == 0) trace(4);
-    if constexpr (LN == 2) {
+    if constexpr (LN >= 2) {
       __syncwarp();
       cluster_wait();
       cluster_sync_all();
@@ -652,11 +669,12 @@ __global__ void __launch_bounds__(64 + 32 * 4, 2) linear_tc_dual_kernel(const __
   linear_tc_body<128, 0, FMT, 4>(P);
 }
 
-// N = 256 LayerNorm GEMM as 2-CTA clusters (one cluster per 128-row tile, BN = 128 per CTA): twice the
-// CTAs of the single-CTA variant for the small-batch regime, row statistics exchanged through DSMEM.
-template <int FMT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_ln_cluster_kernel(const __grid_constant__ TcParams P) {
-  linear_tc_body<128, 2, FMT, kEpiWarps>(P);
+// LayerNorm GEMM as CL-CTA clusters (one cluster per 128-row tile, BN = 128 per CTA, N = 128 CL = 256 / 512 /
+// 1024) for the small-batch regime: CL times the CTAs of a one-CTA-per-row-tile launch share its memory
+// traffic, row statistics exchanged through DSMEM.  The cluster shape is a launch attribute.
+template <int FMT, int CL>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_ln_cluster_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<128, CL, FMT, kEpiWarps>(P);
 }
 
 // ------------------------------------------------------------------ host side
@@ -743,15 +761,15 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   P.stages = stages;
   size_t ring = size_t(stages) * kStageBytes;
   if (ring < size_t(kEpiWarps) * 16384) ring = size_t(kEpiWarps) * 16384;  // the epilogue's output boxes reuse the ring
-  const size_t smem = ring + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 + kEpiWarps * kEpiWarpBytes;
+  const size_t smem = ring + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + (2 + (LN >= 2 ? LN : 1)) * BM * 8 + kEpiWarps * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
-  if constexpr (LN == 2) {
+  if constexpr (LN >= 2) {
     if (!attr_done.load()) {
-      SCATT_CUDA(cudaFuncSetAttribute(linear_tc_ln_cluster_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCATT_CUDA(cudaFuncSetAttribute(linear_tc_ln_cluster_kernel<FMT, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
-    (void)launch_kernel(linear_tc_ln_cluster_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
+    (void)launch_kernel_cluster(linear_tc_ln_cluster_kernel<FMT, LN>, grid, dim3(64 + 32 * kEpiWarps), smem, s, LN, P);
     return after_launch("linear_tc_ln_cluster_kernel");
   } else {
     if (!attr_done.load()) {
@@ -799,6 +817,17 @@ int debug_set_trace(void* dev_buf) {
   return SCATT_OK;
 }
 
+// CTAs that share one LayerNorm row in the tcgen05 engine: 1 = one CTA owns the row (N = 256), 2 / 4 / 8 = a
+// cluster of 128-column CTAs (N = 256 in the small-batch regime; N = 512 / 1024 while the clusters fit one
+// wave of the 148 SMs), 0 = the LayerNorm runs as a separate row-wise launch.
+int linear_tc_ln_cluster(int64_t M, int N, int group, int layer_norm) {
+  if (!layer_norm) return 0;
+  const int64_t row_tiles = ((M + BM - 1) / BM) * group;
+  if (N == 256) return row_tiles <= 74 ? 2 : 1;
+  if ((N == 512 || N == 1024) && row_tiles * (N / 128) <= 148) return N / 128;
+  return 0;
+}
+
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
                      const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s) {
   SCATT_REQUIRE(terms >= 1 && terms <= 3, "linear(tcgen05): terms must be 1, 2 or 3");
@@ -808,20 +837,21 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   SCATT_REQUIRE(ldres % 4 == 0 && ldy % 4 == 0, "linear(tcgen05): row strides must be multiples of 4");
   SCATT_REQUIRE(M < (int64_t(1) << 31), "linear(tcgen05): M too large");
   if (M == 0) return SCATT_OK;
-  const bool fused_ln = ep.layer_norm && N == 256;
-  // LayerNorm wider than one tile: GEMM with the pre-norm part of the chain, then the row-wise tail in place.
-  const bool split_ln = ep.layer_norm && !fused_ln;
   // Small-batch regime: when the 128-row tiles of all problems fill at most half of the 148 SMs, halve the
   // tile width of N = 256 outputs (LayerNorm then spans a 2-CTA cluster) so twice as many SMs share the
-  // memory traffic of the launch.
+  // memory traffic of the launch.  Rows of 512 / 1024 columns are normalised in the GEMM by 4- / 8-CTA
+  // clusters as long as the clusters fit one wave.
   const int64_t row_tiles = ((M + BM - 1) / BM) * group;
-  const bool narrow = N == 256 && row_tiles <= 74;
+  const int ln_cluster = linear_tc_ln_cluster(M, N, group, ep.layer_norm);  // CTAs sharing a LayerNorm row (0: not fused)
+  const bool fused_ln = ln_cluster > 0;
+  // LayerNorm wider than the clusters reach: GEMM with the pre-norm part of the chain, then the row-wise tail in place.
+  const bool split_ln = ep.layer_norm && !fused_ln;
   // Tile width: the candidate whose grid comes closest to one full wave of the 148 SMs without exceeding
   // it (few row tiles -> narrow tiles -> more CTAs sharing the K loop's memory traffic); the widest tile
   // when even that overflows one wave (large batches: fewer re-reads of A).
   int BN = 256;
   if (fused_ln) {
-    BN = narrow ? 128 : 256;
+    BN = ln_cluster >= 2 ? 128 : 256;
   } else {
     int64_t best = -1;
     for (int cand : {256, 128, 64}) {
@@ -849,12 +879,12 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   for (int i = 0; i < group; ++i) {
     SCATT_REQUIRE(p[i].x_planes && p[i].w_planes, "linear(tcgen05): problem %d lacks split planes", i);
     SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || p[i].residual_planes, "linear(tcgen05): residual missing");
-    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || (P.pre_init && fused_ln && !narrow),
+    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || (P.pre_init && ln_cluster == 1),
                   "linear(tcgen05): a residual given as split planes is taken by the large-batch LayerNorm kernel only "
                   "(N = 256, more than 74 row tiles, foldable into the accumulator: residual before LayerNorm, no "
                   "pre-activation, no column scaling)");
     SCATT_REQUIRE(!ep.layer_norm || (p[i].ln_g && p[i].ln_b), "linear(tcgen05): LayerNorm needs gamma and beta");
-    SCATT_REQUIRE(!split_ln || p[i].y, "linear(tcgen05): LayerNorm with N != 256 needs y as scratch");
+    SCATT_REQUIRE(!split_ln || p[i].y, "linear(tcgen05): LayerNorm that is not fused (scatt_linear_ln_fused) needs y as scratch");
     SCATT_REQUIRE(p[i].y || p[i].y_planes, "linear(tcgen05): no output");
     int rc = encode_planes_map(&P.map_a[i], p[i].x_planes, M, K, BM, fmt);
     if (rc != SCATT_OK) return rc;
@@ -867,7 +897,10 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     if (rc != SCATT_OK) return rc;
   }
   int rc;
-  if (fused_ln) rc = narrow ? launch_bn<128, 2>(P, group, s) : launch_bn<256, 1>(P, group, s);
+  if (fused_ln)
+    rc = ln_cluster == 1 ? launch_bn<256, 1>(P, group, s)
+       : ln_cluster == 2 ? launch_bn<128, 2>(P, group, s)
+       : ln_cluster == 4 ? launch_bn<128, 4>(P, group, s) : launch_bn<128, 8>(P, group, s);
   else if (dual) rc = fmt == SCATT_PLANE_F16 ? launch_dual_fmt<SCATT_PLANE_F16>(P, group, s) : launch_dual_fmt<SCATT_PLANE_BF16>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));
   if (rc != SCATT_OK || !split_ln) return rc;

@@ -44,6 +44,47 @@ __global__ void __launch_bounds__(kLsThreads) log_softmax_kernel(const float* __
   for (int i = threadIdx.x; i < V; i += kLsThreads) orow[i] = fminf(fmaxf(xr[i] - lse, lo), hi);
 }
 
+// V <= 1536 with 16-byte aligned rows: one warp owns a row, which stays in registers as float4 chunks between
+// the max, the exp-sum and the store pass (one global read, warp-shuffle reductions, no block barrier).
+constexpr int kLsVec = 12;
+
+__global__ void __launch_bounds__(256) log_softmax_warp_kernel(const float* __restrict__ x, int64_t ldx, int V, int B, int T,
+                                                               int time_major, float lo, float hi, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t M = int64_t(B) * T, warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = V >> 2;
+  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+    const float* xr = x + row * ldx;
+    float4 v[kLsVec];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kLsVec; ++i)
+      if (lane + 32 * i < nvec) {
+        v[i] = *reinterpret_cast<const float4*>(xr + 4 * (lane + 32 * i));
+        mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+      }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kLsVec; ++i)
+      if (lane + 32 * i < nvec) sum += (expf(v[i].x - mx) + expf(v[i].y - mx)) + (expf(v[i].z - mx) + expf(v[i].w - mx));
+    sum = warp_sum(sum);
+    const float lse = mx + logf(sum);
+    const int b = int(row / T), t = int(row % T);
+    float* orow = out + (time_major ? (int64_t(t) * B + b) : row) * V;
+#pragma unroll
+    for (int i = 0; i < kLsVec; ++i)
+      if (lane + 32 * i < nvec) {
+        float4 o;
+        o.x = fminf(fmaxf(v[i].x - lse, lo), hi), o.y = fminf(fmaxf(v[i].y - lse, lo), hi);
+        o.z = fminf(fmaxf(v[i].z - lse, lo), hi), o.w = fminf(fmaxf(v[i].w - lse, lo), hi);
+        *reinterpret_cast<float4*>(orow + 4 * (lane + 32 * i)) = o;
+      }
+  }
+}
+
 struct FiniteGroup {
   const float* p[SCATT_MAX_FINITE];
   int64_t n[SCATT_MAX_FINITE];
@@ -68,6 +109,14 @@ int launch_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int
   SCATT_REQUIRE(logits && out && V >= 1 && ld >= V, "log_softmax: bad argument");
   SCATT_REQUIRE(lo <= hi, "log_softmax: clamp range [%g, %g] is empty", double(lo), double(hi));
   if (int64_t(B) * T == 0) return SCATT_OK;
+  const bool vec = V % 4 == 0 && V <= 4 * 32 * kLsVec && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec) {
+    int64_t blocks = (int64_t(B) * T + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    (void)launch_kernel(log_softmax_warp_kernel, dim3(unsigned(blocks)), dim3(256), 0, s, logits, ld, V, B, T, time_major, lo, hi, out);
+    return after_launch("log_softmax_warp_kernel");
+  }
   (void)launch_kernel(log_softmax_kernel, dim3(unsigned(int64_t(B) * T)), dim3(kLsThreads), 0, s, logits, ld, V, B, T,
                       time_major, lo, hi, out);
   return after_launch("log_softmax_kernel");

@@ -36,6 +36,7 @@ __device__ __forceinline__ RowStats row_stats(const float4* v, int nvec_row, int
   return {mean, rsqrtf(var + eps)};
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -138,72 +139,168 @@ __global__ void __launch_bounds__(256) posembed_ln_kernel(const float* __restric
 
 // ---------------------------------------------------------------- K1 front end
 // One CTA = one anatomical stream; W^T of both coordinate mappings staged in
-// shared memory once, then each warp walks frames: lane j loads joint j's
+// shared memory once, then each warp walks groups of R frames: lane j loads joint j's
 // (x, y) pair straight from keypoints[b,t,idx[j],:] (the region gather),
 // broadcasts it by shuffle, and every lane accumulates its 8 output channels
-// for both branches.  D is fixed at 256 (8 channels per lane as 2 float4).
+// of R frames for both branches (packed fp32 FMAs; a weight vector read from
+// shared memory serves R frames).  D is fixed at 256 (8 channels per lane).
+//
+// Outputs leave through the bulk-copy engine: a warp writes two finished rows
+// (fp32 + hi plane + lo plane = 4 KB) into its shared-memory staging buffer and
+// one lane hands them over with cp.async.bulk (shared -> global, contiguous
+// because consecutive rows are).  With st.global the kernel sat at the SM's
+// LSU store path (~11 B/clk/SM of the ~16 measured, 50 % of the HBM rate); the
+// bulk engine moves ~27 B/clk/SM.
 struct FrontendParams {
   scatt_frontend_stream s[SCATT_MAX_GROUP];
+  int32_t cta_begin[SCATT_MAX_GROUP + 1];  // CTAs [cta_begin[g], cta_begin[g + 1]) work on stream g
 };
 
-__global__ void __launch_bounds__(256) frontend_kernel(const float* __restrict__ kp, int B, int T, int K,
-                                                       FrontendParams prm, int fmt, int wt_stride) {
+constexpr int kFeWarps = 8;
+constexpr int kFeStageRows = 2;                              // rows per bulk hand-over
+constexpr int kFeBufBytes = kFeStageRows * (1024 + 2 * 512); // fp32 rows | hi rows | lo rows
+constexpr int kFeStageBytes = kFeWarps * 2 * kFeBufBytes;    // two buffers per warp
+
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+
+template <int R>  // frames per warp pass: every staged weight vector is used for R frames
+__global__ void __launch_bounds__(32 * kFeWarps, 2) frontend_kernel(const float* __restrict__ kp, int B, int T, int K,
+                                                                    const __grid_constant__ FrontendParams prm, int fmt, int wt_stride) {
   constexpr int D = 256;
-  extern __shared__ float smem[];
-  const scatt_frontend_stream& S = prm.s[blockIdx.y];
+  static_assert(R == 1 || R % kFeStageRows == 0, "R is one row or whole staging buffers");
+  extern __shared__ __align__(128) float smem[];
+  int g = 0;
+  while (g + 1 < SCATT_MAX_GROUP && int(blockIdx.x) >= prm.cta_begin[g + 1]) ++g;
+  const scatt_frontend_stream& S = prm.s[g];
+  const int cta = blockIdx.x - prm.cta_begin[g], nctas = prm.cta_begin[g + 1] - prm.cta_begin[g];
   const int nj = S.n_joints;
   float* wt[2] = {smem, smem + wt_stride};  // [nj][D] transposed mapping weights per branch
   for (int br = 0; br < 2; ++br)  // the host passes W^T [nj][D]: a straight, coalesced copy
     for (int i = threadIdx.x * 4; i < nj * D; i += blockDim.x * 4)
       *reinterpret_cast<float4*>(wt[br] + i) = *reinterpret_cast<const float4*>(S.map_wt[br] + i);
-  pdl_launch_dependents();
-  pdl_wait();  // weights above are static; keypoints / outputs below follow stream order
-  __syncthreads();
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int64_t M = int64_t(B) * T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(smem + 2 * wt_stride) + warp * 2 * kFeBufBytes;
+  const uint32_t stage_addr = uint32_t(__cvta_generic_to_shared(stage));
   const int my_joint = lane < nj ? S.joint_idx[lane] : 0;
   const int c0 = 4 * lane, c1 = 128 + 4 * lane;
+  // per-lane column parameters (static weights, like the staging above: before the dependency wait)
+  float4 bias[2][2], gam[2][2], bet[2][2];
+#pragma unroll
+  for (int br = 0; br < 2; ++br) {
+    bias[br][0] = ld4(S.map_b[br] + c0), bias[br][1] = ld4(S.map_b[br] + c1);
+    gam[br][0] = ld4(S.ln_g[br] + c0), gam[br][1] = ld4(S.ln_g[br] + c1);
+    bet[br][0] = ld4(S.ln_b[br] + c0), bet[br][1] = ld4(S.ln_b[br] + c1);
+  }
+  pdl_launch_dependents();
+  pdl_wait();  // everything above is static; keypoints / outputs below follow stream order
+  __syncthreads();
 
-  for (int64_t row = int64_t(blockIdx.x) * nwarp + warp; row < M; row += int64_t(gridDim.x) * nwarp) {
-    const int t = int(row % T);
-    float2 xy = make_float2(0.f, 0.f);
-    if (lane < nj) {
-      xy = *reinterpret_cast<const float2*>(kp + (row * K + my_joint) * 2);
-      if (S.gathered) *reinterpret_cast<float2*>(S.gathered + (row * nj + lane) * 2) = xy;
+  const int64_t M = int64_t(B) * T;
+  const int64_t ngroups = (M + R - 1) / R;
+  uint32_t handed = 0;  // bulk groups committed by this warp (selects the staging buffer)
+  for (int64_t grp = int64_t(cta) * kFeWarps + warp; grp < ngroups; grp += int64_t(nctas) * kFeWarps) {
+    const int64_t row0 = grp * R;
+    const int t0 = int(row0 % T);
+    float2 xy[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      xy[r] = make_float2(0.f, 0.f);
+      if (lane < nj && row0 + r < M) {
+        xy[r] = *reinterpret_cast<const float2*>(kp + ((row0 + r) * K + my_joint) * 2);
+        if (S.gathered) *reinterpret_cast<float2*>(S.gathered + ((row0 + r) * nj + lane) * 2) = xy[r];
+      }
     }
 #pragma unroll
     for (int br = 0; br < 2; ++br) {
-      const float mine = S.coord[br] == 0 ? xy.x : xy.y;
-      float4 a0 = ld4(S.map_b[br] + c0), a1 = ld4(S.map_b[br] + c1);
-      // nn.Linear accumulates bias + sum_j; keep the dot product in j order.
-      float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
-      for (int j = 0; j < nj; ++j) {
-        const float c = __shfl_sync(0xffffffffu, mine, j);
-        const float4 w0 = ld4(wt[br] + j * D + c0), w1 = ld4(wt[br] + j * D + c1);
-        d0.x = fmaf(c, w0.x, d0.x), d0.y = fmaf(c, w0.y, d0.y), d0.z = fmaf(c, w0.z, d0.z), d0.w = fmaf(c, w0.w, d0.w);
-        d1.x = fmaf(c, w1.x, d1.x), d1.y = fmaf(c, w1.y, d1.y), d1.z = fmaf(c, w1.z, d1.z), d1.w = fmaf(c, w1.w, d1.w);
-      }
-      const float4 p0 = ld4(S.pos[br] + int64_t(t + 2) * D + c0), p1 = ld4(S.pos[br] + int64_t(t + 2) * D + c1);
-      float4 v[kMaxVec];
-      v[0] = make_float4((d0.x + a0.x) + p0.x, (d0.y + a0.y) + p0.y, (d0.z + a0.z) + p0.z, (d0.w + a0.w) + p0.w);
-      v[1] = make_float4((d1.x + a1.x) + p1.x, (d1.y + a1.y) + p1.y, (d1.z + a1.z) + p1.z, (d1.w + a1.w) + p1.w);
-      const RowStats st = row_stats(v, D / 4, lane, D, 1e-5f);
+      float mine[R];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int c = i == 0 ? c0 : c1;
-        const float4 gg = ld4(S.ln_g[br] + c), bb = ld4(S.ln_b[br] + c);
-        float4 o;
-        o.x = (v[i].x - st.mean) * st.rstd * gg.x + bb.x;
-        o.y = (v[i].y - st.mean) * st.rstd * gg.y + bb.y;
-        o.z = (v[i].z - st.mean) * st.rstd * gg.z + bb.z;
-        o.w = (v[i].w - st.mean) * st.rstd * gg.w + bb.w;
-        if (S.out[br]) st4(S.out[br] + row * D + c, o);
-        if (S.out_planes[br])
-          store_planes4(reinterpret_cast<uint16_t*>(S.out_planes[br]), M * int64_t(D), row * D + c, o, fmt);
+      for (int r = 0; r < R; ++r) mine[r] = S.coord[br] == 0 ? xy[r].x : xy[r].y;
+      // nn.Linear accumulates bias + sum_j; keep the dot product in j order.  Packed fp32 FMAs (FFMA2:
+      // two fused multiply-adds per instruction, each rounded like fmaf).
+      float2 acc[R][4];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = make_float2(0.f, 0.f);
+      for (int j = 0; j < nj; ++j) {
+        const float4 w0 = ld4(wt[br] + j * D + c0), w1 = ld4(wt[br] + j * D + c1);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float c = __shfl_sync(0xffffffffu, mine[r], j);
+          const float2 cc = make_float2(c, c);
+          acc[r][0] = __ffma2_rn(cc, make_float2(w0.x, w0.y), acc[r][0]);
+          acc[r][1] = __ffma2_rn(cc, make_float2(w0.z, w0.w), acc[r][1]);
+          acc[r][2] = __ffma2_rn(cc, make_float2(w1.x, w1.y), acc[r][2]);
+          acc[r][3] = __ffma2_rn(cc, make_float2(w1.z, w1.w), acc[r][3]);
+        }
+      }
+      float* out = S.out[br];
+      uint16_t* planes = reinterpret_cast<uint16_t*>(S.out_planes[br]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {  // rows past M are computed on zeros and never handed over (warp-uniform flow)
+        const int rs = r % kFeStageRows;  // row slot inside the staging buffer
+        uint8_t* buf = stage + (handed & 1u) * kFeBufBytes;
+        if (rs == 0 && handed >= 2) {  // the buffer's previous contents must have been read out
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        int t = t0 + r;
+        while (t >= T) t -= T;
+        const float4 a0 = bias[br][0], a1 = bias[br][1];
+        const float4 p0 = ld4(S.pos[br] + int64_t(t + 2) * D + c0), p1 = ld4(S.pos[br] + int64_t(t + 2) * D + c1);
+        // (dot + bias) + position row, as the reference adds them
+        const float2 e0 = __fadd2_rn(__fadd2_rn(acc[r][0], make_float2(a0.x, a0.y)), make_float2(p0.x, p0.y));
+        const float2 e1 = __fadd2_rn(__fadd2_rn(acc[r][1], make_float2(a0.z, a0.w)), make_float2(p0.z, p0.w));
+        const float2 e2 = __fadd2_rn(__fadd2_rn(acc[r][2], make_float2(a1.x, a1.y)), make_float2(p1.x, p1.y));
+        const float2 e3 = __fadd2_rn(__fadd2_rn(acc[r][3], make_float2(a1.z, a1.w)), make_float2(p1.z, p1.w));
+        float4 v[kMaxVec];
+        v[0] = make_float4(e0.x, e0.y, e1.x, e1.y);
+        v[1] = make_float4(e2.x, e2.y, e3.x, e3.y);
+        const RowStats st = row_stats(v, D / 4, lane, D, 1e-5f);
+        const float2 nm = make_float2(-st.mean, -st.mean), rsd = make_float2(st.rstd, st.rstd);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = i == 0 ? c0 : c1;
+          const float4 gg = gam[br][i], bb = bet[br][i];
+          const float2 lo2 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[i].x, v[i].y), nm), rsd), make_float2(gg.x, gg.y),
+                                        make_float2(bb.x, bb.y));
+          const float2 hi2 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[i].z, v[i].w), nm), rsd), make_float2(gg.z, gg.w),
+                                        make_float2(bb.z, bb.w));
+          const float4 o = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+          if (out) *reinterpret_cast<float4*>(buf + rs * 1024 + c * 4) = o;
+          if (planes) {
+            uint2 ph, pl;
+            split_pair_rt(o.x, o.y, fmt, ph.x, pl.x);
+            split_pair_rt(o.z, o.w, fmt, ph.y, pl.y);
+            *reinterpret_cast<uint2*>(buf + kFeStageRows * 1024 + rs * 512 + c * 2) = ph;
+            *reinterpret_cast<uint2*>(buf + kFeStageRows * 1536 + rs * 512 + c * 2) = pl;
+          }
+        }
+        if (rs == kFeStageRows - 1 || r == R - 1) {  // hand the buffer's rows to the bulk-copy engine
+          const int64_t first = row0 + r - rs;
+          const int64_t left = M - first;
+          const uint32_t rows = uint32_t(left < int64_t(rs + 1) ? (left < 0 ? 0 : left) : rs + 1);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows > 0) {
+            const uint32_t src = stage_addr + (handed & 1u) * kFeBufBytes;
+            if (out) bulk_store(out + first * D, src, rows * 1024u);
+            if (planes) {
+              bulk_store(planes + first * D, src + kFeStageRows * 1024, rows * 512u);
+              bulk_store(planes + M * int64_t(D) + first * D, src + kFeStageRows * 1536, rows * 512u);
+            }
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          ++handed;
+        }
       }
     }
   }
+  // the staging buffers must have been read out before the CTA exits; the global writes drain behind it
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- K4 temporal max-pool
@@ -312,14 +409,38 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
   }
   if (int64_t(B) * T == 0) return SCATT_OK;
   const int wt_stride = max_nj * D;
-  const size_t smem = size_t(2) * wt_stride * sizeof(float);
+  const size_t smem = size_t(2) * wt_stride * sizeof(float) + kFeStageBytes;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 32 * 256 * 4));
+    const int max_smem = 2 * 32 * 256 * 4 + kFeStageBytes;
+    SCATT_CUDA(cudaFuncSetAttribute(frontend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    SCATT_CUDA(cudaFuncSetAttribute(frontend_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     attr_done.store(true);
   }
-  dim3 grid(grid_for(int64_t(B) * T, 8 * 4, 148 * 2), n);
-  (void)launch_kernel(frontend_kernel, grid, dim3(256), smem, s, kp, B, T, K, prm, fmt, wt_stride);
+  // Tiny batches: one frame per warp pass; otherwise four (every weight vector read from shared memory serves
+  // four frames).  CTAs per stream: one group per warp while everything fits the 2 x 148 resident CTAs, else
+  // the resident CTAs are shared out by the streams' cost (joints) and walk their groups grid-stride.
+  const int64_t M = int64_t(B) * T;
+  const int R = M * n <= int64_t(148) * kFeWarps * 2 ? 1 : 4;
+  const int64_t ngroups = (M + R - 1) / R;
+  const int64_t want = (ngroups + kFeWarps - 1) / kFeWarps;  // CTAs per stream for one group per warp
+  const int slots = 148 * 2;
+  prm.cta_begin[0] = 0;
+  if (want * n <= slots) {
+    for (int i = 0; i < n; ++i) prm.cta_begin[i + 1] = prm.cta_begin[i] + int(want);
+  } else {
+    int64_t cost[SCATT_MAX_GROUP], total = 0;
+    for (int i = 0; i < n; ++i) total += cost[i] = 11 * int64_t(streams[i].n_joints) + 230;  // instructions per frame, roughly
+    for (int i = 0; i < n; ++i) {
+      int share = int((slots * cost[i]) / total);
+      if (share < 1) share = 1;
+      prm.cta_begin[i + 1] = prm.cta_begin[i] + share;
+    }
+  }
+  for (int i = n; i < SCATT_MAX_GROUP; ++i) prm.cta_begin[i + 1] = prm.cta_begin[n];
+  dim3 grid(prm.cta_begin[n]);
+  if (R == 1) (void)launch_kernel(frontend_kernel<1>, grid, dim3(32 * kFeWarps), smem, s, kp, B, T, K, prm, fmt, wt_stride);
+  else (void)launch_kernel(frontend_kernel<4>, grid, dim3(32 * kFeWarps), smem, s, kp, B, T, K, prm, fmt, wt_stride);
   return after_launch("frontend_kernel");
 }
 

@@ -14,6 +14,7 @@ kernel launch (``grid.z`` = stream).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -187,6 +188,58 @@ def split_planes(x: torch.Tensor, prec: Precision, scale: float = 1.0) -> torch.
     return planes
 
 
+# ----------------------------------------------------------------------------- side branches
+
+_side_streams = {}
+SIDE_BRANCHES = os.environ.get("SCATT_SIDE_BRANCHES", "1") != "0"  # False: every SideBranch body runs in stream order (one chain of launches)
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+class SideBranch:
+    """``with SideBranch(inputs) as br: outs = ...`` runs the body on the device's side stream, forked from
+    the current stream; ``br.join(outs)`` makes the current stream wait for it.  Inside a captured forward
+    the body becomes a parallel graph branch: at small batches one launch fills a fraction of the 148 SMs,
+    so independent launches overlap.  ``inputs`` / ``outs`` are the :class:`Act` that cross streams."""
+
+    def __init__(self, inputs: Sequence["Act"]):
+        self.main = torch.cuda.current_stream()
+        self.side = side_stream(self.main.device) if SIDE_BRANCHES else self.main
+        self.inputs = list(inputs)
+        if self.side is self.main:
+            return
+        fork = torch.cuda.Event()
+        fork.record(self.main)
+        self.side.wait_event(fork)
+
+    def __enter__(self):
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.side is self.main:
+            return self._ctx.__exit__(*exc)
+        self.done = torch.cuda.Event()
+        self.done.record(self.side)
+        return self._ctx.__exit__(*exc)
+
+    def join(self, outs: Sequence["Act"] = ()):
+        if self.side is self.main:
+            return
+        torch.cuda.current_stream().wait_event(self.done)
+        for a in list(self.inputs) + list(outs):  # keep the caching allocator honest in eager mode
+            for t in (a.f32, a.planes):
+                if t is not None:
+                    t.record_stream(self.side)
+                    t.record_stream(self.main)
+
+
 # ----------------------------------------------------------------------------- packed weights
 
 
@@ -256,7 +309,9 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     M, K, N = xs[0].rows, xs[0].cols, packs[0].N
     dev = (xs[0].f32 if xs[0].f32 is not None else xs[0].planes).device
     want_planes = out_planes and prec.uses_planes
-    need_f32 = out_f32 or not want_planes or (ep.layer_norm and (not prec.uses_planes or N != 256))
+    # a LayerNorm the engine does not fuse into the GEMM runs as a row-wise tail in place on the fp32 output
+    ln_scratch = bool(ep.layer_norm) and not L.load().scatt_linear_ln_fused(M, N, G, prec.engine)
+    need_f32 = out_f32 or not want_planes or ln_scratch
     probs = (L.LinearProblem * G)()
     outs: List[Act] = []
     keep = []

@@ -179,14 +179,7 @@ class SeparativeCoordinateAttention(nn.Module):
 
 
 OVERLAP_BRANCHES = True  # run the first causal layer concurrently with the self branch
-_side_streams = {}
-
-
-def _side_stream(device) -> torch.cuda.Stream:
-    key = (device.type, device.index)
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    return _side_streams[key]
+_side_stream = F_.side_stream
 
 
 def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], s: List[Act], c: List[Act],
@@ -216,27 +209,41 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
     for i in range(n):
         s = coordinate_attention_forward(prec, [m.self_attn_layers[i] for m in mods], s, B, T, key_mask,
                                          keep_f32=need_self_f32 and i == n - 1)
-    # K / V of every merge layer read the same final self map: one N = n*2*D GEMM per stream
-    packs = []
-    for m in mods:
+    # K / V of every merge layer read the same final self map: the first layer's pair (N = 2 D) on this stream,
+    # the pairs of the remaining layers as one N = (n - 1) * 2 D GEMM per stream on a side branch that runs
+    # beside the first merge layer
+    def kv_pack(m, tag, layers):
         lins, scales = [], []
-        for i in range(n):
+        for i in layers:
             a = m.coordinates_merge[i].attn
             lins += [a.k_proj, a.v_proj]
             scales += [1.0, 0.5]
-        packs.append(F_.pack_of(m, "merge_kv", lins, scales))
+        return F_.pack_of(m, tag, lins, scales)
+
     kv_planes = prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T  # TMA-fed attention takes the planes as they are
-    kv_all = F_.linear(prec, s, packs, F_.make_epilogue(), out_f32=not kv_planes, out_planes=kv_planes)
+    kv_rest, kv_branch = None, None
+    split_kv = OVERLAP_BRANCHES and n > 1
+    if split_kv:
+        for a in s:
+            a.with_planes(prec)  # made here, not inside the branch: both GEMMs read them
+        with F_.SideBranch(s) as kv_branch:
+            kv_rest = F_.linear(prec, s, [kv_pack(m, "merge_kv_rest", range(1, n)) for m in mods], F_.make_epilogue(),
+                                out_f32=not kv_planes, out_planes=kv_planes)
+    kv_first = F_.linear(prec, s, [kv_pack(m, "merge_kv_first" if split_kv else "merge_kv", range(1 if split_kv else n)) for m in mods],
+                         F_.make_epilogue(), out_f32=not kv_planes, out_planes=kv_planes)
     for i in range(n):
         if i == 0 and c_first is not None:
             torch.cuda.current_stream().wait_event(join)
             c = c_first
         else:
             c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask, keep_f32=False)
+        if split_kv and i == 1:
+            kv_branch.join(kv_rest)
+        kv_src, j = (kv_rest, i - 1) if (split_kv and i >= 1) else (kv_first, i)
         if kv_planes:
-            kv_views = [((kv.planes, 2 * i * d), (kv.planes, (2 * i + 1) * d)) for kv in kv_all]
+            kv_views = [((kv.planes, 2 * j * d), (kv.planes, (2 * j + 1) * d)) for kv in kv_src]
         else:
-            kv_views = [(kv.f32[:, 2 * i * d : (2 * i + 1) * d], kv.f32[:, (2 * i + 1) * d : (2 * i + 2) * d]) for kv in kv_all]
+            kv_views = [(kv.f32[:, 2 * j * d : (2 * j + 1) * d], kv.f32[:, (2 * j + 1) * d : (2 * j + 2) * d]) for kv in kv_src]
         c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask,
                                       keep_f32=i == n - 1)  # the ladder's result feeds the residual network in fp32
     return c, s

@@ -106,16 +106,24 @@ class MSCAEncoder(nn.Module):
         idx = self._compact_idx(keypoints.device)[1] if keypoints.shape[2] == self._n_used() else self._joint_idx(keypoints.device)
         blocks = streams_forward(prec, mods, keypoints, idx, key_mask, b, t)
         (body, left, right), tp = blocks[-1]
+        lg, heads_branch = None, None
+        if with_heads:
+            # the three stream classifiers only need the stream features: they run as a side branch beside
+            # the fusion block
+            rh = self.recognition_head
+            ep = F_.make_epilogue(clamp=50.0)
+            for a in (left, right, body):
+                a.with_planes(prec)  # made here, not inside the branch: both consumers read them
+            with F_.SideBranch([left, right, body]) as heads_branch:
+                lg = F_.linear(prec, [left, right, body],
+                               [F_.pack_of(rh, "left", [rh.left_gloss_classifier]), F_.pack_of(rh, "right", [rh.right_gloss_classifier]),
+                                F_.pack_of(rh, "body", [rh.body_gloss_classifier])], ep, out_planes=False)
         fuse = coordinates_fusion_forward(prec, self.coordinates_fusion, left, right, body, b, tp, out_planes=with_heads)
         out = {"body_embed": body.f32.view(b, tp, -1), "left_embed": left.f32.view(b, tp, -1),
                "right_embed": right.f32.view(b, tp, -1), "fuse_embed": fuse.f32.view(b, tp, -1)}
         if with_heads:
-            rh = self.recognition_head
-            ep = F_.make_epilogue(clamp=50.0)
-            lg = F_.linear(prec, [left, right, body],
-                           [F_.pack_of(rh, "left", [rh.left_gloss_classifier]), F_.pack_of(rh, "right", [rh.right_gloss_classifier]),
-                            F_.pack_of(rh, "body", [rh.body_gloss_classifier])], ep, out_planes=False)
             fl = F_.linear(prec, [fuse], [F_.pack_of(rh, "fuse", [rh.fuse_coord_classifier])], ep, out_planes=False)[0]
+            heads_branch.join(lg)
             out.update(left=lg[0].f32.view(b, tp, -1), right=lg[1].f32.view(b, tp, -1), body=lg[2].f32.view(b, tp, -1),
                        fuse_coord_gloss_logits=fl.f32.view(b, tp, -1))
             if self.alignment:

@@ -60,15 +60,21 @@ class ResidualBlock(nn.Module):
 def residual_blocks_forward(prec: Precision, blocks: Sequence[ResidualBlock], xs: List[Act], B: int, T: int):
     """One ``ResidualBlock`` per anatomical stream (same shapes), grouped launches."""
     blk = blocks[0]
-    if blk.need_projection:
-        res = F_.linear(prec, xs, [F_.pack_of(m, "projection", [m.projection]) for m in blocks], F_.make_epilogue(),
-                        out_planes=False)
-        res = [r.f32 for r in res]
+    proj_branch = None
+    if blk.need_projection:  # reads the same input as linear1: a side branch beside linear1 / norm1
+        for x in xs:
+            x.with_planes(prec)  # made here, not inside the branch: both GEMMs read them
+        with F_.SideBranch(xs) as proj_branch:
+            res_acts = F_.linear(prec, xs, [F_.pack_of(m, "projection", [m.projection]) for m in blocks], F_.make_epilogue(),
+                                 out_planes=False)
+        res = [r.f32 for r in res_acts]
     else:
         res = [x.f32 for x in xs]
     h = F_.linear(prec, xs, [F_.pack_of(m, "linear1", [m.linear1]) for m in blocks],
                   F_.make_epilogue(layer_norm=True, act_post=L.ACT_RELU), lns=[m.norm1 for m in blocks],
                   out_f32=not prec.uses_planes)
+    if proj_branch is not None:
+        proj_branch.join(res_acts)
     out = F_.linear(prec, h, [F_.pack_of(m, "linear2", [m.linear2]) for m in blocks],
                     F_.make_epilogue(layer_norm=True, residual_mode=L.RES_AFTER_LN, act_post=L.ACT_RELU), residuals=res,
                     lns=[m.norm2 for m in blocks], out_planes=not blk.downsample)

@@ -85,7 +85,7 @@ def test_alignment_module_interface():
         m.eval()(torch.zeros(2, 1, 1024))
 
 
-@pytest.mark.parametrize("B,T,V", [(2, 9, 97), (8, 50, 1120), (3, 1, 1), (1, 4, 5000)])
+@pytest.mark.parametrize("B,T,V", [(2, 9, 97), (8, 50, 1120), (3, 1, 1), (1, 4, 5000), (4, 7, 1536), (2, 3, 1540), (300, 50, 1120)])
 def test_log_softmax_clamp(B, T, V):
     g = torch.Generator().manual_seed(V)
     x = torch.randn(B, T, V, generator=g) * 20

@@ -117,6 +117,40 @@ def test_linear_n256_large_m_single_cta_path(mode, epi):
     assert float((out.f32.double() - ref).abs().max()) <= MODE_TOL[mode] * 4
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
+@pytest.mark.parametrize("epi", ["ln_relu", "ln_res_relu", "gelu_res_ln", "res_ln"])
+@pytest.mark.parametrize("G,M,N,K", [(3, 800, 512, 256), (3, 400, 512, 512), (1, 400, 1024, 1024), (1, 2300, 1024, 512),
+                                     (3, 128 * 13, 512, 256), (1, 128 * 19 + 3, 1024, 256)])
+def test_linear_wide_layernorm_cluster_and_tail(mode, epi, G, M, N, K):
+    """Rows of 512 / 1024 columns are normalised inside the GEMM by 4- / 8-CTA clusters (DSMEM statistics
+    exchange) while the clusters fit one wave, and by the row-wise tail launch beyond; both against the chain."""
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    fused = bool(L.load().scatt_linear_ln_fused(M, N, G, prec.engine))
+    assert fused == (-(-M // 128) * G * (N // 128) <= 148)
+    xs = [rnd(M, K, seed=10 + g) for g in range(G)]
+    lins = [make_linear(N, K, 20 + g) for g in range(G)]
+    lns = []
+    for g in range(G):
+        ln = torch.nn.LayerNorm(N)
+        with torch.no_grad():
+            ln.weight.copy_(1.0 + 0.2 * (torch.rand(N, generator=torch.Generator().manual_seed(30 + g)) - 0.5))
+            ln.bias.copy_(0.1 * (torch.rand(N, generator=torch.Generator().manual_seed(40 + g)) - 0.5))
+        lns.append(ln.to(DEV))
+    res = [rnd(M, N, seed=50 + g) for g in range(G)] if kw.get("residual_mode", 0) else None
+    for out_f32 in (True, False):
+        outs = F_.linear(prec, [Act(x) for x in xs], [F_.PackedLinear([l], None, None) for l in lins], F_.make_epilogue(**kw),
+                         residuals=res, lns=lns, out_f32=out_f32)
+        torch.cuda.synchronize()
+        for g in range(G):
+            ref = ref_chain(xs[g], lins[g], kw, None if res is None else res[g], lns[g])
+            got = outs[g].f32.double() if outs[g].f32 is not None else outs[g].planes[0].double() + outs[g].planes[1].double()
+            if not out_f32 and fused:
+                assert outs[g].f32 is None  # planes only: no fp32 round trip when the LayerNorm is fused
+            err = float((got - ref).abs().max())
+            assert err <= MODE_TOL[mode] * 4.0 * max(1.0, math.sqrt(K / 256)), (mode, epi, G, M, N, K, out_f32, err)
+
+
 @pytest.mark.parametrize("mode", ["fp16x3", "fp16x1", "bf16x3"])
 @pytest.mark.parametrize("epi", ["bias", "qscale", "gelu", "clamp"])
 @pytest.mark.parametrize("shape", [(12800 + 5, 768, 256), (19000, 1120, 512)])

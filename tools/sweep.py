@@ -107,12 +107,62 @@ def kernel_sweep(args):
                 print(f"| {M} | {N} | {K} | {name} | {mode} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {by / us / 1e3:.0f} |", flush=True)
                 del xs, packs, res
 
+def membound_sweep(args):
+    """K1 front end, K4 temporal pool, the row-wise LayerNorm tail and the CTC log-softmax front against the
+    measured HBM copy bandwidth.  Buffers are larger than the 126 MB L2 at the big sizes; every launch is timed
+    alone after an L2 flush (CUDA events, median of 15)."""
+    from scattennet_b200.keypoint_module import frontend_forward
+    cfg = model_config("phoenix-2014t")
+    prec = F_.get_precision("fp16x3")
+    model = MSCAEncoder(cfg, 1120, precision="fp16x3").eval()
+    synth.load_synth_(model, 0)
+    model = model.to(dev)
+    mods = [model.body_encoder, model.left_encoder, model.right_encoder]
+    print(f"### memory-bound kernels vs the measured HBM copy bandwidth ({PEAK_GBS:.0f} GB/s); one launch after an L2 flush\n")
+    print("| kernel | shape | algorithmic MB | us | GB/s | % of HBM peak |")
+    print("|---|---|---|---|---|---|")
+    def row(name, shape, nbytes, fn):
+        us = timed(fn, 15) * 1e3
+        print(f"| {name} | {shape} | {nbytes / 1e6:.1f} | {us:.1f} | {nbytes / us / 1e3:.0f} | {100 * nbytes / us / 1e3 / PEAK_GBS:.1f} |", flush=True)
+    T = 200
+    for B in (8, 64, 256, 1024):
+        for compact in (False, True):
+            kp, _ = synth.synth_batch(B, T, seed=1)
+            if compact:
+                used, idx = model._compact_idx(torch.device(dev))
+                kp = kp.index_select(2, used)
+            else:
+                idx = model._joint_idx(torch.device(dev))
+            kp = kp.to(dev).contiguous()
+            nbytes = B * T * (48 * 8 + 6 * 256 * 8)  # 384 B of used joints in, 6 branches x 256 x (fp32 + 2 planes) out
+            row("frontend_kernel" + (" (compact input)" if compact else ""), f"B={B} T={T} K={kp.shape[2]}", nbytes,
+                lambda: frontend_forward(prec, mods, kp, idx, B, T))
+            del kp
+    for B in (8, 256, 1024):
+        for Cc in (256, 512):
+            Tt = 200 if Cc == 256 else 100
+            xs = [torch.randn(B * Tt, Cc, device=dev) for _ in range(3)]
+            nbytes = 3 * B * Tt * Cc * (4 + 0.5 * 8)  # fp32 in; fp32 + planes out for half the rows
+            row("pool_pairs_kernel (3 streams)", f"B={B} T={Tt} C={Cc}", nbytes, lambda: F_.pool_pairs_group(prec, xs, B, Tt))
+            del xs
+    for M, N in ((400, 1024), (51200, 1024), (204800, 512)):
+        z = torch.randn(M, N, device=dev)
+        ln = torch.nn.LayerNorm(N).to(dev)
+        nbytes = M * N * (4 + 8)
+        row("rowwise_kernel (LayerNorm + ReLU)", f"M={M} N={N}", nbytes,
+            lambda: F_.rowwise(prec, z, F_.make_epilogue(layer_norm=True, act_post=L.ACT_RELU), ln))
+        del z
+    for B in (8, 256, 1024):
+        lg = torch.randn(B, 50, 1120, device=dev)
+        row("log_softmax_kernel", f"B={B} T'=50 V=1120", 2 * B * 50 * 1120 * 4, lambda: F_.log_softmax_clamp(lg, time_major=True))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["batch", "kernels"])
+    ap.add_argument("what", choices=["batch", "kernels", "membound"])
     ap.add_argument("--precision", default="fp16x3,fp16x1")
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024")
     ap.add_argument("--T", type=int, default=200)
     ap.add_argument("--config", default="phoenix-2014t")
     a = ap.parse_args()
-    (batch_sweep if a.what == "batch" else kernel_sweep)(a)
+    {"batch": batch_sweep, "kernels": kernel_sweep, "membound": membound_sweep}[a.what](a)
