@@ -102,13 +102,15 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   if (FMT == SCATT_PLANE_F16) {
     const __half2 h = __floats2half2_rn(a, b);
     const float2 back = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    const float2 d = __fadd2_rn(make_float2(a, b), make_float2(-back.x, -back.y));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
   } else {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     const float2 back = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+    const float2 d = __fadd2_rn(make_float2(a, b), make_float2(-back.x, -back.y));
+    const __nv_bfloat162 l = __floats2bfloat162_rn(d.x, d.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
   }
@@ -334,6 +336,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     mx = fmaxf(mx, xch[(half ^ 1) * 128 + r]);  // every row sees key 0, so mx is finite
     const float mneg = -mx * kLog2e;
     float l = 0.f;
+    float2 la = make_float2(0.f, 0.f), lb = la;
 #pragma unroll 1
     for (int blk = 0; blk < nblk; ++blk) {
       if (nblk > 1) {  // S of this block was recomputed; a single block is still there from pass A
@@ -351,10 +354,12 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
           const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
           if (fast) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float p = ex2(fmaf(v[j], kLog2e, mneg));
-              l += p;
-              v[j] = p;
+            for (int j = 0; j < 32; j += 4) {  // packed row sums, two independent chains
+              const float p0 = ex2(fmaf(v[j], kLog2e, mneg)), p1 = ex2(fmaf(v[j + 1], kLog2e, mneg));
+              const float p2 = ex2(fmaf(v[j + 2], kLog2e, mneg)), p3 = ex2(fmaf(v[j + 3], kLog2e, mneg));
+              la = __fadd2_rn(la, make_float2(p0, p1));
+              lb = __fadd2_rn(lb, make_float2(p2, p3));
+              v[j] = p0, v[j + 1] = p1, v[j + 2] = p2, v[j + 3] = p3;
             }
           } else {
 #pragma unroll
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       }
     }
     if (threadIdx.x == 0) trace(6);
+    l += (la.x + la.y) + (lb.x + lb.y);
     xch[256 + half * 128 + r] = l;
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kSoftmaxWarps) : "memory");
 

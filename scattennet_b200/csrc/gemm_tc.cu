@@ -31,6 +31,10 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef SCATT_RES_STAGED
+#define SCATT_RES_STAGED 1
+#endif
+
 namespace scatt {
 
 namespace {
@@ -54,10 +58,11 @@ struct alignas(64) TcParams {
   CUtensorMap map_b[SCATT_MAX_GROUP];
   CUtensorMap map_y[SCATT_MAX_GROUP];   // fp32 output  [M][ldy]      (box 32 x 32, 128B swizzle)
   CUtensorMap map_p[SCATT_MAX_GROUP];   // split planes [2][M][N]     (box 32 x 32 x 1, 64B swizzle)
+  CUtensorMap map_r[SCATT_MAX_GROUP];   // fp32 residual [M][ldres]   (box 32 x 32, 128B swizzle; cluster LayerNorm kernels)
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
-  int32_t N, K, stages, terms, fmt, fused_ln, pre_init;
+  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged;
 };
 
 // Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
@@ -93,6 +98,7 @@ struct EpiCtx {
   const CUtensorMap* map_y;
   const CUtensorMap* map_p;
   int stores;              // output boxes handed to TMA so far (selects the double buffer)
+  const uint8_t* res_box;  // this warp's residual boxes (32 x 32 fp32, 128B swizzle, one per column chunk) or null
 };
 
 // registers <- 32 x 32 fp32 tile of a row-major matrix (two 16-column halves), coalesced
@@ -174,6 +180,16 @@ __device__ __forceinline__ void tile_add_planes(const EpiCtx& E, const float4 (&
       v[h * 16 + j] += t.x, v[h * 16 + j + 1] += t.y, v[h * 16 + j + 2] += t.z, v[h * 16 + j + 3] += t.w;
     }
     __syncwarp();
+  }
+}
+
+// v[32] (thread-per-row) += row `lane` of a 32 x 32 fp32 box the TMA engine wrote with the 128-byte swizzle
+__device__ __forceinline__ void box_add(const EpiCtx& E, const uint8_t* box, float* v) {
+  const int r = E.lane;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(box + r * 128 + ((j ^ (r & 7)) << 4));
+    v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
   }
 }
 
@@ -300,9 +316,13 @@ __device__ __forceinline__ bool chunk_pre(const TcParams& P, const TcProblem& Q,
     modified = true;
   }
   if (late_res) {
-    float4 r[8];
-    tile_fetch(E, Q.residual, P.ldres, c0, r);
-    tile_add(E, r, v);
+    if (E.res_box != nullptr) {  // staged by TMA (cluster LayerNorm kernels): chunk cl / 32 of this CTA's columns
+      box_add(E, E.res_box + (cl & 63) / 32 * 4096, v);
+    } else {
+      float4 r[8];
+      tile_fetch(E, Q.residual, P.ldres, c0, r);
+      tile_add(E, r, v);
+    }
     modified = true;
   }
   return modified;
@@ -376,6 +396,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
   const scatt_epilogue& ep = P.ep;
   constexpr int kMine = BN / 32 / (EW / 4);
   static_assert(LN == 0 || EW == 8, "the fused LayerNorm combines exactly two column halves per CTA");
+  static_assert(LN < 2 || kMine == 2, "the staged residual boxes are indexed for two chunks per warp");
   float v[32];
   const bool late_res_any = ep.residual_mode != SCATT_RES_NONE && !P.pre_init;
 
@@ -449,11 +470,12 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
     float4 r[2][8];
-    if (res_after) tile_fetch(E, Q.residual, P.ldres, n0 + half * kMine * 32, r[0]);
+    const bool res_global = res_after && E.res_box == nullptr;  // cluster kernels find the residual staged in smem
+    if (res_global) tile_fetch(E, Q.residual, P.ldres, n0 + half * kMine * 32, r[0]);
 #pragma unroll 2
     for (int i = 0; i < kMine; ++i) {
       const int cl = (half * kMine + i) * 32;
-      if (res_after && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
+      if (res_global && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
       tc_ld32(tmem_acc + cl, v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -464,7 +486,8 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
         v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
         v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
       }
-      if (res_after) tile_add(E, r[i & 1], v);
+      if (res_global) tile_add(E, r[i & 1], v);
+      else if (res_after) box_add(E, E.res_box + i * 4096, v);
       chunk_store<FMT>(P, Q, E, v, n0 + cl);
     }
   }
@@ -482,12 +505,16 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
   const uint32_t ring_bytes = max(uint32_t(stages) * kStageBytes, uint32_t(EW) * 16384u);
-  const uint32_t bar_base = base + ring_bytes;
+  // cluster LayerNorm kernels: the CTA's residual tile (128 x 128 fp32 as 32 x 32 boxes, 64 KB) is staged by TMA
+  constexpr uint32_t kResBytes = LN >= 2 ? uint32_t(EW) * 2u * 4096u : 0u;
+  const uint32_t res_base = base + ring_bytes;
+  const uint32_t bar_base = res_base + (P.res_staged ? kResBytes : 0u);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   const uint32_t tmem_full_bar = bar_base + 16u * stages;
   const uint32_t acc_init_bar = tmem_full_bar + 8u;
-  const uint32_t tmem_ptr_addr = acc_init_bar + 8u;
+  const uint32_t res_bar = acc_init_bar + 8u;
+  const uint32_t tmem_ptr_addr = res_bar + 8u;
   const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][BN]
   const uint32_t stats_base = col_base + 3u * BN * 4u;               // float2[2][BM]
   const uint32_t xstats_base = stats_base + 2u * BM * 8u;            // float2[LN][BM], slot p written by peer CTA p (LN >= 2)
@@ -510,11 +537,13 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(acc_init_bar, 32 * EW);
+    mbar_init(res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_a[g]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
     if (Q.y) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_y[g]) : "memory");
     if (Q.y_planes) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_p[g]) : "memory");
+    if (LN >= 2 && P.res_staged) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_r[g]) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(BN))
@@ -546,6 +575,18 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   // tcgen05.mma, tcgen05.commit) are issued by an elected lane so they compile to bare UTMALDG / UTCHMMA.
   if (warp == 0) {  // ---------------- TMA producer
     const uint32_t tx = kStageBytes;
+    if constexpr (LN >= 2) {
+      if (P.res_staged) {  // residual boxes in epilogue-warp order: warp (quad, half), chunk i -> rows quad*32, cols (half*2+i)*32
+        if (elect_one()) {
+          mbar_expect_tx(res_bar, kResBytes);
+          for (int b = 0; b < EW * 2; ++b) {
+            const int w = b >> 1, i = b & 1, quad = (w + 2) & 3, half = w >> 2;
+            tma_load_2d(res_base + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+          }
+        }
+        __syncwarp();
+      }
+    }
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % stages;
       mbar_wait(empty_bar(s), ((kb / stages) & 1) ^ 1);
@@ -627,12 +668,19 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     E.map_y = &P.map_y[g];
     E.map_p = &P.map_p[g];
     E.stores = 0;
+    E.res_box = nullptr;
+    if constexpr (LN >= 2) {
+      if (P.res_staged) E.res_box = gen(res_base + uint32_t(warp - 2) * 2u * 4096u);
+    }
     const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
     if (P.pre_init) {
       acc_pre_init<BN, EW, LN == 1>(P, Q, E, my_tmem, n0, half);
       tc_fence_before();
       mbar_arrive(acc_init_bar);
       if (threadIdx.x == 64) trace(9);
+    }
+    if constexpr (LN >= 2) {
+      if (P.res_staged) mbar_wait(res_bar, 0);  // landed long before the accumulator is complete
     }
     mbar_wait(tmem_full_bar, 0);
     if (threadIdx.x == 64) trace(5);
@@ -754,14 +802,15 @@ template <int BN, int LN, int FMT>
 int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
   const int num_kb = (P.K + BK - 1) / BK;
-  int stages = int((197u * 1024u) / kStageBytes);
+  const size_t res_bytes = (LN >= 2 && P.res_staged) ? size_t(kEpiWarps) * 2 * 4096 : 0;  // TMA-staged residual tile
+  int stages = int((197u * 1024u - res_bytes) / kStageBytes);
   if (stages > num_kb) stages = num_kb;
   if (stages > 8) stages = 8;
   if (stages < 1) stages = 1;
   P.stages = stages;
   size_t ring = size_t(stages) * kStageBytes;
   if (ring < size_t(kEpiWarps) * 16384) ring = size_t(kEpiWarps) * 16384;  // the epilogue's output boxes reuse the ring
-  const size_t smem = ring + 1024 /*align slack*/ + 16 * stages + 48 + 3 * BN * 4 + (2 + (LN >= 2 ? LN : 1)) * BM * 8 + kEpiWarps * kEpiWarpBytes;
+  const size_t smem = ring + res_bytes + 1024 /*align slack*/ + 16 * stages + 64 + 3 * BN * 4 + (2 + (LN >= 2 ? LN : 1)) * BM * 8 + kEpiWarps * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
   if constexpr (LN >= 2) {
@@ -792,7 +841,7 @@ int launch_dual_fmt(TcParams& P, int group, cudaStream_t s) {
   P.stages = stages;
   size_t ring = size_t(stages) * kStageBytes;
   if (ring < size_t(EW) * 16384) ring = size_t(EW) * 16384;
-  const size_t smem = ring + 1024 + 16 * stages + 48 + 3 * BN * 4 + 3 * BM * 8 + EW * kEpiWarpBytes;
+  const size_t smem = ring + 1024 + 16 * stages + 64 + 3 * BN * 4 + 3 * BM * 8 + EW * kEpiWarpBytes;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(linear_tc_dual_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -876,6 +925,11 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   // or scaled sits between the GEMM and the add.
   const bool res_early = P.ep.residual_mode == SCATT_RES_BEFORE_LN || (!fused_ln && P.ep.residual_mode == SCATT_RES_AFTER_LN);
   P.pre_init = (res_early && P.ep.act_pre == SCATT_ACT_NONE && P.ep.scale_cols == 0) ? 1 : 0;
+  // Cluster LayerNorm kernels take the residual tile through TMA into shared memory (one 64 KB fetch beside the
+  // operand loads) and add it in the epilogue: fetched with ld.global - into the accumulator up front or in the
+  // epilogue - it cost 3-5 k cycles per launch either way (profiles/r01_linear_phase_trace_v5.txt).
+  P.res_staged = (SCATT_RES_STAGED && ln_cluster >= 2 && P.ep.residual_mode != SCATT_RES_NONE) ? 1 : 0;
+  if (P.res_staged) P.pre_init = 0;
   for (int i = 0; i < group; ++i) {
     SCATT_REQUIRE(p[i].x_planes && p[i].w_planes, "linear(tcgen05): problem %d lacks split planes", i);
     SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || p[i].residual_planes, "linear(tcgen05): residual missing");
@@ -895,6 +949,12 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
                           reinterpret_cast<const uint16_t*>(p[i].residual_planes)};
     rc = encode_out_maps(&P.map_y[i], &P.map_p[i], P.prob[i].y, ldy, P.prob[i].y_planes, M, N, fmt);
     if (rc != SCATT_OK) return rc;
+    if (P.res_staged) {
+      SCATT_REQUIRE(p[i].residual && (reinterpret_cast<uintptr_t>(p[i].residual) & 15) == 0,
+                    "linear(tcgen05): the cluster LayerNorm kernels need a 16-byte aligned fp32 residual");
+      rc = encode_out_maps(&P.map_r[i], nullptr, const_cast<float*>(p[i].residual), ldres, nullptr, M, N, fmt);
+      if (rc != SCATT_OK) return rc;
+    }
   }
   int rc;
   if (fused_ln)
