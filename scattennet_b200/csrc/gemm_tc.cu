@@ -31,6 +31,9 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef SCATT_SUB2
+#define SCATT_SUB2 1
+#endif
 #ifndef SCATT_RES_STAGED
 #define SCATT_RES_STAGED 1
 #endif
@@ -97,7 +100,9 @@ struct EpiCtx {
   uint8_t* out_stage_gen;  // same, generic pointer
   const CUtensorMap* map_y;
   const CUtensorMap* map_p;
-  int stores;              // output boxes handed to TMA so far (selects the double buffer)
+  int stores;              // output boxes handed to TMA so far (selects the buffer)
+  uint32_t nbuf, buf_stride;  // staging buffers of this warp and their distance (2 x 8 KB in the idle operand ring;
+                              // two-sub-tile kernels: 8 KB of dedicated staging = 1 x 8 KB or 2 x 4 KB)
   const uint8_t* res_box;  // this warp's residual boxes (32 x 32 fp32, 128B swizzle, one per column chunk) or null
 };
 
@@ -260,12 +265,16 @@ __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], -c), c);
   }
-  const uint32_t buf = (E.stores & 1) * 8192u;
-  if (E.stores >= 2) {  // the box written two chunks ago must have been read out by the TMA engine
-    if (E.lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  const uint32_t buf = (E.nbuf == 2 ? uint32_t(E.stores & 1) : 0u) * E.buf_stride;
+  if (E.stores >= int(E.nbuf)) {  // the box last written into this buffer must have been read out by the TMA engine
+    if (E.lane == 0) {
+      if (E.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
     __syncwarp();
   }
   uint8_t* box = E.out_stage_gen + buf;
+  const uint32_t poff = Q.y ? 4096u : 0u;  // the plane boxes follow the fp32 box when both are written
   const int r = E.lane;
   if (Q.y) {
 #pragma unroll
@@ -279,8 +288,8 @@ __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& 
       split8<FMT>(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
                   make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
       const uint32_t off = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(box + 4096 + off) = hi;
-      *reinterpret_cast<uint4*>(box + 6144 + off) = lo;
+      *reinterpret_cast<uint4*>(box + poff + off) = hi;
+      *reinterpret_cast<uint4*>(box + poff + 2048 + off) = lo;
     }
   }
   fence_proxy_async();
@@ -289,8 +298,8 @@ __device__ __forceinline__ void chunk_store(const TcParams& P, const TcProblem& 
     const int row = int(E.row0);
     if (Q.y) tma_store_2d(E.map_y, E.out_stage + buf, c0, row);
     if (Q.y_planes) {
-      tma_store_3d(E.map_p, E.out_stage + buf + 4096, c0, row, 0);
-      tma_store_3d(E.map_p, E.out_stage + buf + 6144, c0, row, 1);
+      tma_store_3d(E.map_p, E.out_stage + buf + poff, c0, row, 0);
+      tma_store_3d(E.map_p, E.out_stage + buf + poff + 2048, c0, row, 1);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -493,8 +502,13 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
   }
 }
 
-template <int BN, int LN, int FMT, int EW>
+// NSUB = 2: the CTA owns two adjacent 128 x BN sub-tiles with separate TMEM accumulators and walks them back
+// to back (the A tile is fetched twice, from L2 the second time): the epilogue of the first sub-tile - bound by
+// the SM's ~27 B/clk store path - runs while the MMAs of the second are issued.  One tile per CTA cannot overlap
+// the two phases, and at small batches there is no second CTA on the SM to do it.
+template <int BN, int LN, int FMT, int EW, int NSUB = 1>
 __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
+  static_assert(NSUB == 1 || LN == 0, "sub-tiles are for kernels without a fused LayerNorm");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages][A_hi | A_lo | B_hi | B_lo] tiles, barriers, column parameters, LN partials, staging tiles
   constexpr uint32_t kABytes = BM * 128, kBBytes = BN * 128;
@@ -504,19 +518,22 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t ring_bytes = max(uint32_t(stages) * kStageBytes, uint32_t(EW) * 16384u);
+  const uint32_t ring_bytes = NSUB > 1 ? uint32_t(stages) * kStageBytes : max(uint32_t(stages) * kStageBytes, uint32_t(EW) * 16384u);
+  constexpr uint32_t kOutStage = NSUB > 1 ? uint32_t(EW) * 8192u : 0u;  // dedicated output staging (the ring stays busy)
   // cluster LayerNorm kernels: the CTA's residual tile (128 x 128 fp32 as 32 x 32 boxes, 64 KB) is staged by TMA
   constexpr uint32_t kResBytes = LN >= 2 ? uint32_t(EW) * 2u * 4096u : 0u;
   const uint32_t res_base = base + ring_bytes;
-  const uint32_t bar_base = res_base + (P.res_staged ? kResBytes : 0u);
+  const uint32_t ostage_base = res_base + (P.res_staged ? kResBytes : 0u);
+  const uint32_t bar_base = ostage_base + kOutStage;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 16u * stages;
-  const uint32_t acc_init_bar = tmem_full_bar + 8u;
+  const uint32_t tmem_full_bar = bar_base + 16u * stages;  // NSUB barriers, one per accumulator
+  const uint32_t acc_init_bar = tmem_full_bar + 8u * NSUB;
   const uint32_t res_bar = acc_init_bar + 8u;
   const uint32_t tmem_ptr_addr = res_bar + 8u;
-  const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][BN]
-  const uint32_t stats_base = col_base + 3u * BN * 4u;               // float2[2][BM]
+  constexpr int CW = BN * NSUB;                                       // columns of this CTA
+  const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;       // float[3][CW]
+  const uint32_t stats_base = col_base + 3u * CW * 4u;               // float2[2][BM]
   const uint32_t xstats_base = stats_base + 2u * BM * 8u;            // float2[LN][BM], slot p written by peer CTA p (LN >= 2)
   const uint32_t stage_base = xstats_base + BM * 8u * uint32_t(LN >= 2 ? LN : 1);  // kEpiWarps staging tiles
   auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
@@ -524,7 +541,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = blockIdx.z;
-  const int n0 = blockIdx.x * BN;
+  const int n0 = blockIdx.x * CW;
   const int64_t m0 = int64_t(blockIdx.y) * BM;
   const int num_kb = (P.K + BK - 1) / BK;
   const TcProblem& Q = P.prob[g];
@@ -535,7 +552,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int sub = 0; sub < NSUB; ++sub) mbar_init(tmem_full_bar + 8u * sub, 1);
     mbar_init(acc_init_bar, 32 * EW);
     mbar_init(res_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -546,17 +563,17 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     if (LN >= 2 && P.res_staged) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_r[g]) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(BN))
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(CW))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {  // per-column parameters of this CTA's columns -> shared memory
     float* col = reinterpret_cast<float*>(gen(col_base));
-    for (int i = threadIdx.x - 64; i < BN; i += 32 * EW) {
+    for (int i = threadIdx.x - 64; i < CW; i += 32 * EW) {
       const bool in = n0 + i < P.N;
       col[i] = (in && Q.bias) ? Q.bias[n0 + i] : 0.f;
-      col[BN + i] = (in && Q.ln_g) ? Q.ln_g[n0 + i] : 0.f;
-      col[2 * BN + i] = (in && Q.ln_b) ? Q.ln_b[n0 + i] : 0.f;
+      col[CW + i] = (in && Q.ln_g) ? Q.ln_g[n0 + i] : 0.f;
+      col[2 * CW + i] = (in && Q.ln_b) ? Q.ln_b[n0 + i] : 0.f;
     }
   }
   tc_fence_before();
@@ -587,19 +604,20 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
         __syncwarp();
       }
     }
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % stages;
-      mbar_wait(empty_bar(s), ((kb / stages) & 1) ^ 1);
+    for (int it = 0; it < NSUB * num_kb; ++it) {  // sub-tile after sub-tile through one continuous ring
+      const int kb = NSUB > 1 ? it % num_kb : it, nb = n0 + (NSUB > 1 ? it / num_kb : 0) * BN;
+      const int s = it % stages;
+      mbar_wait(empty_bar(s), ((it / stages) & 1) ^ 1);
       const uint32_t st = base + s * kStageBytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
         tma_load_3d(st, &P.map_a[g], full_bar(s), kb * BK, int(m0), 0);
         if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kb * BK, int(m0), 1);
-        tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, n0, 0);
-        if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, n0, 1);
+        tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, nb, 0);
+        if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, nb, 1);
       }
       __syncwarp();
-      if (kb == 0 && lane == 0) trace(2);
+      if (it == 0 && lane == 0) trace(2);
     }
     if constexpr (LN >= 2) {
       __syncwarp();
@@ -616,32 +634,35 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       tc_fence_after();
       accumulate = 1;
     }
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % stages;
-      mbar_wait(full_bar(s), (kb / stages) & 1);
-      if (kb == 0 && lane == 0) trace(3);
+    for (int it = 0; it < NSUB * num_kb; ++it) {
+      const int kb = NSUB > 1 ? it % num_kb : it, sub = NSUB > 1 ? it / num_kb : 0;
+      const int s = it % stages;
+      mbar_wait(full_bar(s), (it / stages) & 1);
+      if (it == 0 && lane == 0) trace(3);
       tc_fence_after();
       const uint32_t st = base + s * kStageBytes;
       const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kABytes);
       const uint64_t b_hi = umma_desc_sw128(st + kBOff), b_lo = umma_desc_sw128(st + kBOff + kBBytes);
+      const uint32_t acc_addr = tmem_acc + uint32_t(sub * BN);
+      if (NSUB > 1 && kb == 0) accumulate = 0;  // a fresh accumulator per sub-tile (no pre-initialisation with NSUB > 1)
       if (elect_one()) {
         uint32_t acc = accumulate;
 #pragma unroll
         for (int kk = 0; kk < BK / 16; ++kk) {
           const uint64_t adv = uint64_t(kk * 32 >> 4);  // 16 elements x 2 B along K inside the swizzle row
           if (need_b_lo) {
-            tc_mma_f16(tmem_acc, a_hi + adv, b_lo + adv, idesc, acc);
+            tc_mma_f16(acc_addr, a_hi + adv, b_lo + adv, idesc, acc);
             acc = 1;
           }
           if (need_a_lo) {
-            tc_mma_f16(tmem_acc, a_lo + adv, b_hi + adv, idesc, acc);
+            tc_mma_f16(acc_addr, a_lo + adv, b_hi + adv, idesc, acc);
             acc = 1;
           }
-          tc_mma_f16(tmem_acc, a_hi + adv, b_hi + adv, idesc, acc);
+          tc_mma_f16(acc_addr, a_hi + adv, b_hi + adv, idesc, acc);
           acc = 1;
         }
         tc_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
-        if (kb == num_kb - 1) tc_commit(tmem_full_bar);  // accumulator complete
+        if (kb == num_kb - 1) tc_commit(tmem_full_bar + 8u * sub);  // this accumulator is complete
       }
       __syncwarp();
       accumulate = 1;
@@ -658,12 +679,18 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     const float* col = reinterpret_cast<const float*>(gen(col_base));
     EpiCtx E;
     E.stage = reinterpret_cast<float*>(gen(stage_base)) + (warp - 2) * (kEpiWarpBytes / 4);
-    E.col_bias = col, E.col_g = col + BN, E.col_b = col + 2 * BN;
+    E.col_bias = col, E.col_g = col + CW, E.col_b = col + 2 * CW;
     E.row0 = m0 + quad * 32;
     E.rows_valid = int(min(int64_t(32), max(int64_t(0), P.M - E.row0)));
     E.lane = lane;
-    // output boxes live in the (by then idle) operand ring: 2 x 8 KB per epilogue warp
-    E.out_stage = base + uint32_t(warp - 2) * 16384u;
+    // output boxes live in the (by then idle) operand ring: 2 x 8 KB per epilogue warp; with sub-tiles the ring
+    // stays busy: 8 KB of dedicated staging per warp, split in two when only one kind of output is written
+    E.out_stage = NSUB > 1 ? ostage_base + uint32_t(warp - 2) * 8192u : base + uint32_t(warp - 2) * 16384u;
+    E.nbuf = 2, E.buf_stride = 8192u;
+    if (NSUB > 1) {
+      const bool both = Q.y != nullptr && Q.y_planes != nullptr;
+      E.nbuf = both ? 1u : 2u, E.buf_stride = 4096u;
+    }
     E.out_stage_gen = gen(E.out_stage);
     E.map_y = &P.map_y[g];
     E.map_p = &P.map_p[g];
@@ -682,11 +709,15 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     if constexpr (LN >= 2) {
       if (P.res_staged) mbar_wait(res_bar, 0);  // landed long before the accumulator is complete
     }
-    mbar_wait(tmem_full_bar, 0);
-    if (threadIdx.x == 64) trace(5);
-    tc_fence_after();
-    epilogue_rows<BN, LN, FMT, EW>(P, Q, E, my_tmem, n0, half, reinterpret_cast<float2*>(gen(stats_base)), xstats_base,
-                               quad * 32 + lane);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+      mbar_wait(tmem_full_bar + 8u * sub, 0);
+      if (threadIdx.x == 64 && sub == 0) trace(5);
+      tc_fence_after();
+      if (NSUB > 1) E.col_bias = col + sub * BN;  // this sub-tile's slice of the staged column parameters
+      epilogue_rows<BN, LN, FMT, EW>(P, Q, E, my_tmem + uint32_t(sub * BN), n0 + sub * BN, half,
+                                     reinterpret_cast<float2*>(gen(stats_base)), xstats_base, quad * 32 + lane);
+    }
     // the boxes must have been READ out of shared memory before the CTA exits; the global writes drain behind it
     // (they are part of the grid's memory operations: the next kernel's griddepcontrol.wait / stream order covers them)
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -699,13 +730,19 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   if (threadIdx.x == 0) trace(8);
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(BN)) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(CW)) : "memory");
   }
 }
 
 template <int BN, int LN, int FMT>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_kernel(const __grid_constant__ TcParams P) {
   linear_tc_body<BN, LN, FMT, kEpiWarps>(P);
+}
+
+// One-wave grids of 256-column tiles run them as two 128-column sub-tiles (NSUB = 2, see linear_tc_body).
+template <int FMT>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_sub2_kernel(const __grid_constant__ TcParams P) {
+  linear_tc_body<128, 0, FMT, kEpiWarps, 2>(P);
 }
 
 // Multi-wave grids (large batches): a 128 x 128 tile per CTA with one epilogue warp per TMEM quadrant and a
@@ -831,6 +868,29 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
 }
 
 template <int FMT>
+int launch_sub2_fmt(TcParams& P, int group, cudaStream_t s) {
+  constexpr int BN = 128, NSUB = 2;
+  const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
+  const size_t ostage = size_t(kEpiWarps) * 8192;
+  const int num_kb = (P.K + BK - 1) / BK;
+  int stages = int((200u * 1024u - ostage) / kStageBytes);
+  if (stages > NSUB * num_kb) stages = NSUB * num_kb;
+  if (stages > 8) stages = 8;
+  if (stages < 1) stages = 1;
+  P.stages = stages;
+  const size_t smem = size_t(stages) * kStageBytes + ostage + 1024 + 16 * stages + 64 + 8 * NSUB + 3 * BN * NSUB * 4 + 3 * BM * 8 +
+                      kEpiWarps * kEpiWarpBytes;
+  static std::atomic<bool> attr_done{false};
+  if (!attr_done.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_sub2_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done.store(true);
+  }
+  dim3 grid((P.N + BN * NSUB - 1) / (BN * NSUB), unsigned((P.M + BM - 1) / BM), group);
+  (void)launch_kernel(linear_tc_sub2_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
+  return after_launch("linear_tc_sub2_kernel");
+}
+
+template <int FMT>
 int launch_dual_fmt(TcParams& P, int group, cudaStream_t s) {
   constexpr int BN = 128, EW = 4;
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
@@ -911,6 +971,8 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   }
   const bool dual = BN == 0;
   if (dual) BN = 128;
+  const bool sub2 = !fused_ln && !dual && BN == 256 && SCATT_SUB2;  // 256-wide tiles as two 128-wide sub-tiles
+  if (sub2) BN = 128;
 
   TcParams P{};
   P.ep = ep;
@@ -928,6 +990,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   // Cluster LayerNorm kernels take the residual tile through TMA into shared memory (one 64 KB fetch beside the
   // operand loads) and add it in the epilogue: fetched with ld.global - into the accumulator up front or in the
   // epilogue - it cost 3-5 k cycles per launch either way (profiles/r01_linear_phase_trace_v5.txt).
+  if (sub2) P.pre_init = 0;  // the accumulators are started by the MMAs (the residual, if any, is added in the epilogue)
   P.res_staged = (SCATT_RES_STAGED && ln_cluster >= 2 && P.ep.residual_mode != SCATT_RES_NONE) ? 1 : 0;
   if (P.res_staged) P.pre_init = 0;
   for (int i = 0; i < group; ++i) {
@@ -962,6 +1025,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
        : ln_cluster == 2 ? launch_bn<128, 2>(P, group, s)
        : ln_cluster == 4 ? launch_bn<128, 4>(P, group, s) : launch_bn<128, 8>(P, group, s);
   else if (dual) rc = fmt == SCATT_PLANE_F16 ? launch_dual_fmt<SCATT_PLANE_F16>(P, group, s) : launch_dual_fmt<SCATT_PLANE_BF16>(P, group, s);
+  else if (sub2) rc = fmt == SCATT_PLANE_F16 ? launch_sub2_fmt<SCATT_PLANE_F16>(P, group, s) : launch_sub2_fmt<SCATT_PLANE_BF16>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));
   if (rc != SCATT_OK || !split_ln) return rc;
   return launch_rowwise_linear_tail(p, group, M, N, ldres, ldy, ep, fmt, s);
