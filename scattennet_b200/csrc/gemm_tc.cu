@@ -31,6 +31,9 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef SCATT_PERSIST
+#define SCATT_PERSIST 1
+#endif
 #ifndef SCATT_SUB2
 #define SCATT_SUB2 1
 #endif
@@ -65,7 +68,7 @@ struct alignas(64) TcParams {
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
-  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged;
+  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, groups;
 };
 
 // Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
@@ -745,6 +748,184 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_sub2_kernel(
   linear_tc_body<128, 0, FMT, kEpiWarps, 2>(P);
 }
 
+// ------------------------------------------------------------------ persistent kernel (multi-wave grids)
+// One CTA per SM walks 128 x 128 output tiles (tile = cta, cta + grid, ...; column tiles fastest, so the CTAs
+// of a moment share their A tiles in L2).  Two TMEM accumulators alternate: while the eight epilogue warps drain
+// tile i (bias / scaling / GELU / residual / clamp, TMA stores out of dedicated staging), the MMA warp already
+// accumulates tile i + 1 from an operand ring that runs ahead across tile boundaries.  tmem_full / tmem_empty
+// mbarriers hand the accumulators back and forth.  No LayerNorm here (its kernels own whole rows).
+template <int FMT>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kernel(const __grid_constant__ TcParams P) {
+  constexpr int BN = 128, EW = kEpiWarps;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr uint32_t kABytes = BM * 128, kBBytes = BN * 128;
+  const bool need_a_lo = P.terms >= 2, need_b_lo = P.terms >= 3;
+  const uint32_t kBOff = kABytes * (need_a_lo ? 2 : 1);
+  const uint32_t kStageBytes = kBOff + kBBytes * (need_b_lo ? 2 : 1);
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int stages = P.stages;
+  const uint32_t ostage_base = base + uint32_t(stages) * kStageBytes;    // EW x 8 KB output staging
+  const uint32_t bar_base = ostage_base + uint32_t(EW) * 8192u;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 16u * stages;   // [2]
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16u;      // [2]
+  const uint32_t tmem_ptr_addr = tmem_empty_bar + 16u;
+  const uint32_t col_base = (tmem_ptr_addr + 4u + 15u) & ~15u;  // float[2][BN] bias of the tile, double-buffered
+  const uint32_t stage_base = col_base + 2u * BN * 4u;          // EW transposition tiles (residual fetch)
+  auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = (P.K + BK - 1) / BK;
+  const int tiles_n = (P.N + BN - 1) / BN, tiles_m = int((P.M + BM - 1) / BM);
+  const int tiles_per_group = tiles_n * tiles_m, total_tiles = tiles_per_group * int(P.groups);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar + 8u * a, 1);
+      mbar_init(tmem_empty_bar + 8u * a, 32 * EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int g = 0; g < int(P.groups); ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_a[g]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_acc = *tmem_ptr_gen;
+
+  if (warp == 0) {  // ---------------- TMA producer
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int g = t / tiles_per_group, r = t % tiles_per_group;
+      const int m0 = (r / tiles_n) * BM, n0 = (r % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(empty_bar(s), ((it / stages) & 1) ^ 1);
+        const uint32_t st = base + s * kStageBytes;
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          tma_load_3d(st, &P.map_a[g], full_bar(s), kb * BK, m0, 0);
+          if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kb * BK, m0, 1);
+          tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, n0, 0);
+          if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, n0, 1);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {  // ---------------- MMA issuer
+    const uint32_t idesc = (1u << 4) | (uint32_t(FMT) << 7) | (uint32_t(FMT) << 10) | (uint32_t(BN >> 3) << 17) |
+                           (uint32_t(BM >> 4) << 24);
+    int it = 0, i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int a = i & 1;
+      mbar_wait(tmem_empty_bar + 8u * a, ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_acc + uint32_t(a * BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(full_bar(s), (it / stages) & 1);
+        tc_fence_after();
+        const uint32_t st = base + s * kStageBytes;
+        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kABytes);
+        const uint64_t b_hi = umma_desc_sw128(st + kBOff), b_lo = umma_desc_sw128(st + kBOff + kBBytes);
+        if (elect_one()) {
+          uint32_t acc = kb > 0 ? 1u : 0u;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adv = uint64_t(kk * 32 >> 4);
+            if (need_b_lo) {
+              tc_mma_f16(acc_addr, a_hi + adv, b_lo + adv, idesc, acc);
+              acc = 1;
+            }
+            if (need_a_lo) {
+              tc_mma_f16(acc_addr, a_lo + adv, b_hi + adv, idesc, acc);
+              acc = 1;
+            }
+            tc_mma_f16(acc_addr, a_hi + adv, b_hi + adv, idesc, acc);
+            acc = 1;
+          }
+          tc_commit(empty_bar(s));
+          if (kb == num_kb - 1) tc_commit(tmem_full_bar + 8u * a);
+        }
+        __syncwarp();
+      }
+    }
+  } else {  // ---------------- epilogue warps 2..9
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    float* col = reinterpret_cast<float*>(gen(col_base));
+    EpiCtx E;
+    E.stage = reinterpret_cast<float*>(gen(stage_base)) + (warp - 2) * (kEpiWarpBytes / 4);
+    E.col_g = E.col_b = nullptr;
+    E.lane = lane;
+    E.out_stage = ostage_base + uint32_t(warp - 2) * 8192u;
+    E.out_stage_gen = gen(E.out_stage);
+    E.stores = 0;
+    E.res_box = nullptr;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int g = t / tiles_per_group, r = t % tiles_per_group;
+      const int64_t m0 = int64_t(r / tiles_n) * BM;
+      const int n0 = (r % tiles_n) * BN, a = i & 1;
+      const TcProblem& Q = P.prob[g];
+      const bool both = Q.y != nullptr && Q.y_planes != nullptr;
+      E.nbuf = both ? 1u : 2u, E.buf_stride = 4096u;
+      E.map_y = &P.map_y[g], E.map_p = &P.map_p[g];
+      E.row0 = m0 + quad * 32;
+      E.rows_valid = int(min(int64_t(32), max(int64_t(0), P.M - E.row0)));
+      // this tile's bias slice -> col[a] (double-buffered: the other half may still be read by slower warps)
+      if (threadIdx.x - 64 < BN) {
+        const int c = threadIdx.x - 64;
+        col[a * BN + c] = (n0 + c < P.N && Q.bias) ? Q.bias[n0 + c] : 0.f;
+      }
+      epi_bar_sync();
+      E.col_bias = col + a * BN;
+      mbar_wait(tmem_full_bar + 8u * a, (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t my_tmem = tmem_acc + uint32_t(a * BN) + (uint32_t(quad * 32) << 16);
+      {  // epilogue_rows<LN = 0>, with the accumulator released right after its last TMEM read
+        constexpr int kMine = BN / 32 / (EW / 4);
+        const bool late_res = P.ep.residual_mode != SCATT_RES_NONE;
+        float v[kMine][32];
+#pragma unroll
+        for (int c = 0; c < kMine; ++c)
+          if (n0 + (half * kMine + c) * 32 < P.N) tc_ld32(my_tmem + (half * kMine + c) * 32, v[c]);
+        tc_fence_before();
+        mbar_arrive(tmem_empty_bar + 8u * a);
+#pragma unroll
+        for (int c = 0; c < kMine; ++c) {
+          const int cl = (half * kMine + c) * 32, c0 = n0 + cl;
+          if (c0 >= P.N) break;
+          chunk_pre(P, Q, E, v[c], cl, c0, late_res);
+          chunk_store<FMT>(P, Q, E, v[c], c0);
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(2 * BN)) : "memory");
+  }
+}
+
 // Multi-wave grids (large batches): a 128 x 128 tile per CTA with one epilogue warp per TMEM quadrant and a
 // single-stage operand ring needs < 100 KB of shared memory, 128 TMEM columns and 192 threads, so TWO CTAs are
 // resident per SM and the hardware overlaps one CTA's epilogue with the other's TMA / MMA phase - the
@@ -891,6 +1072,29 @@ int launch_sub2_fmt(TcParams& P, int group, cudaStream_t s) {
 }
 
 template <int FMT>
+int launch_persist_fmt(TcParams& P, int group, cudaStream_t s) {
+  constexpr int BN = 128;
+  const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
+  const size_t fixed = size_t(kEpiWarps) * 8192 + 1024 + 256 + 2 * BN * 4 + kEpiWarps * kEpiWarpBytes;
+  int stages = int((227u * 1024u - fixed) / kStageBytes);
+  if (stages > 8) stages = 8;
+  if (stages < 1) stages = 1;
+  P.stages = stages;
+  P.groups = group;
+  P.pre_init = 0;
+  const size_t smem = size_t(stages) * kStageBytes + fixed + 16 * stages;
+  static std::atomic<bool> attr_done{false};
+  if (!attr_done.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_persist_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done.store(true);
+  }
+  const int64_t tiles = int64_t((P.N + BN - 1) / BN) * ((P.M + BM - 1) / BM) * group;
+  dim3 grid(unsigned(tiles < 148 ? tiles : 148));
+  (void)launch_kernel(linear_tc_persist_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
+  return after_launch("linear_tc_persist_kernel");
+}
+
+template <int FMT>
 int launch_dual_fmt(TcParams& P, int group, cudaStream_t s) {
   constexpr int BN = 128, EW = 4;
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
@@ -1024,6 +1228,7 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     rc = ln_cluster == 1 ? launch_bn<256, 1>(P, group, s)
        : ln_cluster == 2 ? launch_bn<128, 2>(P, group, s)
        : ln_cluster == 4 ? launch_bn<128, 4>(P, group, s) : launch_bn<128, 8>(P, group, s);
+  else if (dual && SCATT_PERSIST) rc = fmt == SCATT_PLANE_F16 ? launch_persist_fmt<SCATT_PLANE_F16>(P, group, s) : launch_persist_fmt<SCATT_PLANE_BF16>(P, group, s);
   else if (dual) rc = fmt == SCATT_PLANE_F16 ? launch_dual_fmt<SCATT_PLANE_F16>(P, group, s) : launch_dual_fmt<SCATT_PLANE_BF16>(P, group, s);
   else if (sub2) rc = fmt == SCATT_PLANE_F16 ? launch_sub2_fmt<SCATT_PLANE_F16>(P, group, s) : launch_sub2_fmt<SCATT_PLANE_BF16>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));

@@ -172,6 +172,30 @@ def test_linear_multi_wave_dual_cta_path(mode, epi, shape):
         assert float((rec - out.f32).abs().max()) <= 2.0 ** (-21 if mode.startswith("fp16") else -15) * float(out.f32.abs().max()) + 1e-7
 
 
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
+@pytest.mark.parametrize("epi", ["bias", "gelu", "qscale"])
+@pytest.mark.parametrize("out", ["planes", "f32", "both"])
+def test_linear_multi_wave_grouped_outputs(mode, epi, out):
+    """Multi-wave grids run the persistent kernel (one CTA per SM walks 128 x 128 tiles, two TMEM accumulators):
+    three grouped problems, ragged M and N tails, every output combination (the staging differs)."""
+    G, M, N, K = 3, 128 * 21 + 77, 736, 320
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    xs = [rnd(M, K, seed=60 + g) for g in range(G)]
+    lins = [make_linear(N, K, 70 + g) for g in range(G)]
+    outs = F_.linear(prec, [Act(x) for x in xs], [F_.PackedLinear([l], None, None) for l in lins], F_.make_epilogue(**kw),
+                     out_f32=out != "planes", out_planes=out != "f32")
+    torch.cuda.synchronize()
+    for g in range(G):
+        ref = ref_chain(xs[g], lins[g], kw)
+        o = outs[g]
+        if out != "planes":
+            assert float((o.f32.double() - ref).abs().max()) <= MODE_TOL[mode] * max(1.0, math.sqrt(K / 256)), (mode, epi, out, g)
+        if out != "f32":
+            rec = o.planes[0].double() + o.planes[1].double()
+            assert float((rec - ref).abs().max()) <= MODE_TOL[mode] * max(1.0, math.sqrt(K / 256)) + 1e-6, (mode, epi, out, g)
+
+
 @pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
 @pytest.mark.parametrize("shape", [(128 * 80 + 17, 256, 256), (128 * 75, 256, 768)])
 def test_linear_residual_from_planes(mode, shape):
