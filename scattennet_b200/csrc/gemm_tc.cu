@@ -34,6 +34,9 @@
 #ifndef SCATT_PERSIST
 #define SCATT_PERSIST 1
 #endif
+#ifndef SCATT_PERSIST_WIDE
+#define SCATT_PERSIST_WIDE 1
+#endif
 #ifndef SCATT_SUB2
 #define SCATT_SUB2 1
 #endif
@@ -754,9 +757,13 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_sub2_kernel(
 // tile i (bias / scaling / GELU / residual / clamp, TMA stores out of dedicated staging), the MMA warp already
 // accumulates tile i + 1 from an operand ring that runs ahead across tile boundaries.  tmem_full / tmem_empty
 // mbarriers hand the accumulators back and forth.  No LayerNorm here (its kernels own whole rows).
-template <int FMT>
+// SLIM (BN = 256): 128 x 256 tiles for launches without a residual that write one kind of output - 4 KB of
+// output staging per warp and no transposition tiles leave room for two 96 KB operand stages, i.e. twice the
+// MMA work per byte in flight (the 128-wide variant's main loop waits on TMA latency with its two stages).
+template <int FMT, int BN, bool SLIM>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kernel(const __grid_constant__ TcParams P) {
-  constexpr int BN = 128, EW = kEpiWarps;
+  constexpr int EW = kEpiWarps;
+  constexpr uint32_t kWarpStage = SLIM ? 4096u : 8192u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr uint32_t kABytes = BM * 128, kBBytes = BN * 128;
   const bool need_a_lo = P.terms >= 2, need_b_lo = P.terms >= 3;
@@ -765,8 +772,8 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kern
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int stages = P.stages;
-  const uint32_t ostage_base = base + uint32_t(stages) * kStageBytes;    // EW x 8 KB output staging
-  const uint32_t bar_base = ostage_base + uint32_t(EW) * 8192u;
+  const uint32_t ostage_base = base + uint32_t(stages) * kStageBytes;    // EW x 8 (4) KB output staging
+  const uint32_t bar_base = ostage_base + uint32_t(EW) * kWarpStage;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
   const uint32_t tmem_full_bar = bar_base + 16u * stages;   // [2]
@@ -869,10 +876,10 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kern
     const int quad = warp & 3, half = (warp - 2) >> 2;
     float* col = reinterpret_cast<float*>(gen(col_base));
     EpiCtx E;
-    E.stage = reinterpret_cast<float*>(gen(stage_base)) + (warp - 2) * (kEpiWarpBytes / 4);
+    E.stage = SLIM ? nullptr : reinterpret_cast<float*>(gen(stage_base)) + (warp - 2) * (kEpiWarpBytes / 4);
     E.col_g = E.col_b = nullptr;
     E.lane = lane;
-    E.out_stage = ostage_base + uint32_t(warp - 2) * 8192u;
+    E.out_stage = ostage_base + uint32_t(warp - 2) * kWarpStage;
     E.out_stage_gen = gen(E.out_stage);
     E.stores = 0;
     E.res_box = nullptr;
@@ -883,35 +890,41 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kern
       const int n0 = (r % tiles_n) * BN, a = i & 1;
       const TcProblem& Q = P.prob[g];
       const bool both = Q.y != nullptr && Q.y_planes != nullptr;
-      E.nbuf = both ? 1u : 2u, E.buf_stride = 4096u;
+      E.nbuf = (both || SLIM) ? 1u : 2u, E.buf_stride = 4096u;
       E.map_y = &P.map_y[g], E.map_p = &P.map_p[g];
       E.row0 = m0 + quad * 32;
       E.rows_valid = int(min(int64_t(32), max(int64_t(0), P.M - E.row0)));
       // this tile's bias slice -> col[a] (double-buffered: the other half may still be read by slower warps)
-      if (threadIdx.x - 64 < BN) {
-        const int c = threadIdx.x - 64;
-        col[a * BN + c] = (n0 + c < P.N && Q.bias) ? Q.bias[n0 + c] : 0.f;
+      if constexpr (SLIM) {
+        E.col_bias = Q.bias + n0;  // read in place (warp-uniform, L1-resident): no room for a staged copy
+      } else {
+        for (int c = threadIdx.x - 64; c < BN; c += 32 * EW) col[a * BN + c] = (n0 + c < P.N && Q.bias) ? Q.bias[n0 + c] : 0.f;
+        epi_bar_sync();
+        E.col_bias = col + a * BN;
       }
-      epi_bar_sync();
-      E.col_bias = col + a * BN;
       mbar_wait(tmem_full_bar + 8u * a, (i >> 1) & 1);
       tc_fence_after();
       const uint32_t my_tmem = tmem_acc + uint32_t(a * BN) + (uint32_t(quad * 32) << 16);
       {  // epilogue_rows<LN = 0>, with the accumulator released right after its last TMEM read
         constexpr int kMine = BN / 32 / (EW / 4);
-        const bool late_res = P.ep.residual_mode != SCATT_RES_NONE;
-        float v[kMine][32];
-#pragma unroll
-        for (int c = 0; c < kMine; ++c)
-          if (n0 + (half * kMine + c) * 32 < P.N) tc_ld32(my_tmem + (half * kMine + c) * 32, v[c]);
-        tc_fence_before();
-        mbar_arrive(tmem_empty_bar + 8u * a);
-#pragma unroll
-        for (int c = 0; c < kMine; ++c) {
+        const bool late_res = !SLIM && P.ep.residual_mode != SCATT_RES_NONE;
+        int nvalid = (P.N - n0 - half * kMine * 32 + 31) / 32;  // chunks of this warp left of N
+        nvalid = nvalid < 0 ? 0 : (nvalid > kMine ? kMine : nvalid);
+        if (nvalid == 0) {
+          tc_fence_before();
+          mbar_arrive(tmem_empty_bar + 8u * a);
+        }
+        float v[32];
+#pragma unroll 1
+        for (int c = 0; c < nvalid; ++c) {
           const int cl = (half * kMine + c) * 32, c0 = n0 + cl;
-          if (c0 >= P.N) break;
-          chunk_pre(P, Q, E, v[c], cl, c0, late_res);
-          chunk_store<FMT>(P, Q, E, v[c], c0);
+          tc_ld32(my_tmem + cl, v);
+          if (c == nvalid - 1) {
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar + 8u * a);
+          }
+          chunk_pre(P, Q, E, v, cl, c0, late_res);
+          chunk_store<FMT>(P, Q, E, v, c0);
         }
       }
     }
@@ -1071,12 +1084,11 @@ int launch_sub2_fmt(TcParams& P, int group, cudaStream_t s) {
   return after_launch("linear_tc_sub2_kernel");
 }
 
-template <int FMT>
+template <int FMT, int BN, bool SLIM>
 int launch_persist_fmt(TcParams& P, int group, cudaStream_t s) {
-  constexpr int BN = 128;
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
-  const size_t fixed = size_t(kEpiWarps) * 8192 + 1024 + 256 + 2 * BN * 4 + kEpiWarps * kEpiWarpBytes;
-  int stages = int((227u * 1024u - fixed) / kStageBytes);
+  const size_t fixed = size_t(kEpiWarps) * (SLIM ? 4096 : 8192) + 1024 + 256 + (SLIM ? 0 : 2 * BN * 4 + kEpiWarps * kEpiWarpBytes);
+  int stages = int((227u * 1024u - fixed - 128) / kStageBytes);
   if (stages > 8) stages = 8;
   if (stages < 1) stages = 1;
   P.stages = stages;
@@ -1085,12 +1097,12 @@ int launch_persist_fmt(TcParams& P, int group, cudaStream_t s) {
   const size_t smem = size_t(stages) * kStageBytes + fixed + 16 * stages;
   static std::atomic<bool> attr_done{false};
   if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_persist_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCATT_CUDA(cudaFuncSetAttribute(linear_tc_persist_kernel<FMT, BN, SLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done.store(true);
   }
   const int64_t tiles = int64_t((P.N + BN - 1) / BN) * ((P.M + BM - 1) / BM) * group;
   dim3 grid(unsigned(tiles < 148 ? tiles : 148));
-  (void)launch_kernel(linear_tc_persist_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
+  (void)launch_kernel(linear_tc_persist_kernel<FMT, BN, SLIM>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
   return after_launch("linear_tc_persist_kernel");
 }
 
@@ -1175,8 +1187,13 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   }
   const bool dual = BN == 0;
   if (dual) BN = 128;
+  bool one_kind = true;  // every problem writes fp32 or planes, not both
+  for (int i = 0; i < group; ++i) one_kind = one_kind && !(p[i].y && p[i].y_planes && !split_ln);
   const bool sub2 = !fused_ln && !dual && BN == 256 && SCATT_SUB2;  // 256-wide tiles as two 128-wide sub-tiles
   if (sub2) BN = 128;
+  // multi-wave launches without a residual that write one kind of output: 128 x 256 tiles in the persistent kernel
+  const bool persist_wide = dual && SCATT_PERSIST && SCATT_PERSIST_WIDE && one_kind && ep.residual_mode == SCATT_RES_NONE && !split_ln && N >= 256;
+  if (persist_wide) BN = 256;
 
   TcParams P{};
   P.ep = ep;
@@ -1228,7 +1245,10 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     rc = ln_cluster == 1 ? launch_bn<256, 1>(P, group, s)
        : ln_cluster == 2 ? launch_bn<128, 2>(P, group, s)
        : ln_cluster == 4 ? launch_bn<128, 4>(P, group, s) : launch_bn<128, 8>(P, group, s);
-  else if (dual && SCATT_PERSIST) rc = fmt == SCATT_PLANE_F16 ? launch_persist_fmt<SCATT_PLANE_F16>(P, group, s) : launch_persist_fmt<SCATT_PLANE_BF16>(P, group, s);
+  else if (dual && SCATT_PERSIST && persist_wide)
+    rc = fmt == SCATT_PLANE_F16 ? launch_persist_fmt<SCATT_PLANE_F16, 256, true>(P, group, s) : launch_persist_fmt<SCATT_PLANE_BF16, 256, true>(P, group, s);
+  else if (dual && SCATT_PERSIST)
+    rc = fmt == SCATT_PLANE_F16 ? launch_persist_fmt<SCATT_PLANE_F16, 128, false>(P, group, s) : launch_persist_fmt<SCATT_PLANE_BF16, 128, false>(P, group, s);
   else if (dual) rc = fmt == SCATT_PLANE_F16 ? launch_dual_fmt<SCATT_PLANE_F16>(P, group, s) : launch_dual_fmt<SCATT_PLANE_BF16>(P, group, s);
   else if (sub2) rc = fmt == SCATT_PLANE_F16 ? launch_sub2_fmt<SCATT_PLANE_F16>(P, group, s) : launch_sub2_fmt<SCATT_PLANE_BF16>(P, group, s);
   else rc = BN == 256 ? launch_bn<256, 0>(P, group, s) : (BN == 128 ? launch_bn<128, 0>(P, group, s) : launch_bn<64, 0>(P, group, s));

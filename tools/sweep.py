@@ -65,7 +65,7 @@ def kernel_sweep(args):
     print(f"### stream attention, B*3 streams grouped, H=16, hd=16 (us per grouped launch, back-to-back in a CUDA graph)\n")
     print("| T | B | kind | engine | us | TFLOP/s (4BT^2D, causal half) | % bf16 peak | exp/s (1e12) |")
     print("|---|---|---|---|---|---|---|---|")
-    for T in (64, 128, 192, 200, 256, 320, 384, 448, 512):
+    for T in (() if args.only == "linear" else (64, 128, 192, 200, 256, 320, 384, 448, 512)):
         B = max(1, 12800 // T)
         qkv = [torch.randn(B * T, 3 * D, generator=gen).to(dev) for _ in range(3)]
         km = torch.ones(B, T, dtype=torch.uint8, device=dev)
@@ -164,5 +164,6 @@ if __name__ == "__main__":
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024")
     ap.add_argument("--T", type=int, default=200)
     ap.add_argument("--config", default="phoenix-2014t")
+    ap.add_argument("--only", default="", help="kernels: 'linear' skips the attention section")
     a = ap.parse_args()
     {"batch": batch_sweep, "kernels": kernel_sweep, "membound": membound_sweep}[a.what](a)
