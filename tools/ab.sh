@@ -1,5 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "linear" 2>&1 | tail -3
-echo A_wide; python tools/sweep.py kernels --only linear 2>&1 | grep "fp16x3" | grep -v "^| 1600" | grep "qkv\|fc1"
-python tools/sweep.py batch --precision fp16x3 --batches 64,256 2>&1 | tail -2
-echo B_128; SCATT_LIB=$PWD/scattennet_b200/libscatt_b.so python tools/sweep.py kernels --only linear 2>&1 | grep "fp16x3" | grep -v "^| 1600" | grep "qkv\|fc1"
-SCATT_LIB=$PWD/scattennet_b200/libscatt_b.so python tools/sweep.py batch --precision fp16x3 --batches 64,256 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --batch 256 --steps 10 --warmup 3 --no-cpu-baseline --no-consumers 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('B256', round(d['ms_per_step'],3), d['value'], d['launches_per_step'], d['roofline'])"
