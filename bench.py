@@ -169,7 +169,7 @@ def run_ours(args):
     from scattennet_b200 import MSCAEncoder, _lib, synth
     from scattennet_b200 import functional as F_
     from scattennet_b200.config import model_config
-    from scattennet_b200.distributed import gather_logits
+    from scattennet_b200.distributed import gather_logits_peer as gather_logits  # NVLink peer-memory push; NCCL if unavailable
 
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a B200; the product path has no CPU fallback")

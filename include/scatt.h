@@ -38,6 +38,7 @@ extern "C" {
 
 #define SCATT_ABI_VERSION 2
 #define SCATT_MAX_GROUP 4 /* problems per grouped launch (the 3 anatomical streams + spare) */
+#define SCATT_MAX_PEERS 8  /* GPUs of one NVSwitch box taking part in scatt_peer_allgather */
 #define SCATT_MAX_FINITE 16 /* tensors per scatt_finite_check call */
 
 enum scatt_error {
@@ -278,6 +279,19 @@ int scatt_finite_check(const float* const* tensors_host, const int64_t* sizes_ho
  * beam <= 16; shared memory grows with V, T and beam (V = 1120, T = 512, beam = 5: ~75 KB). */
 int scatt_ctc_beam_decode(const float* logits, int B, int T, int V, const int32_t* lengths, int beam, int32_t* out_ids,
                           int32_t* out_len, float* out_score, void* stream);
+
+/* ------------------------------------------------------------------ K6: logits all-gather over NVLink peer memory
+ *
+ * The path's one exchange step (the reference has no parallelism, its NCCL group is never used:
+ * utils.py:237-265).  Rank `rank` pushes `bytes` (multiple of 16) from `src` into slot `rank` of every peer's
+ * gather buffer - peer_bufs_host[p] is the base of rank p's buffer [world][bytes], mapped into this process
+ * (torch.distributed symmetric memory / CUDA VMM) - and the same launch runs the barrier: it publishes `seq` in
+ * entry `rank` of every peer's flag pad (peer_flags_host[p]: uint64[world], zero-initialised) and returns, in
+ * stream order, once all `world` entries of its own pad have reached `seq`.  `seq` must grow by one per call and
+ * the caller must alternate between two buffers (seq parity), see csrc/peer.cu.  `counter_dev`: a zero-initialised
+ * uint32 of this rank.  A peer that never arrives traps the launch after a bounded spin instead of hanging. */
+int scatt_peer_allgather(const void* src, int64_t bytes, void* const* peer_bufs_host, void* const* peer_flags_host, int world,
+                         int rank, void* counter_dev, uint64_t seq, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ SYMBOLS = (
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
     "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
-    "scatt_ctc_beam_decode",
+    "scatt_ctc_beam_decode", "scatt_peer_allgather",
 )
 
 
@@ -116,6 +116,8 @@ def _declare(lib):
     lib.scatt_finite_check.restype = i32
     lib.scatt_ctc_beam_decode.argtypes = [vp, i32, i32, i32, vp, i32, vp, vp, vp, vp]
     lib.scatt_ctc_beam_decode.restype = i32
+    lib.scatt_peer_allgather.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, vp, C.c_uint64, vp]
+    lib.scatt_peer_allgather.restype = i32
     for name in ("scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_rowwise",
                  "scatt_attention", "scatt_fusion_attention", "scatt_pool_pairs"):
         getattr(lib, name).restype = i32

@@ -167,4 +167,9 @@ int scatt_ctc_beam_decode(const float* logits, int B, int T, int V, const int32_
   return launch_ctc_beam(logits, B, T, V, lengths, beam, out_ids, out_len, out_score, as_stream(stream));
 }
 
+int scatt_peer_allgather(const void* src, int64_t bytes, void* const* peer_bufs_host, void* const* peer_flags_host, int world,
+                         int rank, void* counter_dev, uint64_t seq, void* stream) {
+  return launch_peer_allgather(src, bytes, peer_bufs_host, peer_flags_host, world, rank, counter_dev, seq, as_stream(stream));
+}
+
 }  // extern "C"

@@ -214,6 +214,8 @@ int launch_log_softmax(const float* logits, int64_t ld, int V, int B, int T, int
 int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths, int beam, int* out_ids, int* out_len,
                     float* out_score, cudaStream_t s);
 int launch_finite_check(const float* const* tensors, const int64_t* sizes, int count, int* flags, cudaStream_t s);
+int launch_peer_allgather(const void* src, int64_t bytes, void* const* peer_bufs, void* const* peer_flags, int world, int rank,
+                          void* counter, uint64_t seq, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);
 

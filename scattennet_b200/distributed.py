@@ -55,6 +55,101 @@ def gather_logits(local: torch.Tensor, group=None) -> torch.Tensor:
     return out
 
 
+class PeerGather:
+    """All-gather of equally shaped shards over NVLink peer memory: one kernel per call (``scatt_peer_allgather``)
+    pushes this rank's shard into every peer's buffer and runs the barrier, instead of NCCL's ring of ``world - 1``
+    dependent hops.  Buffers are ``torch.distributed`` symmetric memory (CUDA VMM handles exchanged once, in
+    ``__init__`` - a collective call); two of them alternate so a shard never lands in a buffer a peer still reads.
+
+    ``gather(local)`` returns a view ``[world * B_loc, ...]`` of the current buffer, valid until the call after
+    the next one.  Construction raises if symmetric memory cannot be set up (callers fall back to
+    :func:`gather_logits`, the NCCL path)."""
+
+    def __init__(self, shard_shape, dtype=torch.float32, device=None, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib as L
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("PeerGather covers the GPUs of one NVSwitch box (<= 8)")
+        self.shard_shape = tuple(shard_shape)
+        self.dtype = dtype
+        esz = torch.empty(0, dtype=dtype).element_size()
+        n = 1
+        for d in self.shard_shape:
+            n *= int(d)
+        self.shard_bytes = n * esz
+        if self.shard_bytes % 16:
+            raise ValueError("PeerGather: the shard must be a multiple of 16 bytes")
+        self.buf_bytes = self.world * self.shard_bytes
+        pad = 256  # flag pad: uint64[world], kept apart from the data
+        total = 2 * self.buf_bytes + pad
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.mem = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self.mem.zero_()
+        self.handle = symm_mem.rendezvous(self.mem, self.group.group_name)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)  # every pad is zero before anybody signals
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._bufs = [(C.c_void_p * self.world)(*[p + par * self.buf_bytes for p in ptrs]) for par in range(2)]
+        self._flags = (C.c_void_p * self.world)(*[p + 2 * self.buf_bytes for p in ptrs])
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seq = 0
+        self._lib = L
+
+    def gather(self, local: torch.Tensor) -> torch.Tensor:
+        if tuple(local.shape) != self.shard_shape or local.dtype != self.dtype:
+            raise ValueError(f"PeerGather: expected a {self.shard_shape} {self.dtype} shard, got {tuple(local.shape)} {local.dtype}")
+        local = local.detach().contiguous()
+        self.seq += 1
+        par = self.seq & 1
+        L = self._lib
+        L.check(L.load().scatt_peer_allgather(local.data_ptr(), self.shard_bytes, self._bufs[par], self._flags, self.world, self.rank,
+                                              self.counter.data_ptr(), self.seq, torch.cuda.current_stream().cuda_stream),
+                "scatt_peer_allgather")
+        view = self.mem[par * self.buf_bytes:(par + 1) * self.buf_bytes].view(self.dtype)
+        return view.view((self.world * self.shard_shape[0],) + self.shard_shape[1:])
+
+
+_peer_gathers = {}
+
+
+def gather_logits_peer(local: torch.Tensor, group=None) -> torch.Tensor:
+    """:func:`gather_logits` over NVLink peer memory when it can be set up (one box, CUDA tensors, symmetric
+    memory available; ``SCATT_PEER_GATHER=0`` switches it off), else the NCCL all-gather.  The first call for a
+    shard shape is collective (it allocates and exchanges the buffers)."""
+    import os
+
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    key = (tuple(local.shape), local.dtype, str(local.device), id(group))
+    pg = _peer_gathers.get(key)
+    if pg is None:
+        pg = False
+        if local.is_cuda and os.environ.get("SCATT_PEER_GATHER", "1") != "0":
+            try:
+                pg = PeerGather(local.shape, local.dtype, local.device, group)
+            except Exception as exc:  # symmetric memory is not available here: keep NCCL (said once, on stderr)
+                import sys
+
+                print(f"[scattennet_b200] peer-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+                pg = False
+        # every rank must take the same route
+        ok = torch.tensor([1 if pg else 0], device=local.device if local.is_cuda else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            pg = False
+        _peer_gathers[key] = pg
+    if pg is False:
+        return gather_logits(local, group)
+    return pg.gather(local)
+
+
 def sharded_encoder_forward(model, keypoints: torch.Tensor, mask: torch.Tensor, group=None, head: str = "fuse_coord_gloss_logits"):
     """Run ``model`` on this rank's slice of the global batch and all-gather the
     logits of ``head``.  ``keypoints`` / ``mask`` are the *global* batch (host or

@@ -196,9 +196,9 @@ class MSCAEncoder(nn.Module):
         if gather:
             import torch.distributed as dist
 
-            from .distributed import gather_logits
+            from .distributed import gather_logits_peer
 
-            full = gather_logits(out[heads[0]])
+            full = gather_logits_peer(out[heads[0]])
             if dist.get_rank() == 0:
                 out = dict(out)
                 out[heads[0]] = full
