@@ -10,7 +10,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from scattennet_b200.distributed import gather_logits, partition, partition_by_length, sharded_encoder_forward
+from scattennet_b200.distributed import (gather_logits, gather_logits_peer, partition, partition_by_length,
+                                        sharded_encoder_forward)
 
 
 class StubEncoder(torch.nn.Module):
@@ -44,7 +45,9 @@ def _worker(rank, world, port, batch, ret):
         ref = model(kp, mask)["fuse_coord_gloss_logits"]
         ok = torch.equal(full, ref)
         same_shape = gather_logits(torch.full((2, 3), float(rank))).tolist()
-        ret[rank] = (ok, same_shape)
+        # host tensors cannot take the NVLink peer-memory route: both ranks must agree on the NCCL / gloo one
+        routed = gather_logits_peer(torch.full((2, 3), float(rank))).tolist()
+        ret[rank] = (ok and routed == same_shape, same_shape)
     finally:
         dist.destroy_process_group()
 

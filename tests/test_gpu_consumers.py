@@ -187,3 +187,20 @@ def test_forward_check_finite():
         m.coordinates_fusion.out_proj.bias[3] = float("inf")  # in-place under no_grad: bumps the version, weights repack
         with pytest.raises(ValueError, match="fuse_embed"):
             m(kp.to(DEV), mask.to(DEV), check_finite=True)
+
+
+def test_peer_gather_two_gpus():
+    """NVLink peer-memory logits gather (scatt_peer_allgather) against NCCL on two GPUs of one box: identical
+    values over several calls (both buffer parities).  Skipped on single-GPU boxes."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29547", os.path.join(root, "tools", "test_peer_gather.py")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "equal=True" in res.stdout
