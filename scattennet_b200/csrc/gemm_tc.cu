@@ -31,6 +31,9 @@
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef SCATT_RES_IN_RING
+#define SCATT_RES_IN_RING 1
+#endif
 #ifndef SCATT_PERSIST
 #define SCATT_PERSIST 1
 #endif
@@ -50,6 +53,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
+__host__ __device__ constexpr int num_kb_of(int K) { return (K + BK - 1) / BK; }
 constexpr int kEpiWarps = 8;   // default: two epilogue warps per TMEM lane quadrant (EW template parameter)
 
 struct TcProblem {
@@ -71,7 +75,7 @@ struct alignas(64) TcParams {
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
-  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, groups;
+  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, res_in_ring, groups;
 };
 
 // Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
@@ -529,7 +533,11 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   // cluster LayerNorm kernels: the CTA's residual tile (128 x 128 fp32 as 32 x 32 boxes, 64 KB) is staged by TMA
   constexpr uint32_t kResBytes = LN >= 2 ? uint32_t(EW) * 2u * 4096u : 0u;
   const uint32_t res_base = base + ring_bytes;
-  const uint32_t ostage_base = res_base + (P.res_staged ? kResBytes : 0u);
+  const uint32_t ostage_base = res_base + ((P.res_staged && !P.res_in_ring) ? kResBytes : 0u);
+  // res_in_ring (three 64 KB stages): the residual tile lands in the ring slot that is freed first at the end of
+  // the K loop, the output boxes take the other two slots - three operand stages AND the staged residual fit
+  const uint32_t res_slot = uint32_t(num_kb_of(P.K) % 3);
+  const uint32_t res_addr = P.res_in_ring ? base + res_slot * kStageBytes : res_base;
   const uint32_t bar_base = ostage_base + kOutStage;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
@@ -599,7 +607,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   if (warp == 0) {  // ---------------- TMA producer
     const uint32_t tx = kStageBytes;
     if constexpr (LN >= 2) {
-      if (P.res_staged) {  // residual boxes in epilogue-warp order: warp (quad, half), chunk i -> rows quad*32, cols (half*2+i)*32
+      if (P.res_staged && !P.res_in_ring) {  // residual boxes in epilogue-warp order: warp (quad, half), chunk i -> rows quad*32, cols (half*2+i)*32
         if (elect_one()) {
           mbar_expect_tx(res_bar, kResBytes);
           for (int b = 0; b < EW * 2; ++b) {
@@ -624,6 +632,20 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       }
       __syncwarp();
       if (it == 0 && lane == 0) trace(2);
+    }
+    if constexpr (LN >= 2) {
+      if (P.res_staged && P.res_in_ring) {  // the slot the next operand stage would take: free once its MMAs retired
+        const int it = num_kb, s = it % stages;
+        mbar_wait(empty_bar(s), ((it / stages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(res_bar, kResBytes);
+          for (int b = 0; b < EW * 2; ++b) {
+            const int w = b >> 1, i = b & 1, quad = (w + 2) & 3, half = w >> 2;
+            tma_load_2d(res_addr + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+          }
+        }
+        __syncwarp();
+      }
     }
     if constexpr (LN >= 2) {
       __syncwarp();
@@ -692,6 +714,8 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     // output boxes live in the (by then idle) operand ring: 2 x 8 KB per epilogue warp; with sub-tiles the ring
     // stays busy: 8 KB of dedicated staging per warp, split in two when only one kind of output is written
     E.out_stage = NSUB > 1 ? ostage_base + uint32_t(warp - 2) * 8192u : base + uint32_t(warp - 2) * 16384u;
+    if (LN >= 2 && P.res_in_ring)  // four warps in each of the two slots the residual does not occupy
+      E.out_stage = base + ((res_slot + 1u + (uint32_t(warp - 2) >> 2)) % 3u) * kStageBytes + (uint32_t(warp - 2) & 3u) * 16384u;
     E.nbuf = 2, E.buf_stride = 8192u;
     if (NSUB > 1) {
       const bool both = Q.y != nullptr && Q.y_planes != nullptr;
@@ -703,7 +727,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     E.stores = 0;
     E.res_box = nullptr;
     if constexpr (LN >= 2) {
-      if (P.res_staged) E.res_box = gen(res_base + uint32_t(warp - 2) * 2u * 4096u);
+      if (P.res_staged) E.res_box = gen(res_addr + uint32_t(warp - 2) * 2u * 4096u);
     }
     const uint32_t my_tmem = tmem_acc + (uint32_t(quad * 32) << 16);
     if (P.pre_init) {
@@ -713,7 +737,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       if (threadIdx.x == 64) trace(9);
     }
     if constexpr (LN >= 2) {
-      if (P.res_staged) mbar_wait(res_bar, 0);  // landed long before the accumulator is complete
+      if (P.res_staged) mbar_wait(res_bar, 0);  // lands before (dedicated region) or about when (ring slot) the accumulator completes
     }
 #pragma unroll 1
     for (int sub = 0; sub < NSUB; ++sub) {
@@ -1033,7 +1057,9 @@ template <int BN, int LN, int FMT>
 int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   const uint32_t kStageBytes = BM * 128 * (P.terms >= 2 ? 2 : 1) + BN * 128 * (P.terms >= 3 ? 2 : 1);
   const int num_kb = (P.K + BK - 1) / BK;
-  const size_t res_bytes = (LN >= 2 && P.res_staged) ? size_t(kEpiWarps) * 2 * 4096 : 0;  // TMA-staged residual tile
+  // TMA-staged residual tile: inside the ring when three 64 KB stages are in play, else in its own 64 KB
+  P.res_in_ring = (LN >= 2 && P.res_staged && SCATT_RES_IN_RING && kStageBytes == 65536u && num_kb >= 3) ? 1 : 0;
+  const size_t res_bytes = (LN >= 2 && P.res_staged && !P.res_in_ring) ? size_t(kEpiWarps) * 2 * 4096 : 0;
   int stages = int((197u * 1024u - res_bytes) / kStageBytes);
   if (stages > num_kb) stages = num_kb;
   if (stages > 8) stages = 8;
