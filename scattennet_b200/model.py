@@ -14,6 +14,7 @@ tokenizer stay outside.
 
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -27,6 +28,7 @@ from .fusion import CoordinatesFusion, coordinates_fusion_forward
 from .keypoint_module import KeypointModule, frontend_forward, streams_forward
 
 PARTS = ("body", "left", "right")  # order of model/__init__.py:133-142
+HOST_GRAPH = os.environ.get("SCATT_HOST_GRAPH", "1") != "0"  # forward_host as one graph (copies included)
 
 
 class LinearHeads(nn.Module):
@@ -190,6 +192,10 @@ class MSCAEncoder(nn.Module):
             self._host_staging[key] = st
         torch.index_select(keypoints, 2, used, out=st["kp_pin"])  # exact gather on the host
         st["mask_pin"].copy_(mask != 0)
+        if self.use_graph and not gather and decode_beam <= 0 and HOST_GRAPH:
+            # the whole step - both H2D copies, the encoder, the D2H copies of the requested heads - is ONE
+            # captured graph: a single launch instead of eight stream operations with the host in between
+            return self._host_graph_step(st, heads, dev)
         st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
         st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
         out = self.forward(st["kp_dev"], st["mask_dev"])
@@ -220,6 +226,31 @@ class MSCAEncoder(nn.Module):
             pin.copy_(out[k], non_blocking=True)
             res[k] = pin
         return res
+
+    def _host_graph_step(self, st, heads, dev):
+        key = ("hostgraph", tuple(heads), F_.get_precision(self.precision).name)
+        ent = st.get(key)
+        if ent is None:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():  # warm-up: packs weights, sets kernel attributes
+                st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
+                st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
+                for _ in range(2):
+                    out = self._run(st["kp_dev"], st["mask_dev"], True)
+                pins = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in heads}
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
+                st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
+                out = self._run_branches(st["kp_dev"], st["mask_dev"], True)
+                for k in heads:
+                    pins[k].copy_(out[k], non_blocking=True)
+            ent = st[key] = (graph, pins, out)
+        graph, pins, _ = ent
+        graph.replay()
+        return dict(pins)
 
     # ------------------------------------------------------------------ CUDA graph replay
     def _run_graph(self, keypoints, mask, with_heads):
