@@ -24,6 +24,21 @@
 //   * LayerNorm is fused when the CTA owns the whole row (N == BN == 256): one
 //     statistics pass over TMEM (Chan-combined between the two column halves),
 //     one normalise-and-store pass.
+//
+// Schedules (picked per launch in launch_linear_tc from M, N, the group size and the epilogue):
+//   linear_tc_ln_cluster_kernel<FMT, CL>   LayerNorm rows of 128 CL = 256 / 512 / 1024 columns over CL-CTA clusters
+//                                          (DSMEM statistics exchange), while the clusters fit one wave; the residual
+//                                          tile is staged by TMA (in the ring slot that frees first at the end of the
+//                                          K loop when three 64 KB stages are in play)
+//   linear_tc_kernel<256, 1, FMT>          LayerNorm with one CTA per 128 x 256 row tile (large batches; residual
+//                                          stream optionally in split planes only)
+//   linear_tc_sub2_kernel<FMT>             one-wave grids of 256-column tiles as two 128-column sub-tiles: the first
+//                                          sub-tile's epilogue overlaps the second's MMAs
+//   linear_tc_kernel<128 | 64, 0, FMT>     one-wave grids of narrower tiles
+//   linear_tc_persist_kernel<FMT, BN, SLIM> multi-wave grids: one CTA per SM walks tiles, two TMEM accumulators
+//   linear_tc_dual_kernel<FMT>             (SCATT_PERSIST=0 builds) two CTAs per SM instead
+// Compile-time switches for A/B builds (tools/ab.sh): SCATT_RES_STAGED, SCATT_RES_IN_RING, SCATT_SUB2,
+// SCATT_PERSIST, SCATT_PERSIST_WIDE (all default to 1).
 #include <cuda.h>
 
 #include <mutex>
