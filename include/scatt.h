@@ -151,9 +151,10 @@ typedef struct scatt_linear_problem {
   float* y;              /* [M, N] fp32, row stride ldy; may be NULL if y_planes is given and no LayerNorm scratch is needed */
   void* y_planes;        /* [2][M][N] split planes or NULL */
   const void* residual_planes; /* the residual as [2][M][N] split planes (hi + lo is added) when `residual` is NULL:
-                                * lets a residual stream live in planes only.  Large-batch LayerNorm GEMM of the
-                                * tcgen05 engine only: N = 256, M > 74 * 128 rows, RES_BEFORE_LN, no
-                                * pre-activation / column scaling */
+                                * lets a residual stream live in planes only.  LayerNorm GEMMs of the tcgen05 engine
+                                * only (scatt_linear_ln_fused): the cluster kernels stage the planes by TMA; the
+                                * one-CTA-per-row-tile kernel (N = 256, more than 74 row tiles) takes them with
+                                * RES_BEFORE_LN and no pre-activation / column scaling */
 } scatt_linear_problem;
 
 int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx,

@@ -86,11 +86,12 @@ struct alignas(64) TcParams {
   CUtensorMap map_b[SCATT_MAX_GROUP];
   CUtensorMap map_y[SCATT_MAX_GROUP];   // fp32 output  [M][ldy]      (box 32 x 32, 128B swizzle)
   CUtensorMap map_p[SCATT_MAX_GROUP];   // split planes [2][M][N]     (box 32 x 32 x 1, 64B swizzle)
-  CUtensorMap map_r[SCATT_MAX_GROUP];   // fp32 residual [M][ldres]   (box 32 x 32, 128B swizzle; cluster LayerNorm kernels)
+  CUtensorMap map_r[SCATT_MAX_GROUP];
+  CUtensorMap map_rp[SCATT_MAX_GROUP];  // residual kept as split planes [2][M][N] (box 32 x 32 x 1, 64B swizzle)   // fp32 residual [M][ldres]   (box 32 x 32, 128B swizzle; cluster LayerNorm kernels)
   TcProblem prob[SCATT_MAX_GROUP];
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
-  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, res_in_ring, groups;
+  int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, res_in_ring, res_planes, groups;
 };
 
 // Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
@@ -223,6 +224,20 @@ __device__ __forceinline__ void box_add(const EpiCtx& E, const uint8_t* box, flo
   }
 }
 
+// The same for a residual staged as split planes: hi box (32 rows x 64 B, 64-byte swizzle) at +0, lo box at +2048
+__device__ __forceinline__ void box_add_planes(const EpiCtx& E, const uint8_t* box, float* v, int fmt) {
+  const int r = E.lane;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t off = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+    const float4 h = *reinterpret_cast<const float4*>(box + off), l = *reinterpret_cast<const float4*>(box + 2048 + off);
+    const float2 p0 = unpack_pair(h.x, l.x, fmt), p1 = unpack_pair(h.y, l.y, fmt);
+    const float2 p2 = unpack_pair(h.z, l.z, fmt), p3 = unpack_pair(h.w, l.w, fmt);
+    v[8 * j] += p0.x, v[8 * j + 1] += p0.y, v[8 * j + 2] += p1.x, v[8 * j + 3] += p1.y;
+    v[8 * j + 4] += p2.x, v[8 * j + 5] += p2.y, v[8 * j + 6] += p3.x, v[8 * j + 7] += p3.y;
+  }
+}
+
 __device__ __forceinline__ void add_cols(float* v, const float* __restrict__ p) {  // p: shared memory, warp-uniform
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
@@ -351,7 +366,8 @@ __device__ __forceinline__ bool chunk_pre(const TcParams& P, const TcProblem& Q,
   }
   if (late_res) {
     if (E.res_box != nullptr) {  // staged by TMA (cluster LayerNorm kernels): chunk cl / 32 of this CTA's columns
-      box_add(E, E.res_box + (cl & 63) / 32 * 4096, v);
+      if (P.res_planes) box_add_planes(E, E.res_box + (cl & 63) / 32 * 4096, v, P.fmt);
+      else box_add(E, E.res_box + (cl & 63) / 32 * 4096, v);
     } else {
       float4 r[8];
       tile_fetch(E, Q.residual, P.ldres, c0, r);
@@ -521,6 +537,7 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
         v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
       }
       if (res_global) tile_add(E, r[i & 1], v);
+      else if (res_after && P.res_planes) box_add_planes(E, E.res_box + i * 4096, v, P.fmt);
       else if (res_after) box_add(E, E.res_box + i * 4096, v);
       chunk_store<FMT>(P, Q, E, v, n0 + cl);
     }
@@ -589,7 +606,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_b[g]) : "memory");
     if (Q.y) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_y[g]) : "memory");
     if (Q.y_planes) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_p[g]) : "memory");
-    if (LN >= 2 && P.res_staged) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_r[g]) : "memory");
+    if (LN >= 2 && P.res_staged) asm volatile("prefetch.tensormap [%0];" ::"l"(P.res_planes ? &P.map_rp[g] : &P.map_r[g]) : "memory");
   }
   if (warp == 1) {  // TMEM allocation (whole warp, .sync.aligned)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(uint32_t(CW))
@@ -627,7 +644,12 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
           mbar_expect_tx(res_bar, kResBytes);
           for (int b = 0; b < EW * 2; ++b) {
             const int w = b >> 1, i = b & 1, quad = (w + 2) & 3, half = w >> 2;
-            tma_load_2d(res_base + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+            if (P.res_planes) {
+              tma_load_3d(res_base + uint32_t(b) * 4096u, &P.map_rp[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32, 0);
+              tma_load_3d(res_base + uint32_t(b) * 4096u + 2048u, &P.map_rp[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32, 1);
+            } else {
+              tma_load_2d(res_base + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+            }
           }
         }
         __syncwarp();
@@ -656,7 +678,12 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
           mbar_expect_tx(res_bar, kResBytes);
           for (int b = 0; b < EW * 2; ++b) {
             const int w = b >> 1, i = b & 1, quad = (w + 2) & 3, half = w >> 2;
-            tma_load_2d(res_addr + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+            if (P.res_planes) {
+              tma_load_3d(res_addr + uint32_t(b) * 4096u, &P.map_rp[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32, 0);
+              tma_load_3d(res_addr + uint32_t(b) * 4096u + 2048u, &P.map_rp[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32, 1);
+            } else {
+              tma_load_2d(res_addr + uint32_t(b) * 4096u, &P.map_r[g], res_bar, n0 + (half * 2 + i) * 32, int(m0) + quad * 32);
+            }
           }
         }
         __syncwarp();
@@ -1258,10 +1285,9 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
   for (int i = 0; i < group; ++i) {
     SCATT_REQUIRE(p[i].x_planes && p[i].w_planes, "linear(tcgen05): problem %d lacks split planes", i);
     SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || p[i].residual_planes, "linear(tcgen05): residual missing");
-    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || (P.pre_init && ln_cluster == 1),
-                  "linear(tcgen05): a residual given as split planes is taken by the large-batch LayerNorm kernel only "
-                  "(N = 256, more than 74 row tiles, foldable into the accumulator: residual before LayerNorm, no "
-                  "pre-activation, no column scaling)");
+    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[i].residual || (P.pre_init && ln_cluster == 1) || P.res_staged,
+                  "linear(tcgen05): a residual given as split planes is taken by the LayerNorm kernels only (cluster kernels: any "
+                  "residual mode; N = 256 beyond 74 row tiles: residual before LayerNorm, no pre-activation, no column scaling)");
     SCATT_REQUIRE(!ep.layer_norm || (p[i].ln_g && p[i].ln_b), "linear(tcgen05): LayerNorm needs gamma and beta");
     SCATT_REQUIRE(!split_ln || p[i].y, "linear(tcgen05): LayerNorm that is not fused (scatt_linear_ln_fused) needs y as scratch");
     SCATT_REQUIRE(p[i].y || p[i].y_planes, "linear(tcgen05): no output");
@@ -1274,10 +1300,17 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
                           reinterpret_cast<const uint16_t*>(p[i].residual_planes)};
     rc = encode_out_maps(&P.map_y[i], &P.map_p[i], P.prob[i].y, ldy, P.prob[i].y_planes, M, N, fmt);
     if (rc != SCATT_OK) return rc;
-    if (P.res_staged) {
-      SCATT_REQUIRE(p[i].residual && (reinterpret_cast<uintptr_t>(p[i].residual) & 15) == 0,
-                    "linear(tcgen05): the cluster LayerNorm kernels need a 16-byte aligned fp32 residual");
-      rc = encode_out_maps(&P.map_r[i], nullptr, const_cast<float*>(p[i].residual), ldres, nullptr, M, N, fmt);
+    if (P.res_staged) {  // fp32 residual, or the residual stream kept in split planes only
+      const bool as_planes = p[i].residual == nullptr;
+      SCATT_REQUIRE(i == 0 || as_planes == (P.res_planes != 0), "linear(tcgen05): the residuals of a group must all be fp32 or all planes");
+      P.res_planes = as_planes ? 1 : 0;
+      if (as_planes) {
+        rc = encode_out_maps(nullptr, &P.map_rp[i], nullptr, 0, const_cast<void*>(p[i].residual_planes), M, N, fmt);
+      } else {
+        SCATT_REQUIRE((reinterpret_cast<uintptr_t>(p[i].residual) & 15) == 0,
+                      "linear(tcgen05): the cluster LayerNorm kernels need a 16-byte aligned fp32 residual");
+        rc = encode_out_maps(&P.map_r[i], nullptr, const_cast<float*>(p[i].residual), ldres, nullptr, M, N, fmt);
+      }
       if (rc != SCATT_OK) return rc;
     }
   }

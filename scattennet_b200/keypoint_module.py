@@ -17,6 +17,8 @@ shapes); the three streams of the model run as grouped launches.
 
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import List, Optional, Sequence
 
@@ -79,12 +81,17 @@ class CoordinateAttention(nn.Module):
 # fp32 copy as well (module-level calls, final outputs, anything a non-GEMM consumer reads).
 
 
-# Measured: +4 % frames/s at B = 256, but -1.5 % at B = 8 (there the launches are latency-bound and the plane
-# residual's conversion sits on the critical path), so only the large-batch LayerNorm kernel implements it.
+# Measured: +4 % frames/s at B = 256.  At B = 8 it used to cost 1.5 % while the cluster kernels fetched the residual
+# with ld.global (the plane conversion sat on the critical path); with the TMA-staged residual the planes arrive
+# beside the operands and only the halved output traffic remains.  SCATT_PLANES_ONLY_SMALL=0 restores fp32 + planes
+# below the large-batch threshold (A/B).
+_PLANES_ONLY_SMALL = os.environ.get("SCATT_PLANES_ONLY_SMALL", "1") != "0"
+
+
 def _keep_f32(prec, acts: List[Act], keep_f32: bool) -> bool:
     # scatt_linear runs an N = 256 LayerNorm GEMM one CTA per 128-row tile once the row tiles of the group exceed 74
     large = ((acts[0].rows + 127) // 128) * len(acts) > 74
-    return keep_f32 or not prec.uses_planes or not large
+    return keep_f32 or not prec.uses_planes or not (large or _PLANES_ONLY_SMALL)
 
 
 def _attn_out_ln(prec, attns, ctx, norms, residuals: List[Act], keep_f32: bool = True) -> List[Act]:

@@ -219,13 +219,37 @@ def test_linear_residual_from_planes(mode, shape):
         assert torch.equal(got.planes, want.planes), (mode, shape, layer_norm)
 
 
-def test_linear_residual_from_planes_rejected_when_not_foldable():
+def test_linear_residual_from_planes_rejected_when_not_fused():
+    """A residual given as planes needs a LayerNorm kernel that stages / folds it; a plain GEMM rejects it loudly."""
     prec = F_.get_precision("fp16x3")
-    x, res = rnd(64, 256, seed=1), rnd(64, 256, seed=2)
-    with pytest.raises(Exception, match="large-batch LayerNorm kernel"):  # 64 rows: the 2-CTA cluster kernel would run
-        F_.linear(prec, [Act(x)], [F_.PackedLinear([make_linear(256, 256, 2)], None, None)],
-                  F_.make_epilogue(residual_mode=L.RES_BEFORE_LN, layer_norm=True), residuals=[Act(None, F_.split_planes(res, prec))],
-                  lns=[torch.nn.LayerNorm(256).to(DEV)])
+    x, res = rnd(64, 256, seed=1), rnd(64, 768, seed=2)
+    with pytest.raises(Exception, match="residual"):
+        F_.linear(prec, [Act(x)], [F_.PackedLinear([make_linear(768, 256, 2)], None, None)],
+                  F_.make_epilogue(residual_mode=L.RES_BEFORE_LN), residuals=[Act(None, F_.split_planes(res, prec))])
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
+@pytest.mark.parametrize("epi", ["res_ln", "ln_res_relu", "gelu_res_ln"])
+@pytest.mark.parametrize("G,M,N,K", [(3, 1600, 256, 256), (3, 1600, 256, 768), (1, 77, 256, 128), (3, 400, 512, 512), (1, 400, 1024, 1024)])
+def test_linear_cluster_residual_from_planes(mode, epi, G, M, N, K):
+    """Small-batch LayerNorm GEMMs (2- / 4- / 8-CTA clusters) with the residual stream kept in split planes only:
+    the planes are staged by TMA and hi + lo is added in the epilogue; planes-only output."""
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    xs = [rnd(M, K, seed=10 + g) for g in range(G)]
+    lins = [make_linear(N, K, 20 + g) for g in range(G)]
+    lns = [torch.nn.LayerNorm(N).to(DEV) for _ in range(G)]
+    res = [rnd(M, N, seed=50 + g) for g in range(G)]
+    res_pl = [F_.split_planes(r, prec) for r in res]
+    res_rec = [pl[0].float() + pl[1].float() for pl in res_pl]  # what the kernel adds
+    outs = F_.linear(prec, [Act(x) for x in xs], [F_.PackedLinear([l], None, None) for l in lins], F_.make_epilogue(**kw),
+                     residuals=[Act(None, pl) for pl in res_pl], lns=lns, out_f32=False)
+    torch.cuda.synchronize()
+    for g in range(G):
+        ref = ref_chain(xs[g], lins[g], kw, res_rec[g], lns[g])
+        assert outs[g].f32 is None
+        got = outs[g].planes[0].double() + outs[g].planes[1].double()
+        assert float((got - ref).abs().max()) <= MODE_TOL[mode] * 4.0 * max(1.0, math.sqrt(K / 256)), (mode, epi, G, M, N, K)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16x3", "fp16x1"])
