@@ -29,6 +29,21 @@ def test_library_exports_header_symbols():
     assert b"sm_100a" in lib.scatt_version()
 
 
+def test_linear_ln_fused_query_is_host_logic():
+    """scatt_linear_ln_fused mirrors the kernel choice of scatt_linear (no device needed): LayerNorm is fused for
+    N = 256 always and for N = 512 / 1024 while the 4- / 8-CTA clusters of all problems fit one wave of 148 SMs."""
+    lib = _lib.load()
+    tc, simt = _lib.ENGINE_TCGEN05, _lib.ENGINE_SIMT
+    assert lib.scatt_linear_ln_fused(1600, 256, 3, tc) == 1
+    assert lib.scatt_linear_ln_fused(51200, 256, 3, tc) == 1
+    assert lib.scatt_linear_ln_fused(800, 512, 3, tc) == 1      # 7 row tiles x 3 x 4 CTAs = 84
+    assert lib.scatt_linear_ln_fused(400, 1024, 1, tc) == 1     # 4 x 8 = 32
+    assert lib.scatt_linear_ln_fused(128 * 13, 512, 3, tc) == 0  # 156 CTAs > 148: GEMM + row-wise tail
+    assert lib.scatt_linear_ln_fused(2400, 1024, 1, tc) == 0    # 19 x 8 = 152
+    assert lib.scatt_linear_ln_fused(400, 384, 1, tc) == 0
+    assert lib.scatt_linear_ln_fused(400, 256, 1, simt) == 0
+
+
 def test_ctypes_structs_match_header_sizes():
     import ctypes as C
 
