@@ -386,6 +386,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             r = time_oracle(steps=40, warmup=2, budget_s=25.0)
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        from scattennet_b200 import distributed as _D
+        peer_used = world > 1 and any(v is not False for v in _D._peer_gathers.values())
+        gather_route = ("none (one GPU)" if world == 1 else
+                        "scatt_peer_allgather: push into the peers' symmetric buffers over NVLink + barrier, one kernel per step"
+                        if peer_used else "NCCL all_gather_into_tensor")
         line = {
             "metric": METRIC, "value": frames / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -394,13 +399,14 @@ def run_ours(args):
             "config": {"workload": f"SCAttenNet {CFG_NAME}.yaml encoder forward (region split + 3 streams + fusion + 4 linear heads), "
                                    f"batch {args.batch} per GPU, T={T}, V={VOCAB}, random-init weights",
                        "global_batch": world * args.batch, "seq_len": T, "parallelism": f"dp{world} (batch shards, logits all-gather)",
+                       "gather": gather_route,
                        "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
                        "e2e_path": "MSCAEncoder.forward_host: host tensors in, exact host gather of the used joints, H2D, "
                                    "graph replay, D2H of fuse_coord_gloss_logits",
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks", "cuda_graph": True},
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": (launches_per_step + (1 if peer_used else 0)) * args.steps,
             "launches_per_step": launches_per_step,
             "wall_s_timed_region": wall,
             "clocks": sampler.result(),
