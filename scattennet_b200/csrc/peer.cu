@@ -35,8 +35,6 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 
 __global__ void __launch_bounds__(256) peer_allgather_kernel(const uint8_t* __restrict__ src, int64_t bytes, PeerPtrs pp, int world,
                                                             int rank, unsigned int* __restrict__ counter, uint64_t seq) {
-  pdl_launch_dependents();
-  pdl_wait();  // src is the output of the preceding kernel
   const int64_t nvec = bytes >> 4;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
@@ -84,8 +82,10 @@ int launch_peer_allgather(const void* src, int64_t bytes, void* const* peer_bufs
   int64_t blocks = ((bytes >> 4) + 256 * 4 - 1) / (256 * 4);
   if (blocks < 1) blocks = 1;
   if (blocks > 64) blocks = 64;  // a few dozen CTAs saturate the NVLink ports; the rest of the GPU stays free
-  (void)launch_kernel(peer_allgather_kernel, dim3(unsigned(blocks)), dim3(256), 0, s, reinterpret_cast<const uint8_t*>(src), bytes, pp,
-                      world, rank, reinterpret_cast<unsigned int*>(counter), seq);
+  // plain stream order (no programmatic dependent launch): the shard is usually the output of a whole CUDA-graph
+  // launch, and a barrier kernel must not become resident before its producer has finished everywhere
+  peer_allgather_kernel<<<dim3(unsigned(blocks)), dim3(256), 0, s>>>(reinterpret_cast<const uint8_t*>(src), bytes, pp, world, rank,
+                                                                    reinterpret_cast<unsigned int*>(counter), seq);
   return after_launch("peer_allgather_kernel");
 }
 
