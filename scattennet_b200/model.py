@@ -23,9 +23,8 @@ from torch import nn
 from . import _lib as L
 from . import functional as F_
 from .alignment_module import AlignmentModule, alignment_forward
-from .functional import Act
 from .fusion import CoordinatesFusion, coordinates_fusion_forward
-from .keypoint_module import KeypointModule, frontend_forward, streams_forward
+from .keypoint_module import KeypointModule, streams_forward
 
 PARTS = ("body", "left", "right")  # order of model/__init__.py:133-142
 HOST_GRAPH = os.environ.get("SCATT_HOST_GRAPH", "1") != "0"  # forward_host as one graph (copies included)

@@ -3,7 +3,7 @@
     python tools/sweep.py batch   [--precision fp16x3]     # frames/s vs batch at T=200
     python tools/sweep.py kernels                          # attention / linear launches vs roofline
 """
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from scattennet_b200 import MSCAEncoder, synth, functional as F_, _lib as L
