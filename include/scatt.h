@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SCATT_ABI_VERSION 2
+#define SCATT_ABI_VERSION 3
 #define SCATT_MAX_GROUP 4 /* problems per grouped launch (the 3 anatomical streams + spare) */
 #define SCATT_MAX_PEERS 8  /* GPUs of one NVSwitch box taking part in scatt_peer_allgather */
 #define SCATT_MAX_FINITE 16 /* tensors per scatt_finite_check call */
@@ -160,6 +160,36 @@ typedef struct scatt_linear_problem {
 int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx,
                  int64_t ldres, int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms,
                  void* stream);
+
+/* ------------------------------------------------------------------ K2b: fused row-local layer tail
+ *
+ * y = LayerNorm2(h + fc2(GELU(fc1(h)))),  h = LayerNorm1(x + ctx Wo^T + bo)
+ * i.e. everything of a self / merge layer behind the attention core in ONE kernel (tcgen05 engine): out_proj
+ * (model/attention.py:74,126), residual + attn_layer_norm (model/keypoint_module.py:62-66,98-102), FeedForward
+ * (model/layers.py:103-108), residual + last_layer_norm (model/keypoint_module.py:68-72,104-107); the same tail
+ * closes an EncoderLayer (model/encoder.py:38-55).  h and the F-wide hidden activation stay on the SM (shared /
+ * tensor memory); per 128-row tile only ctx and x are read and y is written.  D must be 256, F a multiple of 128
+ * up to 1024 (scatt_attn_block_supported); other shapes run as three scatt_linear calls. */
+typedef struct scatt_block_problem {
+  const void* ctx_planes;      /* [2][M][D] attention output, heads concatenated (scatt_attention_planes out_planes) */
+  const void* residual_planes; /* [2][M][D] the layer input x (hi + lo is added), 16-byte aligned */
+  const void* wo_planes;       /* [2][D][D] out_proj.weight */
+  const float* bo;             /* [D] */
+  const float* ln1_g;          /* [D] attn_layer_norm */
+  const float* ln1_b;
+  const void* w1_planes;       /* [2][F][D] fc1.weight */
+  const float* b1;             /* [F] */
+  const void* w2_planes;       /* [2][D][F] fc2.weight */
+  const float* b2;             /* [D] */
+  const float* ln2_g;          /* [D] last_layer_norm */
+  const float* ln2_b;
+  float* y;                    /* [M][D] fp32 contiguous or NULL */
+  void* y_planes;              /* [2][M][D] split planes or NULL */
+} scatt_block_problem;
+
+int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_t M, int D, int F, float ln_eps,
+                     int plane_fmt, int terms, void* stream);
+int scatt_attn_block_supported(int64_t M, int D, int F);
 
 /* 1 when scatt_linear with a LayerNorm epilogue normalises inside the GEMM kernel for this shape (tcgen05
  * engine: N = 256 always; N = 512 / 1024 by 4- / 8-CTA clusters while ceil(M / 128) * group * N / 128 <= 148),

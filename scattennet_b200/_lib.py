@@ -27,7 +27,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
-    "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ln_fused",
+    "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
     "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
@@ -51,6 +51,11 @@ class LinearProblem(C.Structure):
         ("x", C.c_void_p), ("x_planes", C.c_void_p), ("w", C.c_void_p), ("w_planes", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("y", C.c_void_p), ("y_planes", C.c_void_p), ("residual_planes", C.c_void_p),
     ]
+
+
+class BlockProblem(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ctx_planes", "residual_planes", "wo_planes", "bo", "ln1_g", "ln1_b", "w1_planes", "b1",
+                                          "w2_planes", "b2", "ln2_g", "ln2_b", "y", "y_planes")]
 
 
 class AttentionProblem(C.Structure):
@@ -95,6 +100,10 @@ def _declare(lib):
     lib.scatt_posembed_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.scatt_linear.argtypes = [C.POINTER(LinearProblem), i32, i64, i32, i32, i64, i64, i64, C.POINTER(Epilogue), i32, i32,
                                  i32, vp]
+    lib.scatt_attn_block.argtypes = [C.POINTER(BlockProblem), i32, i64, i32, i32, f32, i32, i32, vp]
+    lib.scatt_attn_block.restype = i32
+    lib.scatt_attn_block_supported.argtypes = [i64, i32, i32]
+    lib.scatt_attn_block_supported.restype = i32
     lib.scatt_linear_ln_fused.argtypes = [i64, i32, i32, i32]
     lib.scatt_linear_ln_fused.restype = i32
     lib.scatt_rowwise.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, C.POINTER(Epilogue), vp, i64, vp, i32, vp]
@@ -140,7 +149,7 @@ def load(build_if_missing: bool = True):
         if missing:
             raise ScattError(f"{LIB_PATH} lacks symbols {missing}")
         _declare(lib)
-        if lib.scatt_abi_version() != 2:
+        if lib.scatt_abi_version() != 3:
             raise ScattError("libscatt ABI version mismatch; rebuild with python -m scattennet_b200.build --force")
         _lib = lib
         return lib

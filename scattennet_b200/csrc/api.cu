@@ -59,7 +59,9 @@ int scatt_debug_set_trace(void* dev_buf) {
   const int rc = debug_set_trace(dev_buf);
   if (rc != SCATT_OK) return rc;
   const int rc2 = debug_set_trace_attention(dev_buf);
-  return rc2 != SCATT_OK ? rc2 : debug_set_trace_fa(dev_buf);
+  if (rc2 != SCATT_OK) return rc2;
+  const int rc3 = debug_set_trace_fa(dev_buf);
+  return rc3 != SCATT_OK ? rc3 : debug_set_trace_block(dev_buf);
 }
 
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,
@@ -94,6 +96,16 @@ int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M
   set_error("linear: unknown engine %d", engine);
   return SCATT_ERR_INVALID;
 }
+
+int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_t M, int D, int F, float ln_eps, int plane_fmt,
+                     int terms, void* stream) {
+  SCATT_REQUIRE(problems_host && fmt_ok(plane_fmt), "attn_block: null pointer or bad plane format");
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "attn_block: group must be 1..%d", SCATT_MAX_GROUP);
+  SCATT_REQUIRE(M >= 0, "attn_block: bad shape M=%lld", (long long)M);
+  return launch_attn_block(problems_host, group, M, D, F, ln_eps, plane_fmt, terms, as_stream(stream));
+}
+
+int scatt_attn_block_supported(int64_t M, int D, int F) { return attn_block_supported(M, D, F) ? 1 : 0; }
 
 int scatt_linear_ln_fused(int64_t M, int N, int group, int engine) {
   if (engine != SCATT_ENGINE_TCGEN05 || M < 0 || N < 1 || group < 1) return 0;

@@ -195,6 +195,10 @@ int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int 
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
                      const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s);
 int linear_tc_ln_cluster(int64_t M, int N, int group, int layer_norm);
+bool attn_block_supported(int64_t M, int D, int F);
+int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D, int F, float eps, int fmt, int terms,
+                      cudaStream_t s);
+int debug_set_trace_block(void* dev_buf);
 int debug_set_trace(void* dev_buf);
 int debug_set_trace_attention(void* dev_buf);
 int debug_set_trace_fa(void* dev_buf);

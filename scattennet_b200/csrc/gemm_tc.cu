@@ -45,6 +45,8 @@
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tc_epi.cuh"
+#include "tc_host.cuh"
 
 #ifndef SCATT_RES_IN_RING
 #define SCATT_RES_IN_RING 1
@@ -177,18 +179,6 @@ __device__ __forceinline__ void tile_fetch_planes(const EpiCtx& E, const uint16_
     }
   }
 }
-__device__ __forceinline__ float2 unpack_pair(float hi_bits, float lo_bits, int fmt) {
-  const uint32_t h = __float_as_uint(hi_bits), l = __float_as_uint(lo_bits);
-  float2 a, b;
-  if (fmt == SCATT_PLANE_F16) {
-    a = __half22float2(*reinterpret_cast<const __half2*>(&h));
-    b = __half22float2(*reinterpret_cast<const __half2*>(&l));
-  } else {
-    a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h));
-    b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l));
-  }
-  return make_float2(a.x + b.x, a.y + b.y);
-}
 // v[32] (thread-per-row) += hi + lo of the fetched plane tile, transposed through the staging tile
 __device__ __forceinline__ void tile_add_planes(const EpiCtx& E, const float4 (&r)[8], float* v, int fmt) {
   const int sub = E.lane >> 2, q = E.lane & 3;
@@ -238,14 +228,6 @@ __device__ __forceinline__ void box_add_planes(const EpiCtx& E, const uint8_t* b
   }
 }
 
-__device__ __forceinline__ void add_cols(float* v, const float* __restrict__ p) {  // p: shared memory, warp-uniform
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(p + j);
-    v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
-  }
-}
-
 __device__ __forceinline__ void act_vec32(float* v, int act) {
   if (act == SCATT_ACT_GELU) {
 #pragma unroll
@@ -254,40 +236,6 @@ __device__ __forceinline__ void act_vec32(float* v, int act) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-}
-
-template <int FMT>
-__device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (FMT == SCATT_PLANE_F16) {
-      const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-      const float2 back = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
-      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-    } else {
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-      const float2 back = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
-      h[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[e] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
-               "r"(c1), "r"(c2)
-               : "memory");
 }
 
 // act_post (none / ReLU) -> clamp -> outputs.  Each thread writes its row of the 32 x 32 chunk into
@@ -418,24 +366,6 @@ __device__ __forceinline__ void acc_pre_init(const TcParams& P, const TcProblem&
     }
   }
   acc_pre_init_impl<BN, EW, false>(P, Q, E, tmem_acc, n0, half);
-}
-
-// cluster helpers (LN >= 2: the row's columns live in the LN CTAs of a cluster)
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_sync_all() {
-  cluster_arrive();
-  cluster_wait();
-}
-__device__ __forceinline__ void st_peer_f32x2(uint32_t local_addr, uint32_t peer_rank, float a, float b) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer_rank));
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
 }
 
 // LN: 0 = no LayerNorm in this kernel, 1 = the CTA owns the whole row (N == BN), 2 / 4 / 8 = the row is split
@@ -1022,12 +952,14 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_ln_cluster_k
   linear_tc_body<128, CL, FMT, kEpiWarps>(P);
 }
 
+}  // namespace
+
 // ------------------------------------------------------------------ host side
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeFn get_encode() {
+static EncodeFn get_encode() {
   static EncodeFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -1094,6 +1026,8 @@ int encode_out_maps(CUtensorMap* map_y, CUtensorMap* map_p, float* y, int64_t ld
   }
   return SCATT_OK;
 }
+
+namespace {
 
 template <int BN, int LN, int FMT>
 int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {

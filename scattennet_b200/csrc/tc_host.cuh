@@ -1,0 +1,18 @@
+// Host-side tensor-map encoders shared by the tcgen05 kernels (defined in gemm_tc.cu).
+#pragma once
+
+#include <cuda.h>
+
+#include <cstdint>
+
+namespace scatt {
+
+// split planes [2][rows][K] -> boxes of 64 K-elements x box_rows rows x 1 plane, 128-byte swizzle
+// (the K-major operand tiles of the UMMA descriptors)
+int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K, int box_rows, int fmt);
+
+// output maps written by one epilogue warp at a time: fp32 [M][ldy] as 32 x 32 boxes (128-byte swizzle) and / or
+// split planes [2][M][N] as 32 x 32 x 1 boxes (64-byte swizzle); either pointer may be null
+int encode_out_maps(CUtensorMap* map_y, CUtensorMap* map_p, float* y, int64_t ldy, void* planes, int64_t M, int N, int fmt);
+
+}  // namespace scatt

@@ -363,6 +363,44 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     return outs
 
 
+FUSED_BLOCK = os.environ.get("SCATT_FUSED_BLOCK", "1") != "0"  # False: out_proj+LN, fc1, fc2+LN as three scatt_linear launches
+
+
+def attn_block_supported(prec: Precision, M: int, D: int, F: int) -> bool:
+    return FUSED_BLOCK and prec.uses_planes and bool(L.load().scatt_attn_block_supported(M, D, F))
+
+
+def attn_block(prec: Precision, ctx: Sequence[Act], residuals: Sequence[Act], out_packs: Sequence[PackedLinear],
+               norms1: Sequence[torch.nn.LayerNorm], fc1_packs: Sequence[PackedLinear], fc2_packs: Sequence[PackedLinear],
+               norms2: Sequence[torch.nn.LayerNorm], out_f32: bool = False, out_planes: bool = True) -> List[Act]:
+    """Grouped ``LN2(h + fc2(GELU(fc1(h))))`` with ``h = LN1(x + ctx Wo^T + bo)`` - everything of a self / merge layer
+    behind the attention core as ONE launch (``scatt_attn_block``); ``h`` and the hidden activation stay on the SM."""
+    G = len(ctx)
+    M, D, Fh = ctx[0].rows, ctx[0].cols, fc1_packs[0].N
+    dev = ctx[0].planes.device
+    probs = (L.BlockProblem * G)()
+    outs: List[Act] = []
+    for g in range(G):
+        residuals[g].with_planes(prec)
+        y = torch.empty(M, D, dtype=torch.float32, device=dev) if out_f32 else None
+        yp = torch.empty(2, M, D, dtype=prec.plane_dtype, device=dev) if (out_planes or not out_f32) else None
+        p = probs[g]
+        p.ctx_planes, p.residual_planes = ctx[g].planes.data_ptr(), residuals[g].planes.data_ptr()
+        p.wo_planes, p.bo = out_packs[g].planes(prec).data_ptr(), out_packs[g].b32.data_ptr()
+        p.ln1_g, p.ln1_b = norms1[g].weight.data_ptr(), norms1[g].bias.data_ptr()
+        p.w1_planes, p.b1 = fc1_packs[g].planes(prec).data_ptr(), fc1_packs[g].b32.data_ptr()
+        p.w2_planes, p.b2 = fc2_packs[g].planes(prec).data_ptr(), fc2_packs[g].b32.data_ptr()
+        p.ln2_g, p.ln2_b = norms2[g].weight.data_ptr(), norms2[g].bias.data_ptr()
+        p.y, p.y_planes = _ptr(y), _ptr(yp)
+        outs.append(Act(y, yp))
+    flops = 2.0 * G * M * (D * D + 2.0 * D * Fh)
+    nbytes = G * (3.0 * M * D * 4 + (D * D + 2.0 * D * Fh) * 4)  # ctx + x in, y out (planes), weights once
+    with _timed("attn_block_kernel", flops, nbytes):
+        L.check(L.load().scatt_attn_block(probs, G, M, D, Fh, norms1[0].eps, prec.plane_fmt, max(prec.terms, 1), _stream()),
+                "scatt_attn_block")
+    return outs
+
+
 ATTN_TC_MAX_T = 256  # longest key sequence the tcgen05 attention kernel takes (longer ones run on the fp32 kernel)
 
 

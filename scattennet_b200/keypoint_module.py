@@ -110,6 +110,28 @@ def _ffn_ln(prec, mlps: Sequence[FeedForward], norms, h: List[Act], keep_f32: bo
                      out_f32=keep_f32 or not prec.uses_planes)
 
 
+def _fused_tail_ok(prec, attns, mlps, norms1, norms2, ctx: List[Act], residuals: List[Act]) -> bool:
+    """``scatt_attn_block`` takes the tail of the layer: plane operands, biased linears, both LayerNorms alike."""
+    if not F_.attn_block_supported(prec, ctx[0].rows, ctx[0].cols, mlps[0].fc1.out_features):
+        return False
+    if any(c.planes is None for c in ctx) or any(r.planes is None and r.f32 is None for r in residuals):
+        return False
+    if any(l.bias is None for a, m in zip(attns, mlps) for l in (a.out_proj, m.fc1, m.fc2)):
+        return False
+    return all(n1.eps == norms1[0].eps == n2.eps for n1, n2 in zip(norms1, norms2))
+
+
+def _attn_tail(prec, attns, mlps, norms1, norms2, ctx: List[Act], residuals: List[Act], keep_f32: bool) -> List[Act]:
+    """out_proj + residual + LayerNorm, FeedForward + residual + LayerNorm (reference
+    ``model/keypoint_module.py:62-72,98-107``): one fused launch when the shapes allow, three GEMM launches otherwise."""
+    if _fused_tail_ok(prec, attns, mlps, norms1, norms2, ctx, residuals):
+        return F_.attn_block(prec, ctx, residuals, [F_.pack_of(a, "out", [a.out_proj]) for a in attns], norms1,
+                             [F_.pack_of(m, "fc1", [m.fc1]) for m in mlps], [F_.pack_of(m, "fc2", [m.fc2]) for m in mlps],
+                             norms2, out_f32=keep_f32)
+    h = _attn_out_ln(prec, attns, ctx, norms1, residuals, False)
+    return _ffn_ln(prec, mlps, norms2, h, keep_f32)
+
+
 def coordinate_attention_forward(prec: Precision, mods: Sequence[CoordinateAttention], xs: List[Act], B: int, T: int,
                                  key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None,
                                  keep_f32: bool = True) -> List[Act]:
@@ -117,10 +139,10 @@ def coordinate_attention_forward(prec: Precision, mods: Sequence[CoordinateAtten
     kind = L.ATTN_SELF if mods[0].attn_type == "self_attn" else L.ATTN_CAUSAL
     is_self = mods[0].attn_type == "self_attn"
     ctx = attention_core(prec, [m.attn for m in mods], xs, None, B, T, T, kind, key_mask, additive)
-    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], xs, keep_f32 and not is_self)
     if is_self:
-        h = _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h, keep_f32)
-    return h
+        return _attn_tail(prec, [m.attn for m in mods], [m.mlp for m in mods], [m.attn_layer_norm for m in mods],
+                          [m.last_layer_norm for m in mods], ctx, xs, keep_f32)
+    return _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], xs, keep_f32)
 
 
 class CoordinatesMerge(nn.Module):
@@ -149,8 +171,8 @@ def coordinates_merge_forward(prec: Precision, mods: Sequence[CoordinatesMerge],
                               additive: Optional[torch.Tensor] = None, keep_f32: bool = True) -> List[Act]:
     """reference ``model/keypoint_module.py:97-115`` for a group of streams."""
     ctx = attention_core(prec, [m.attn for m in mods], ys, xs, B, Tq, Tk, L.ATTN_CROSS, key_mask, additive, kv_views)
-    h = _attn_out_ln(prec, [m.attn for m in mods], ctx, [m.attn_layer_norm for m in mods], ys, False)
-    return _ffn_ln(prec, [m.mlp for m in mods], [m.last_layer_norm for m in mods], h, keep_f32)
+    return _attn_tail(prec, [m.attn for m in mods], [m.mlp for m in mods], [m.attn_layer_norm for m in mods],
+                      [m.last_layer_norm for m in mods], ctx, ys, keep_f32)
 
 
 class SeparativeCoordinateAttention(nn.Module):

@@ -61,10 +61,35 @@ class MSCAEncoder(nn.Module):
         # > 1: inside the captured graph the batch is cut into this many independent sub-batches that
         # run as parallel graph branches (sequences are independent); their latency-bound kernels overlap
         self.micro_batches = micro_batches
-        self._graphs: Dict = {}
+        self._graphs: Dict = {}        # (shape, device, precision, heads, compact) -> captured graph; LRU, see _cache_put
+        self._host_staging: Dict = {}  # (B, T, device) -> pinned staging slots + their graphs (forward_host)
         self._idx_cache: Dict = {}
+        self.max_cached_shapes = 8     # captured graphs / staging sets kept per cache (variable-length inference)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_graphs())
 
     # ------------------------------------------------------------------ plumbing
+    def invalidate_graphs(self) -> None:
+        """Drop every captured graph and staging set: they hold pointers to the packed (split-plane / transposed)
+        copies of the weights, which are rebuilt when a parameter changes."""
+        self._graphs.clear()
+        self._host_staging.clear()
+
+    def _apply(self, fn, recurse=True):  # .to() / .cuda() / .float(): parameters move, captured pointers go stale
+        self.invalidate_graphs()
+        return super()._apply(fn, recurse)
+
+    def _cache_put(self, cache: Dict, key, value):
+        cache[key] = value
+        while len(cache) > self.max_cached_shapes:  # dicts keep insertion order: evict the least recently used
+            cache.pop(next(iter(cache)))
+
+    @staticmethod
+    def _cache_get(cache: Dict, key):
+        ent = cache.pop(key, None)
+        if ent is not None:
+            cache[key] = ent  # most recently used goes last
+        return ent
+
     def _joint_idx(self, device):
         key = str(device)
         if key not in self._idx_cache:
@@ -99,12 +124,29 @@ class MSCAEncoder(nn.Module):
         return self.load_state_dict(picked, strict=strict_path)
 
     # ------------------------------------------------------------------ forward
-    def _run(self, keypoints: torch.Tensor, key_mask: torch.Tensor, with_heads: bool = True) -> Dict[str, torch.Tensor]:
+    def _validate(self, keypoints: torch.Tensor, mask: torch.Tensor, compact: bool = False):
+        """Shape / index checks the reference gets from ATen (``keypoints[:, :, idx, :]`` raises ``IndexError`` for a
+        joint index past ``K``, ``model/__init__.py:133-142``); the kernels would read out of bounds instead."""
+        if keypoints.ndim != 4 or keypoints.shape[-1] != 2:
+            raise ValueError(f"keypoints must be [B, T, K, 2]; got {tuple(keypoints.shape)}")
+        b, t, k = keypoints.shape[:3]
+        if tuple(mask.shape) != (b, t):
+            raise ValueError(f"mask must be [B, T] = {(b, t)}; got {tuple(mask.shape)}")
+        need = self._n_used() if compact else self._max_joint() + 1
+        if k < need:
+            raise IndexError(f"index {need - 1} is out of bounds for dimension 2 with size {k}")
+
+    def _max_joint(self) -> int:
+        if "max_joint" not in self._idx_cache:
+            self._idx_cache["max_joint"] = max(j for p in PARTS for j in self.cfg[p + "_idx"])
+        return self._idx_cache["max_joint"]
+
+    def _run(self, keypoints: torch.Tensor, key_mask: torch.Tensor, with_heads: bool = True, compact: bool = False) -> Dict[str, torch.Tensor]:
         prec = F_.get_precision(self.precision)
         b, t = keypoints.shape[:2]
         mods = [self.body_encoder, self.left_encoder, self.right_encoder]
         # a compact tensor (only the joints the three streams use, see forward_host) carries remapped indices
-        idx = self._compact_idx(keypoints.device)[1] if keypoints.shape[2] == self._n_used() else self._joint_idx(keypoints.device)
+        idx = self._compact_idx(keypoints.device)[1] if compact else self._joint_idx(keypoints.device)
         blocks = streams_forward(prec, mods, keypoints, idx, key_mask, b, t)
         (body, left, right), tp = blocks[-1]
         lg, heads_branch = None, None
@@ -133,7 +175,7 @@ class MSCAEncoder(nn.Module):
         return out
 
     def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True,
-                check_finite: bool = False) -> Dict[str, torch.Tensor]:
+                check_finite: bool = False, compact: bool = False) -> Dict[str, torch.Tensor]:
         """``keypoints [B,T,K,2]`` (the full collated tensor - the region split is
         part of the path), ``mask [B,T]`` 0/1.  Returns the stream / fusion
         features and the clamped per-frame logits (fp32).
@@ -141,16 +183,23 @@ class MSCAEncoder(nn.Module):
         ``check_finite=True`` reproduces the NaN / inf guards of ``MSCA_Net.forward`` (reference
         ``model/__init__.py:130-167``: input, the three stream outputs, the fused features, every head) and
         raises ``ValueError`` naming the first offender - with one fused kernel and one 4-byte read-back
-        instead of 16 host synchronisations."""
+        instead of 16 host synchronisations.  ``compact=True``: ``keypoints`` holds only the joints the three
+        streams use, in ascending joint order (what ``forward_host`` ships).
+
+        With ``use_graph=True`` the returned tensors are the captured graph's static outputs: the next call with
+        the same shape overwrites them (clone what must survive).  Captured graphs are dropped by
+        ``load_state_dict`` / ``.to()`` / ``.cuda()`` (``invalidate_graphs``); after modifying parameters in place
+        call ``invalidate_graphs()`` yourself."""
         if self.training:
             raise RuntimeError("scattennet_b200 is inference-only: call .eval() before forward")
         F_.require_cuda(keypoints, mask)
+        self._validate(keypoints, mask, compact)
         if keypoints.dtype != torch.float32 or not keypoints.is_contiguous():
             keypoints = keypoints.float().contiguous()
         if not self.use_graph:
-            out = self._run(keypoints, F_.key_mask_u8(mask), with_heads)
+            out = self._run(keypoints, F_.key_mask_u8(mask), with_heads, compact)
         else:
-            out = self._run_graph(keypoints, mask, with_heads)
+            out = self._run_graph(keypoints, mask, with_heads, compact)
         if check_finite:
             names = ["input keypoints"] + list(out)
             bits = int(F_.finite_flags([keypoints] + [out[k] for k in out]).item())
@@ -159,16 +208,25 @@ class MSCAEncoder(nn.Module):
         return out
 
     def forward_host(self, keypoints: torch.Tensor, mask: torch.Tensor, heads=("fuse_coord_gloss_logits",), device=None,
-                     gather: bool = False, decode_beam: int = 0, input_lengths: Optional[torch.Tensor] = None):
+                     gather: bool = False, decode_beam: int = 0, input_lengths: Optional[torch.Tensor] = None,
+                     gather_to_host: str = "rank0"):
         """End-to-end call for host-resident batches (the collator -> device path).
 
         ``keypoints [B,T,K,2]`` / ``mask [B,T]`` are CPU tensors.  Only the joints the three streams read
         (48 of 542 for the Phoenix configs: 384 of 4336 bytes per frame) are gathered - an exact copy - into a
         pinned staging buffer and sent to the device; the requested ``heads`` come back in pinned host
         tensors.  Returns ``{name: host tensor}``; call ``torch.cuda.current_stream().synchronize()`` (or use
-        the tensors after any sync) before reading them.  ``gather=True`` (inside an initialised
-        ``torch.distributed`` job): the first head is all-gathered over NVLink before the read-back, and only
-        rank 0 reads the gathered ``[world*B, T', V]`` logits (the others read their own shard).
+        the tensors after any sync) before reading them.
+
+        **Buffering.**  Staging and result buffers are double-buffered per ``(B, T)``: a call may be issued while
+        the previous one is still running on the device (the host gather of batch ``i + 1`` overlaps the encoder
+        of batch ``i``); a third call first waits, on the host, for the call two steps back to finish.  The
+        tensors returned by call ``i`` are therefore valid until call ``i + 2`` of the same shape is issued.
+
+        ``gather=True`` (inside an initialised ``torch.distributed`` job): the first head is all-gathered over
+        NVLink on the device.  ``gather_to_host="rank0"``: rank 0 reads the gathered ``[world*B, T', V]`` logits
+        back, the other ranks their own shard (one decoder process); ``"shard"``: every rank reads only its own
+        shard (one decoder per rank; the gathered tensor stays on the device under ``"<head>/gathered_dev"``).
         ``decode_beam > 0``: the first head is CTC-decoded on the device (prefix beam search, the reference's
         ``utils.ctc_decode``; ``input_lengths [B]`` = valid pooled frames per sequence) and only
         ``gloss_ids [B,T'] int32`` (padded with -1) and ``gloss_len [B]`` come back instead of logits."""
@@ -177,84 +235,110 @@ class MSCAEncoder(nn.Module):
         dev = device or next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("scattennet_b200 runs on a CUDA device (sm_100a) only; there is no CPU fallback")
+        if keypoints.is_cuda or mask.is_cuda:
+            raise RuntimeError("forward_host takes host tensors; call forward() for device-resident batches")
+        self._validate(keypoints, mask)
         used, _ = self._compact_idx(dev)
         b, t = keypoints.shape[:2]
         key = ("host", b, t, str(dev))
-        st = self._host_staging.get(key) if hasattr(self, "_host_staging") else None
+        st = self._cache_get(self._host_staging, key)
         if st is None:
-            if not hasattr(self, "_host_staging"):
-                self._host_staging = {}
-            st = {"kp_pin": torch.empty(b, t, used.numel(), 2, dtype=torch.float32).pin_memory(),
-                  "mask_pin": torch.empty(b, t, dtype=torch.uint8).pin_memory(),
+            def make_slot():
+                return {"kp_pin": torch.empty(b, t, used.numel(), 2, dtype=torch.float32).pin_memory(),
+                        "mask_pin": torch.empty(b, t, dtype=torch.uint8).pin_memory(), "out_pin": {}, "busy": None}
+            st = {"slots": [make_slot(), make_slot()], "next": 0,
                   "kp_dev": torch.empty(b, t, used.numel(), 2, dtype=torch.float32, device=dev),
-                  "mask_dev": torch.empty(b, t, dtype=torch.uint8, device=dev), "out_pin": {}}
-            self._host_staging[key] = st
-        torch.index_select(keypoints, 2, used, out=st["kp_pin"])  # exact gather on the host
-        st["mask_pin"].copy_(mask != 0)
-        if self.use_graph and not gather and decode_beam <= 0 and HOST_GRAPH:
-            # the whole step - both H2D copies, the encoder, the D2H copies of the requested heads - is ONE
-            # captured graph: a single launch instead of eight stream operations with the host in between
-            return self._host_graph_step(st, heads, dev)
-        st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
-        st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
-        out = self.forward(st["kp_dev"], st["mask_dev"])
-        if gather:
-            import torch.distributed as dist
+                  "mask_dev": torch.empty(b, t, dtype=torch.uint8, device=dev)}
+            self._cache_put(self._host_staging, key, st)
+        slot = st["slots"][st["next"]]
+        st["next"] ^= 1
+        if slot["busy"] is not None:
+            slot["busy"].synchronize()  # the step that last used this slot has read its staging and written its results
+        torch.index_select(keypoints, 2, used, out=slot["kp_pin"])  # exact gather on the host
+        slot["mask_pin"].copy_(mask != 0)
+        try:
+            if self.use_graph and not gather and decode_beam <= 0 and HOST_GRAPH:
+                # the whole step - both H2D copies, the encoder, the D2H copies of the requested heads - is ONE
+                # captured graph: a single launch instead of eight stream operations with the host in between
+                return self._host_graph_step(st, slot, heads, dev)
+            st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
+            st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
+            out = self.forward(st["kp_dev"], st["mask_dev"], compact=True)
+            extra = {}
+            if gather:
+                import torch.distributed as dist
 
-            from .distributed import gather_logits_peer
+                from .distributed import gather_logits_peer
 
-            full = gather_logits_peer(out[heads[0]])
-            if dist.get_rank() == 0:
-                out = dict(out)
-                out[heads[0]] = full
-        if decode_beam > 0:
-            lens = st.get("len_dev")
-            if input_lengths is not None:
-                if lens is None:
-                    lens = st["len_dev"] = torch.empty(b, dtype=torch.int32, device=dev)
-                lens.copy_(input_lengths.to(torch.int32), non_blocking=True)
-            ids, n_ids, _ = F_.ctc_beam_decode(out[heads[0]], lens if input_lengths is not None else None, decode_beam)
-            out = {"gloss_ids": ids, "gloss_len": n_ids}
-            heads = ("gloss_ids", "gloss_len")
-        res = {}
-        for k in heads:
-            pin = st["out_pin"].get(k)
-            if pin is None or pin.shape != out[k].shape:
-                pin = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
-                st["out_pin"][k] = pin
-            pin.copy_(out[k], non_blocking=True)
-            res[k] = pin
-        return res
+                full = gather_logits_peer(out[heads[0]])
+                if gather_to_host == "rank0":
+                    if dist.get_rank() == 0:
+                        out = dict(out)
+                        out[heads[0]] = full
+                elif gather_to_host == "shard":
+                    extra[heads[0] + "/gathered_dev"] = full
+                else:
+                    raise ValueError("gather_to_host must be 'rank0' or 'shard'")
+            if decode_beam > 0:
+                lens = st.get("len_dev")
+                if input_lengths is not None:
+                    if lens is None:
+                        lens = st["len_dev"] = torch.empty(b, dtype=torch.int32, device=dev)
+                    len_pin = slot.get("len_pin")
+                    if len_pin is None:
+                        len_pin = slot["len_pin"] = torch.empty(b, dtype=torch.int32).pin_memory()
+                    len_pin.copy_(input_lengths.to(torch.int32))
+                    lens.copy_(len_pin, non_blocking=True)
+                ids, n_ids, _ = F_.ctc_beam_decode(out[heads[0]], lens if input_lengths is not None else None, decode_beam)
+                out = {"gloss_ids": ids, "gloss_len": n_ids}
+                heads = ("gloss_ids", "gloss_len")
+            res = dict(extra)
+            for k in heads:
+                pin = slot["out_pin"].get(k)
+                if pin is None or pin.shape != out[k].shape:
+                    pin = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                    slot["out_pin"][k] = pin
+                pin.copy_(out[k], non_blocking=True)
+                res[k] = pin
+            return res
+        finally:
+            busy = slot["busy"] or torch.cuda.Event()
+            busy.record(torch.cuda.current_stream(dev))
+            slot["busy"] = busy
 
-    def _host_graph_step(self, st, heads, dev):
+    def _host_graph_step(self, st, slot, heads, dev):
         key = ("hostgraph", tuple(heads), F_.get_precision(self.precision).name)
-        ent = st.get(key)
+        ent = slot.get(key)
         if ent is None:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():  # warm-up: packs weights, sets kernel attributes
-                st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
-                st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
+                st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
+                st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
                 for _ in range(2):
-                    out = self._run(st["kp_dev"], st["mask_dev"], True)
+                    out = self._run(st["kp_dev"], st["mask_dev"], True, True)
                 pins = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in heads}
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), torch.no_grad():
-                st["kp_dev"].copy_(st["kp_pin"], non_blocking=True)
-                st["mask_dev"].copy_(st["mask_pin"], non_blocking=True)
-                out = self._run_branches(st["kp_dev"], st["mask_dev"], True)
+            # the two slots' graphs replay in stream order, never concurrently: they share one memory pool
+            pool = st.get("pool")
+            with torch.cuda.graph(graph, pool=pool), torch.no_grad():
+                st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
+                st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
+                out = self._run_branches(st["kp_dev"], st["mask_dev"], True, True)
                 for k in heads:
                     pins[k].copy_(out[k], non_blocking=True)
-            ent = st[key] = (graph, pins, out)
+            if pool is None:
+                st["pool"] = graph.pool()
+            ent = slot[key] = (graph, pins, out)
         graph, pins, _ = ent
         graph.replay()
         return dict(pins)
 
     # ------------------------------------------------------------------ CUDA graph replay
-    def _run_graph(self, keypoints, mask, with_heads):
-        key = (tuple(keypoints.shape), str(keypoints.device), F_.get_precision(self.precision).name, with_heads)
-        ent = self._graphs.get(key)
+    def _run_graph(self, keypoints, mask, with_heads, compact=False):
+        key = (tuple(keypoints.shape), str(keypoints.device), F_.get_precision(self.precision).name, with_heads, compact)
+        ent = self._cache_get(self._graphs, key)
         if ent is None:
             static_kp = torch.empty_like(keypoints)
             static_mask = torch.empty(mask.shape, dtype=torch.uint8, device=mask.device)
@@ -264,27 +348,27 @@ class MSCAEncoder(nn.Module):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up: packs weights, sets kernel attributes
                 for _ in range(2):
-                    self._run(static_kp, static_mask, with_heads)
+                    self._run(static_kp, static_mask, with_heads, compact)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
             with torch.cuda.graph(graph):
-                static_out = self._run_branches(static_kp, static_mask, with_heads)
+                static_out = self._run_branches(static_kp, static_mask, with_heads, compact)
             ent = (graph, static_kp, static_mask, static_out, L.launch_count() - n0)
-            self._graphs[key] = ent
+            self._cache_put(self._graphs, key, ent)
         graph, static_kp, static_mask, static_out, _ = ent
         static_kp.copy_(keypoints, non_blocking=True)
         static_mask.copy_(F_.key_mask_u8(mask), non_blocking=True)
         graph.replay()
         return static_out
 
-    def _run_branches(self, kp, km, with_heads):
+    def _run_branches(self, kp, km, with_heads, compact=False):
         """One `_run` per sub-batch on forked streams (captured as parallel graph branches), joined and
         concatenated on the capturing stream."""
         b = kp.shape[0]
         n = min(self.micro_batches, b)
         if n <= 1:
-            return self._run(kp, km, with_heads)
+            return self._run(kp, km, with_heads, compact)
         bounds = [(i * b) // n for i in range(n + 1)]
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
@@ -295,7 +379,7 @@ class MSCAEncoder(nn.Module):
             if i:
                 st.wait_event(fork)
             with torch.cuda.stream(st):
-                parts.append(self._run(kp[bounds[i]:bounds[i + 1]], km[bounds[i]:bounds[i + 1]], with_heads))
+                parts.append(self._run(kp[bounds[i]:bounds[i + 1]], km[bounds[i]:bounds[i + 1]], with_heads, compact))
                 if i:
                     ev = torch.cuda.Event()
                     ev.record(st)
@@ -306,6 +390,6 @@ class MSCAEncoder(nn.Module):
 
     def graph_launches(self, keypoints_shape, device, with_heads=True) -> int:
         """Kernels inside the captured graph for this shape (0 if not captured)."""
-        key = (tuple(keypoints_shape), str(device), F_.get_precision(self.precision).name, with_heads)
+        key = (tuple(keypoints_shape), str(device), F_.get_precision(self.precision).name, with_heads, False)
         ent = self._graphs.get(key)
         return 0 if ent is None else ent[4]

@@ -25,7 +25,7 @@ def test_library_exports_header_symbols():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.scatt_abi_version() == 2
+    assert lib.scatt_abi_version() == 3
     assert b"sm_100a" in lib.scatt_version()
 
 
