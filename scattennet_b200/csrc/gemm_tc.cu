@@ -972,7 +972,7 @@ static EncodeFn get_encode() {
   return fn;
 }
 
-int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K, int box_rows, int fmt) {
+int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K, int box_rows, int fmt, int box_planes) {
   EncodeFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -980,7 +980,7 @@ int encode_planes_map(CUtensorMap* map, const void* planes, int64_t rows, int K,
   }
   const cuuint64_t dims[3] = {cuuint64_t(K), cuuint64_t(rows), 2};
   const cuuint64_t strides[2] = {cuuint64_t(K) * 2, cuuint64_t(rows) * cuuint64_t(K) * 2};
-  const cuuint32_t box[3] = {BK, cuuint32_t(box_rows), 1};
+  const cuuint32_t box[3] = {BK, cuuint32_t(box_rows), cuuint32_t(box_planes)};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, fmt == SCATT_PLANE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -364,10 +364,16 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
 
 
 FUSED_BLOCK = os.environ.get("SCATT_FUSED_BLOCK", "1") != "0"  # False: out_proj+LN, fc1, fc2+LN as three scatt_linear launches
+# Row tiles (128 rows, all streams of the group) from which the fused layer tail replaces the three GEMM launches.
+# One CTA runs a whole row tile through all three GEMMs, so a handful of tiles leaves most SMs idle where the
+# separate launches spread each GEMM over ~100 CTAs (measured cross-over: profiles/r02_sweep_batch_1gpu.md).
+FUSED_BLOCK_MIN_TILES = int(os.environ.get("SCATT_FUSED_BLOCK_MIN_TILES", "60"))
 
 
-def attn_block_supported(prec: Precision, M: int, D: int, F: int) -> bool:
-    return FUSED_BLOCK and prec.uses_planes and bool(L.load().scatt_attn_block_supported(M, D, F))
+def attn_block_supported(prec: Precision, M: int, D: int, F: int, group: int = 1) -> bool:
+    if not (FUSED_BLOCK and prec.uses_planes) or ((M + 127) // 128) * group < FUSED_BLOCK_MIN_TILES:
+        return False
+    return bool(L.load().scatt_attn_block_supported(M, D, F))
 
 
 def attn_block(prec: Precision, ctx: Sequence[Act], residuals: Sequence[Act], out_packs: Sequence[PackedLinear],

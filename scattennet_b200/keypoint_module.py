@@ -112,7 +112,7 @@ def _ffn_ln(prec, mlps: Sequence[FeedForward], norms, h: List[Act], keep_f32: bo
 
 def _fused_tail_ok(prec, attns, mlps, norms1, norms2, ctx: List[Act], residuals: List[Act]) -> bool:
     """``scatt_attn_block`` takes the tail of the layer: plane operands, biased linears, both LayerNorms alike."""
-    if not F_.attn_block_supported(prec, ctx[0].rows, ctx[0].cols, mlps[0].fc1.out_features):
+    if not F_.attn_block_supported(prec, ctx[0].rows, ctx[0].cols, mlps[0].fc1.out_features, len(ctx)):
         return False
     if any(c.planes is None for c in ctx) or any(r.planes is None and r.f32 is None for r in residuals):
         return False

@@ -6,6 +6,7 @@ torch restatement and against the three-launch path it replaces.  Tolerances per
 import pytest
 import torch
 
+from scattennet_b200 import _lib as L
 from scattennet_b200 import functional as F_
 from scattennet_b200 import synth
 from scattennet_b200.functional import Act
@@ -58,7 +59,7 @@ def run_block(prec, ctxs, xs, layers, out_f32=True, out_planes=True):
 def test_attn_block_vs_fp64(mode, M, Fh, G):
     prec = F_.get_precision(mode)
     D = 256
-    assert F_.attn_block_supported(prec, M, D, Fh)
+    assert L.load().scatt_attn_block_supported(M, D, Fh)
     layers = [make_layer(D, Fh, 3 + g) for g in range(G)]
     ctxs = [rnd(M, D, seed=10 + g) for g in range(G)]
     xs = [rnd(M, D, seed=20 + g) for g in range(G)]
