@@ -39,6 +39,35 @@ CFG_NAME, BATCH, T = "phoenix-2014t", 8, 200
 VOCAB = 1120
 
 
+def workload(batch: int) -> str:
+    """One description of the work for both arms (the driver compares the two ``config.workload`` strings)."""
+    return (f"SCAttenNet {CFG_NAME}.yaml encoder forward (region split + 3 streams + fusion + 4 linear heads), "
+            f"batch {batch} per GPU, T={T}, V={VOCAB}, random-init weights")
+
+
+def kernel_key(name: str):
+    """``(base name, template ints)`` of a kernel symbol, from a demangled profiler name or ``scatt_last_kernel``:
+    ``void scatt::(anonymous namespace)::linear_tc_kernel<256, 1, 0>(...)`` -> ``("linear_tc_kernel", (256, 1, 0))``."""
+    import re
+
+    head = name.replace("(anonymous namespace)", "anon").split("(")[0].strip()
+    m = re.match(r"^(?:.*?[\s:])?(\w+)(?:<(.*)>)?$", head)
+    if not m:
+        return (name, ())
+    args = []
+    for tok in (m.group(2) or "").split(","):
+        tok = tok.strip().split(")")[-1]  # "(scatt_plane_fmt)0" -> "0"
+        if tok in ("true", "false"):
+            args.append(1 if tok == "true" else 0)
+        elif tok.lstrip("-").isdigit():
+            args.append(int(tok))
+    return (m.group(1), tuple(args))
+
+
+def key_str(key) -> str:
+    return key[0] + (f"<{', '.join(str(a) for a in key[1])}>" if key[1] else "")
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -150,8 +179,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"SCAttenNet {CFG_NAME}.yaml encoder forward (3 streams + fusion + 4 linear heads), batch {BATCH}, T={T}",
-                   "host": "CPU only (reference path: the oracle port of model/*.py, ATen fp32)"},
+        "config": {"workload": workload(BATCH),
+                   "host": "CPU only (reference path: the oracle port of model/*.py, ATen fp32, all host cores)"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -209,6 +238,14 @@ def run_ours(args):
             out = step()
         torch.cuda.synchronize()
         launches_per_step = model.graph_launches(kp_dev.shape, dev)
+        gather_check = None
+        if world > 1:  # one-off, untimed: the gathered logits of the step equal NCCL's all-gather of the same shards
+            shard = out["fuse_coord_gloss_logits"].contiguous()
+            ref = [torch.empty_like(shard) for _ in range(world)]
+            dist.all_gather(ref, shard)
+            ok = torch.tensor([1 if torch.equal(out["gathered"], torch.cat(ref, 0)) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            gather_check = {"ok": bool(int(ok)), "against": "torch.distributed.all_gather (NCCL) of the same shards, every rank"}
 
         sampler = ClockSampler(local)
         sampler.start()
@@ -237,28 +274,29 @@ def run_ours(args):
         h2d = args.batch * T * n_used * 2 * 4 + args.batch * T
         d2h = sum(out[k].numel() * out[k].element_size() for k in e2e_heads)
 
-        if world > 1 and rank == 0:
-            d2h *= world  # rank 0 reads the gathered logits
-
         def e2e_step():
-            return model.forward_host(kp_pin, mask_pin, heads=e2e_heads, device=dev, gather=world > 1)
+            # N > 1: the logits are all-gathered on the device (every rank can decode any sequence) and each rank
+            # reads back its own shard - no rank funnels the whole batch through its PCIe link
+            return model.forward_host(kp_pin, mask_pin, heads=e2e_heads, device=dev, gather=world > 1, gather_to_host="shard")
 
         for _ in range(3):
             e2e_step()
         ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         sampler.active.set()
+        wall0 = time.perf_counter()
         for e0, e1 in ev2:
             flush.zero_()
             e0.record()
             e2e_step()
             e1.record()
         barrier()
+        e2e_wall = time.perf_counter() - wall0
         sampler.active.clear()
         e2e_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev2)
         sampler.stop_flag.set()
 
-        # ---- per-kernel share and achieved rate: eager passes with CUDA-event brackets per C-ABI call
+        # ---- algorithmic flops / bytes per kernel symbol: eager passes, every C-ABI call bracketed (also the fallback timing)
         model.use_graph = False
         for _ in range(2):
             model(kp_dev, mask_dev)
@@ -269,8 +307,56 @@ def run_ours(args):
                 # time kernels running back to back, not the host's launch latency
                 torch.cuda._sleep(20_000_000)
                 model(kp_dev, mask_dev)
-        per_kernel = prof.summary()
+        per_call = prof.summary()
         model.use_graph = True
+        # ---- per-kernel time INSIDE the replayed graph (the timed region's own launches): CUPTI kernel records
+        graph_kernels, graph_prof_ms, prof_err = None, None, None
+        try:
+            from torch.profiler import ProfilerActivity, profile
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.profile_steps)]
+            with profile(activities=[ProfilerActivity.CUDA]) as kprof:
+                for e0, e1 in pe:
+                    flush.zero_()
+                    e0.record()
+                    model(kp_dev, mask_dev)
+                    e1.record()
+                torch.cuda.synchronize()
+            graph_prof_ms = sum(e0.elapsed_time(e1) for e0, e1 in pe) / args.profile_steps
+            # Programmatic dependent launch makes successive kernels OVERLAP on the timeline (the successor becomes
+            # resident and waits in griddepcontrol.wait), so raw durations double count.  Sweep the timeline and give
+            # every instant to the running kernel that started first (the one doing the work); kernels on parallel
+            # graph branches that really run side by side therefore share the wall time instead of both counting it.
+            recs = []
+            for evt in kprof.events():
+                if "DeviceType.CUDA" not in str(getattr(evt, "device_type", "")):
+                    continue
+                key = kernel_key(evt.name)
+                if "Memset" in evt.name or "Memcpy" in evt.name or key[0] in ("vectorized_elementwise_kernel", "direct_copy_kernel_cuda"):
+                    continue  # the L2 flush and the input copies are not kernels of the path
+                recs.append((float(evt.time_range.start), float(evt.time_range.end), key))
+            recs.sort()
+            graph_kernels = {}
+            for st, en, key in recs:
+                g = graph_kernels.setdefault(key, {"launches": 0, "ms": 0.0, "raw_ms": 0.0})
+                g["launches"] += 1
+                g["raw_ms"] += (en - st) * 1e-3
+            bounds = sorted({t for r in recs for t in r[:2]})
+            active, nxt = [], 0
+            for t0, t1 in zip(bounds, bounds[1:]):
+                while nxt < len(recs) and recs[nxt][0] <= t0:
+                    active.append(recs[nxt])
+                    nxt += 1
+                active = [r for r in active if r[1] > t0]
+                if active:
+                    graph_kernels[min(active)[2]]["ms"] += (t1 - t0) * 1e-3
+            if not graph_kernels:
+                graph_kernels, prof_err = None, "the profiler returned no kernel records"
+        except Exception as exc:  # CUPTI unavailable: fall back to the eager event brackets
+            graph_kernels, prof_err = None, f"{type(exc).__name__}: {exc}"
 
         # ---- the same step with the path's first consumer attached (BiLSTM alignment head):
         # reported beside the headline, not part of it
@@ -359,28 +445,65 @@ def run_ours(args):
     if rank == 0:
         peaks = measured_peaks()
         frames = world * args.batch * T * args.steps
+        terms = F_.get_precision(args.precision).terms
+        nprof = args.profile_steps
+        work = {}  # kernel key -> algorithmic flops / bytes per step, launches per step (eager pass)
+        for sym, v in per_call.items():
+            w = work.setdefault(kernel_key(sym), {"flops": 0.0, "bytes": 0.0, "calls": 0.0, "eager_ms": 0.0})
+            w["flops"] += v["flops"] / nprof
+            w["bytes"] += v["bytes"] / nprof
+            w["calls"] += v["calls"] / nprof
+            w["eager_ms"] += v["ms"] / nprof
+        per_kernel = {}
+        if graph_kernels is not None:
+            source = ("CUPTI kernel records (torch.profiler) of replays of the SAME captured graph the timed region replays, "
+                      f"L2 flushed between replays, {nprof} replays; overlapping records (programmatic dependent launch, parallel "
+                      "branches) are de-overlapped: every instant goes to the running kernel that started first")
+            for key, gk in graph_kernels.items():
+                w = work.get(key) or next((v for k, v in work.items() if k[0] == key[0]), None) or {"flops": 0.0, "bytes": 0.0}
+                per_kernel[key] = {"ms": gk["ms"] / nprof, "launches": gk["launches"] / nprof, "flops": w["flops"], "bytes": w["bytes"],
+                                   "raw_ms": gk["raw_ms"] / nprof}
+            step_ms_prof = graph_prof_ms
+        else:
+            source = f"CUDA-event brackets around every C-ABI call of eager passes (profiler unavailable: {prof_err})"
+            for key, w in work.items():
+                per_kernel[key] = {"ms": w["eager_ms"], "launches": w["calls"], "flops": w["flops"], "bytes": w["bytes"]}
+            step_ms_prof = sum(v["ms"] for v in per_kernel.values())
         top = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
         tk = per_kernel[top]
-        total_prof_ms = sum(v["ms"] for v in per_kernel.values())
-        terms = F_.get_precision(args.precision).terms
-        tensor_bound = top in ("linear_tc_kernel", "stream_attention_kernel", "stream_attention_tc_kernel", "fusion_attention_kernel", "linear_simt_kernel")
-        if tensor_bound:
-            achieved = tk["flops"] / (tk["ms"] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops"]}
+        sec = tk["ms"] * 1e-3
+        tf, gbs = tk["flops"] / sec / 1e12, tk["bytes"] / sec / 1e9
+        f_tensor, f_hbm = tf / peaks["bf16_tflops"], gbs / peaks["hbm_gbs"]
+        if f_tensor >= f_hbm:
+            roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": f_tensor,
+                    "other_bound": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": f_hbm}}
         else:
-            achieved = tk["bytes"] / (tk["ms"] * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"]}
+            roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": f_hbm,
+                    "other_bound": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": f_tensor}}
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get(top)
+                tj = json.load(fh)
+            traffic = tj.get(key_str(top), tj.get(top[0]))
+        sum_ms = sum(v["ms"] for v in per_kernel.values())
+        total_flops = sum(v["flops"] for v in per_kernel.values())
+        ms_step = dev_ms / args.steps
         roof.update({
-            "traffic": traffic, "kernel": top, "launches_profiled": tk["calls"], "avg_launch_us": 1e3 * tk["ms"] / tk["calls"],
-            "share_of_step": tk["ms"] / total_prof_ms, "peak_source": peaks["source"] + ", burst figure",
-            "note": f"algorithmic flops (2*M*N*K, one product per MAC); the {terms}-term split issues {max(terms, 1)}x that on the tensor pipe",
-            "per_kernel_ms_per_step": {k: round(v["ms"] / args.profile_steps, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])},
+            "traffic": traffic, "kernel": key_str(top), "launches_per_step": tk["launches"],
+            "avg_launch_us": 1e3 * tk["ms"] / max(tk["launches"], 1e-9), "share_of_step": tk["ms"] / step_ms_prof,
+            "algorithmic_flops_per_step": tk["flops"], "algorithmic_bytes_per_step": tk["bytes"],
+            "peak_source": peaks["source"] + ", burst figure", "timing_source": source,
+            "step_ms_under_profiler": step_ms_prof, "sum_kernel_ms_per_step": sum_ms,
+            "note": f"algorithmic flops (2*M*N*K, one product per MAC; the {terms}-term split issues {max(terms, 1)}x that on the tensor pipe); "
+                    "kernels on parallel graph branches overlap, so the per-kernel sum may exceed the step",
+            "whole_step": {"algorithmic_tflops": total_flops / (ms_step * 1e-3) / 1e12,
+                           "frac_of_bf16_peak": total_flops / (ms_step * 1e-3) / 1e12 / peaks["bf16_tflops"]},
+            "per_kernel": {key_str(k): {"ms_per_step": round(v["ms"], 5), "launches_per_step": round(v["launches"], 2),
+                                        "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else None,
+                                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                                        "raw_record_ms_per_step": round(v.get("raw_ms", v["ms"]), 5)}
+                           for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms"])},
         })
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -396,16 +519,18 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": f"{args.precision} (16-bit split planes on tcgen05, fp32 accumulate; fp32 softmax/LN)",
             "data": "synthetic",
-            "config": {"workload": f"SCAttenNet {CFG_NAME}.yaml encoder forward (region split + 3 streams + fusion + 4 linear heads), "
-                                   f"batch {args.batch} per GPU, T={T}, V={VOCAB}, random-init weights",
+            "config": {"workload": workload(args.batch),
                        "global_batch": world * args.batch, "seq_len": T, "parallelism": f"dp{world} (batch shards, logits all-gather)",
                        "gather": gather_route,
                        "l2": "flushed between timed steps (256 MiB memset outside the event brackets)",
-                       "e2e_path": "MSCAEncoder.forward_host: host tensors in, exact host gather of the used joints, H2D, "
-                                   "graph replay, D2H of fuse_coord_gloss_logits",
+                       "e2e_path": "MSCAEncoder.forward_host: host tensors in, exact host gather of the used joints into "
+                                   "double-buffered pinned staging (event per slot), H2D, graph replay, D2H of "
+                                   "fuse_coord_gloss_logits" + (" (N > 1: all-gathered on the device, each rank reads back its own shard)" if world > 1 else ""),
                        "timing": "CUDA events per step on the launching stream, summed; max over ranks", "cuda_graph": True},
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "wall_ms_per_step_incl_l2_flush": 1e3 * e2e_wall / args.steps},
+            "gather_check": gather_check,
             "gpu_launches": (launches_per_step + (1 if peer_used else 0)) * args.steps,
             "launches_per_step": launches_per_step,
             "wall_s_timed_region": wall,

@@ -67,6 +67,9 @@ enum scatt_attention_kind { SCATT_ATTN_SELF = 0, SCATT_ATTN_CAUSAL = 1, SCATT_AT
 int scatt_abi_version(void);
 const char* scatt_version(void);
 const char* scatt_last_error(void);
+/* Name of the kernel the calling host thread launched last, with its template arguments as a demangler prints them
+ * ("linear_tc_kernel<256, 1, 0>"): lets bench.py attach algorithmic flops / bytes to the symbols of a profiler trace. */
+const char* scatt_last_kernel(void);
 /* Number of kernels this library has launched from the calling process (all
  * threads); bench.py's `gpu_launches` is the difference across the timed region. */
 uint64_t scatt_launch_count(void);

@@ -25,7 +25,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 
 # every symbol include/scatt.h declares (tests check the .so exports all of them)
 SYMBOLS = (
-    "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_launch_count", "scatt_device_check",
+    "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
@@ -91,6 +91,7 @@ def _declare(lib):
     lib.scatt_abi_version.restype = i32
     lib.scatt_version.restype = C.c_char_p
     lib.scatt_last_error.restype = C.c_char_p
+    lib.scatt_last_kernel.restype = C.c_char_p
     lib.scatt_launch_count.restype = C.c_uint64
     lib.scatt_device_check.restype = i32
     lib.scatt_debug_set_trace.argtypes = [vp]

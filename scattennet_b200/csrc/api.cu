@@ -15,6 +15,14 @@ std::atomic<int> g_pdl{[] {
 
 namespace {
 thread_local char t_error[512] = "";
+thread_local char t_kernel[128] = "";
+}
+
+void set_last_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_kernel, sizeof(t_kernel), fmt, ap);
+  va_end(ap);
 }
 
 void set_error(const char* fmt, ...) {
@@ -40,6 +48,8 @@ int scatt_abi_version(void) { return SCATT_ABI_VERSION; }
 const char* scatt_version(void) { return "scatt-b200 0.1 (sm_100a; tcgen05+TMA linear engine, fp32 SIMT engine)"; }
 
 const char* scatt_last_error(void) { return t_error; }
+
+const char* scatt_last_kernel(void) { return t_kernel; }
 
 uint64_t scatt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -215,7 +215,7 @@ int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq,
   }
   const size_t smem = (size_t(Tk) * HD * 2 + Tk) * sizeof(float);
   SCATT_REQUIRE(smem <= 200 * 1024, "attention: Tk=%d too long for the shared-memory K/V stage", Tk);
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(stream_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done.store(true);
@@ -232,7 +232,7 @@ int launch_fusion_attention(const float* q, const float* k, const float* v, int 
   if (B == 0 || T == 0) return SCATT_OK;
   const size_t smem = (size_t(FQ) * D + size_t(FQ) * T + FQ) * sizeof(float);
   SCATT_REQUIRE(smem <= 200 * 1024, "fusion_attention: T=%d too long", T);
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(fusion_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done.store(true);

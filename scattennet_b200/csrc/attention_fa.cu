@@ -501,7 +501,7 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
     P.p[i] = FaProblem{a.key_mask, a.out, reinterpret_cast<uint16_t*>(a.out_planes), a.q.col, a.k.col, a.v.col};
   }
   const uint32_t kFaSmem = fa_smem_map(P.nblk, P.kbox).total;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     const int max_smem = int(fa_smem_map(kMaxBlocks, KBLK).total);
     SCATT_CUDA(cudaFuncSetAttribute(stream_attention_fa_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -513,7 +513,9 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
     (void)launch_kernel(stream_attention_fa_kernel<SCATT_PLANE_F16>, grid, dim3(kThreadsFa), kFaSmem, s, P);
   else
     (void)launch_kernel(stream_attention_fa_kernel<SCATT_PLANE_BF16>, grid, dim3(kThreadsFa), kFaSmem, s, P);
-  return after_launch("stream_attention_fa_kernel");
+  const int rc = after_launch("stream_attention_fa_kernel");
+  set_last_kernel("stream_attention_fa_kernel<%d>", fmt);
+  return rc;
 }
 
 }  // namespace scatt

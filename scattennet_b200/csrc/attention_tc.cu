@@ -389,7 +389,7 @@ int launch_attention_tc(const scatt_attention_problem* p, int group, int B, int 
   }
   P.B = B, P.Tq = Tq, P.Tk = Tk, P.H = H, P.kind = kind, P.fmt = fmt, P.terms = terms;
   P.ldq = ldq, P.ldk = ldk, P.ldv = ldv;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(stream_attention_tc_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     int(kSmemBytes)));

@@ -650,19 +650,19 @@ int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D,
     if (rc != SCATT_OK) return rc;
     P.prob[i] = BlkProblem{a.bo, a.ln1_g, a.ln1_b, a.b1, a.b2, a.ln2_g, a.ln2_b, a.y, reinterpret_cast<uint16_t*>(a.y_planes)};
   }
-  static std::atomic<bool> attr_done[64];  // per device: the attribute belongs to the device's context
-  int dev = 0;
-  SCATT_CUDA(cudaGetDevice(&dev));
-  if (!attr_done[dev & 63].load()) {
+  static PerDeviceFlag attr_done;
+  if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-    attr_done[dev & 63].store(true);
+    attr_done.store(true);
   }
   const int tiles = P.tiles_m * group;
   dim3 grid(unsigned(tiles < 148 ? tiles : 148));
   if (fmt == SCATT_PLANE_F16) (void)launch_kernel(attn_block_kernel<SCATT_PLANE_F16>, grid, dim3(kThreads), kSmemBytes, s, P);
   else (void)launch_kernel(attn_block_kernel<SCATT_PLANE_BF16>, grid, dim3(kThreads), kSmemBytes, s, P);
-  return after_launch("attn_block_kernel");
+  const int rc = after_launch("attn_block_kernel");
+  set_last_kernel("attn_block_kernel<%d>", fmt);
+  return rc;
 }
 
 }  // namespace scatt

@@ -37,8 +37,29 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     }                                       \
   } while (0)
 
+// Per-device "done" flag with the interface of std::atomic<bool>: kernel attributes (cudaFuncSetAttribute) belong to
+// the device's context, so a process that drives several GPUs must set them once per device, not once per process.
+class PerDeviceFlag {
+ public:
+  bool load() const { return flags_[index()].load(std::memory_order_acquire); }
+  void store(bool v) { flags_[index()].store(v, std::memory_order_release); }
+
+ private:
+  static int index() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  std::atomic<bool> flags_[64] = {};
+};
+
+// Name (with template arguments, as a demangler prints them) of the kernel this host thread launched last:
+// bench.py matches it with the symbols of a profiler trace to attach algorithmic flops / bytes to each kernel.
+void set_last_kernel(const char* fmt, ...);
+
 // Call after every kernel launch: counts it and surfaces launch-config errors.
 inline int after_launch(const char* name) {
+  set_last_kernel("%s", name);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -287,10 +287,10 @@ int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths
   const size_t smem = size_t((V + 3) & ~3) * 4 + size_t(node_cap) * 8 + size_t(kCtcThreads / 32) * beam * 8 + sizeof(Beam) + 16;
   SCATT_REQUIRE(smem <= 200 * 1024, "ctc_beam_decode: T=%d, V=%d, beam=%d need %zu bytes of shared memory (limit 200 KB)", T, V,
                 beam, smem);
-  static std::atomic<size_t> configured{48 * 1024};
-  if (smem > configured.load(std::memory_order_acquire)) {
-    SCATT_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured.store(smem, std::memory_order_release);
+  static PerDeviceFlag configured;  // the attribute belongs to the device's context: once per device, to the limit
+  if (!configured.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(ctc_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured.store(true);
   }
   (void)launch_kernel(ctc_beam_kernel, dim3(B), dim3(kCtcThreads), smem, s, logits, T, V, lengths, beam, node_cap, out_ids,
                       out_len, out_score);

@@ -1044,7 +1044,7 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
   size_t ring = size_t(stages) * kStageBytes;
   if (ring < size_t(kEpiWarps) * 16384) ring = size_t(kEpiWarps) * 16384;  // the epilogue's output boxes reuse the ring
   const size_t smem = ring + res_bytes + 1024 /*align slack*/ + 16 * stages + 64 + 3 * BN * 4 + (2 + (LN >= 2 ? LN : 1)) * BM * 8 + kEpiWarps * kEpiWarpBytes;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
   if constexpr (LN >= 2) {
     if (!attr_done.load()) {
@@ -1052,14 +1052,18 @@ int launch_bn_fmt(TcParams& P, int group, cudaStream_t s) {
       attr_done.store(true);
     }
     (void)launch_kernel_cluster(linear_tc_ln_cluster_kernel<FMT, LN>, grid, dim3(64 + 32 * kEpiWarps), smem, s, LN, P);
-    return after_launch("linear_tc_ln_cluster_kernel");
+    const int rc = after_launch("linear_tc_ln_cluster_kernel");
+    set_last_kernel("linear_tc_ln_cluster_kernel<%d, %d>", FMT, LN);
+    return rc;
   } else {
     if (!attr_done.load()) {
       SCATT_CUDA(cudaFuncSetAttribute(linear_tc_kernel<BN, LN, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attr_done.store(true);
     }
     (void)launch_kernel(linear_tc_kernel<BN, LN, FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
-    return after_launch("linear_tc_kernel");
+    const int rc = after_launch("linear_tc_kernel");
+    set_last_kernel("linear_tc_kernel<%d, %d, %d>", BN, LN, FMT);
+    return rc;
   }
 }
 
@@ -1076,14 +1080,16 @@ int launch_sub2_fmt(TcParams& P, int group, cudaStream_t s) {
   P.stages = stages;
   const size_t smem = size_t(stages) * kStageBytes + ostage + 1024 + 16 * stages + 64 + 8 * NSUB + 3 * BN * NSUB * 4 + 3 * BM * 8 +
                       kEpiWarps * kEpiWarpBytes;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(linear_tc_sub2_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done.store(true);
   }
   dim3 grid((P.N + BN * NSUB - 1) / (BN * NSUB), unsigned((P.M + BM - 1) / BM), group);
   (void)launch_kernel(linear_tc_sub2_kernel<FMT>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
-  return after_launch("linear_tc_sub2_kernel");
+  const int rc = after_launch("linear_tc_sub2_kernel");
+  set_last_kernel("linear_tc_sub2_kernel<%d>", FMT);
+  return rc;
 }
 
 template <int FMT, int BN, bool SLIM>
@@ -1097,7 +1103,7 @@ int launch_persist_fmt(TcParams& P, int group, cudaStream_t s) {
   P.groups = group;
   P.pre_init = 0;
   const size_t smem = size_t(stages) * kStageBytes + fixed + 16 * stages;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(linear_tc_persist_kernel<FMT, BN, SLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done.store(true);
@@ -1105,7 +1111,9 @@ int launch_persist_fmt(TcParams& P, int group, cudaStream_t s) {
   const int64_t tiles = int64_t((P.N + BN - 1) / BN) * ((P.M + BM - 1) / BM) * group;
   dim3 grid(unsigned(tiles < 148 ? tiles : 148));
   (void)launch_kernel(linear_tc_persist_kernel<FMT, BN, SLIM>, grid, dim3(64 + 32 * kEpiWarps), smem, s, P);
-  return after_launch("linear_tc_persist_kernel");
+  const int rc = after_launch("linear_tc_persist_kernel");
+  set_last_kernel("linear_tc_persist_kernel<%d, %d, %d>", FMT, BN, SLIM ? 1 : 0);
+  return rc;
 }
 
 template <int FMT>
@@ -1120,14 +1128,16 @@ int launch_dual_fmt(TcParams& P, int group, cudaStream_t s) {
   size_t ring = size_t(stages) * kStageBytes;
   if (ring < size_t(EW) * 16384) ring = size_t(EW) * 16384;
   const size_t smem = ring + 1024 + 16 * stages + 64 + 3 * BN * 4 + 3 * BM * 8 + EW * kEpiWarpBytes;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     SCATT_CUDA(cudaFuncSetAttribute(linear_tc_dual_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_done.store(true);
   }
   dim3 grid((P.N + BN - 1) / BN, unsigned((P.M + BM - 1) / BM), group);
   (void)launch_kernel(linear_tc_dual_kernel<FMT>, grid, dim3(64 + 32 * EW), smem, s, P);
-  return after_launch("linear_tc_dual_kernel");
+  const int rc = after_launch("linear_tc_dual_kernel");
+  set_last_kernel("linear_tc_dual_kernel<%d>", FMT);
+  return rc;
 }
 
 template <int BN, int LN>

@@ -240,10 +240,11 @@ int launch_lstm_bidir(const float* gates_x, int64_t ldg, const float* w_hh, floa
   SCATT_REQUIRE(gates_x && w_hh && workspace && (y || y_planes), "lstm_bidir: null argument");
   if (B == 0 || T == 0) return SCATT_OK;
   const size_t smem = sizeof(LstmSmem) + size_t(B) * kUnits * sizeof(float);
-  static std::atomic<size_t> configured{0};
-  if (configured.load(std::memory_order_acquire) < smem) {
-    SCATT_CUDA(cudaFuncSetAttribute(lstm_bidir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured.store(smem, std::memory_order_release);
+  SCATT_REQUIRE(smem <= 227 * 1024, "lstm_bidir: B=%lld needs %zu bytes of shared memory", (long long)B, smem);
+  static PerDeviceFlag configured;  // the attribute belongs to the device's context: once per device, to the limit
+  if (!configured.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(lstm_bidir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured.store(true);
   }
   SCATT_CUDA(cudaMemsetAsync(workspace, 0, lstm_workspace_bytes(B, H), s));
   // all 128 CTAs spin on each other: the launch must be co-resident (co-operative), and is not programmatic

@@ -410,7 +410,7 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
   if (int64_t(B) * T == 0) return SCATT_OK;
   const int wt_stride = max_nj * D;
   const size_t smem = size_t(2) * wt_stride * sizeof(float) + kFeStageBytes;
-  static std::atomic<bool> attr_done{false};
+  static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
     const int max_smem = 2 * 32 * 256 * 4 + kFeStageBytes;
     SCATT_CUDA(cudaFuncSetAttribute(frontend_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -441,7 +441,9 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
   dim3 grid(prm.cta_begin[n]);
   if (R == 1) (void)launch_kernel(frontend_kernel<1>, grid, dim3(32 * kFeWarps), smem, s, kp, B, T, K, prm, fmt, wt_stride);
   else (void)launch_kernel(frontend_kernel<4>, grid, dim3(32 * kFeWarps), smem, s, kp, B, T, K, prm, fmt, wt_stride);
-  return after_launch("frontend_kernel");
+  const int rc = after_launch("frontend_kernel");
+  set_last_kernel("frontend_kernel<%d>", R);
+  return rc;
 }
 
 int launch_pool_pairs(const float* x, int B, int T, int C, float* y, void* planes, int fmt, cudaStream_t s) {

@@ -79,9 +79,10 @@ class OpProfiler:
     ``bench.py`` to find the dominant kernel and its achieved rate."""
 
     def __init__(self):
-        self.records = []  # (kernel name, start event, end event, algorithmic flops, algorithmic bytes)
+        self.records = []  # (kernel symbol, start event, end event, algorithmic flops, algorithmic bytes)
 
     def summary(self):
+        """Per kernel symbol (``scatt_last_kernel``: name + template arguments): calls, event-bracketed ms, flops, bytes."""
         torch.cuda.synchronize()
         agg = {}
         for name, e0, e1, flops, nbytes in self.records:
@@ -124,7 +125,8 @@ class _timed:
         if _profiler is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profiler.records.append((self.name, self.e0, e1, self.flops, self.nbytes))
+            sym = L.load().scatt_last_kernel().decode() or self.name  # the symbol the C ABI call actually launched
+            _profiler.records.append((sym, self.e0, e1, self.flops, self.nbytes))
         return False
 
 
@@ -349,9 +351,13 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     if isinstance(r0, Act):
         r0 = r0.f32
     ldres = r0.stride(0) if r0 is not None else N
-    esz = 2 if prec.uses_planes else 4
     name = "linear_tc_kernel" if prec.uses_planes else "linear_simt_kernel"
-    with _timed(name, 2.0 * G * M * N * K, G * ((M * K + N * K) * esz + M * N * 4.0)):
+    if prec.uses_planes:  # operand planes actually read (hi, + lo of x from 2 terms, + lo of W from 3), outputs written
+        in_bytes = M * K * 2.0 * (2 if prec.terms >= 2 else 1) + N * K * 2.0 * (2 if prec.terms >= 3 else 1)
+    else:
+        in_bytes = (M * K + N * K) * 4.0
+    out_bytes = M * N * 4.0 * ((1 if need_f32 else 0) + (1 if want_planes else 0)) + (M * N * 4.0 if residuals is not None else 0.0)
+    with _timed(name, 2.0 * G * M * N * K, G * (in_bytes + out_bytes)):
         L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
                                       max(prec.terms, 1), _stream()), "scatt_linear")
     for g in range(G):
