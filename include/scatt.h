@@ -193,6 +193,9 @@ typedef struct scatt_block_problem {
 int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_t M, int D, int F, float ln_eps,
                      int plane_fmt, int terms, void* stream);
 int scatt_attn_block_supported(int64_t M, int D, int F);
+/* Developer aid: 1 | 2 forces one CTA / a 2-CTA cluster per 128-row tile in scatt_attn_block, 0 restores the automatic
+ * choice (clusters while there are at most 74 row tiles). */
+int scatt_debug_set_block_cluster(int cluster);
 
 /* 1 when scatt_linear with a LayerNorm epilogue normalises inside the GEMM kernel for this shape (tcgen05
  * engine: N = 256 always; N = 512 / 1024 by 4- / 8-CTA clusters while ceil(M / 128) * group * N / 128 <= 148),

@@ -115,6 +115,8 @@ int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_
   return launch_attn_block(problems_host, group, M, D, F, ln_eps, plane_fmt, terms, as_stream(stream));
 }
 
+int scatt_debug_set_block_cluster(int cluster) { return debug_set_block_cluster(cluster); }
+
 int scatt_attn_block_supported(int64_t M, int D, int F) { return attn_block_supported(M, D, F) ? 1 : 0; }
 
 int scatt_linear_ln_fused(int64_t M, int N, int group, int engine) {

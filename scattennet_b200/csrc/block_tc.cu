@@ -34,7 +34,17 @@
 // (out_proj, fc2; fc2 reads A from TMEM: 139 cycles against the 128-cycle floor), N = 128 for the fc1 chunks
 // (shared-memory A: 108 cycles against 64 - the shared-memory read port, not the tensor pipe, is the limit).
 // The kernel is persistent: CTA b walks tiles b, b + grid, ...; the ring runs ahead across tile boundaries.
+//
+// CL = 2 (few row tiles: the small-batch regime): a 2-CTA cluster shares one row tile.  Both CTAs compute out_proj +
+// LayerNorm1 (identical results - nothing to exchange), then CTA r takes the hidden chunks j = r, r + 2, ... : half of
+// the W1 / W2 stream and half of the fc1 / fc2 MMAs each.  fc2 is thereby split along K: CTA 1 accumulates its partial
+// sum on top of zeros, CTA 0 on top of h + b2; at the end CTA 1's epilogue warps push their 128 x 256 fp32 partial into
+// CTA 0's (by then idle) hA through distributed shared memory, and CTA 0 adds it in LayerNorm2's statistics pass.
+// (staged in its own hA, then one cp.async.bulk shared::cta -> shared::cluster per warp).  Hand-shake: mbarriers with
+// cluster-scope release / acquire: CTA 0 -> 1 "hA is free", the copies' complete_tx on CTA 0, CTA 0 -> 1 "copied".
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_epi.cuh"
@@ -140,7 +150,30 @@ __device__ __forceinline__ void add_cols_g(float* v, const float* __restrict__ p
   }
 }
 
-template <int FMT>
+__device__ __forceinline__ uint32_t map_to_peer(uint32_t local_addr, uint32_t peer_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(peer_rank));
+  return remote;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {  // releases this thread's earlier (remote) writes
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  for (uint32_t it = 0; it < kWaitLimit; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
+template <int FMT, int CL>
 __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_constant__ BlkParams P) {
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
@@ -151,14 +184,19 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   const uint32_t oproj_full = ctx_bar + 32u, h_ready = oproj_full + 8u;
   const uint32_t fc1_full = h_ready + 8u;   // [2]
   const uint32_t g_ready = fc1_full + 16u;  // [2]
-  const uint32_t out_full = g_ready + 16u, tile_done = out_full + 8u, tmem_ptr_addr = tile_done + 8u;
+  const uint32_t out_full = g_ready + 16u, tile_done = out_full + 8u;
+  const uint32_t peer_free = tile_done + 8u, partial_full = peer_free + 8u, xfer_done = partial_full + 8u, tmem_ptr_addr = xfer_done + 8u;
   volatile uint32_t* trp = reinterpret_cast<volatile uint32_t*>(sm + kTraceOff);
   const bool tracing = SCATT_BLOCK_TRACE && g_trace_blk != nullptr && blockIdx.x == 0;
   (void)trp, (void)tracing;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunk = P.nchunk;
   const int total_tiles = P.tiles_m * P.groups;
+  // CL = 2: the CTAs of a cluster walk the same tiles; CTA `rank` owns the hidden chunks rank, rank + 2, ...
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int first_tile = CL > 1 ? int(blockIdx.x) / CL : int(blockIdx.x), tile_step = CL > 1 ? int(gridDim.x) / CL : int(gridDim.x);
+  const int nchunk = (P.nchunk - int(rank) + CL - 1) / CL;  // local chunks; local chunk i is global chunk rank + i * CL
+  auto chunk_of = [&](int i) { return int(rank) + i * CL; };
   const bool a_lo = P.terms >= 2, b_lo = P.terms >= 3;
 
   if ((base & 1023u) != 0u) __trap();  // the swizzled tiles need the 1024-byte alignment the declaration asks for
@@ -179,6 +217,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     }
     mbar_init(out_full, 1);
     mbar_init(tile_done, 1);
+    mbar_init(peer_free, 1);
+    mbar_init(partial_full, 1);
+    mbar_init(xfer_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int g = 0; g < P.groups; ++g) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_ctx[g]) : "memory");
@@ -209,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (CL > 1) cluster_sync_all();  // the peer's mbarriers exist before anybody arrives on them remotely
   pdl_launch_dependents();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + (tmem_ptr_addr - base));
   if (threadIdx.x == 0) trace(0);
@@ -227,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       ++it;
     };
     int ti = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+    for (int t = first_tile; t < total_tiles; t += tile_step, ++ti) {
       const int g = t / P.tiles_m, m0 = (t % P.tiles_m) * BM;
       auto put_wo = [&](int kb) {
         put(&P.map_wo[g], kb * 64, 0, 0, kStageBytes);
@@ -248,21 +290,25 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       if (lane == 0 && ti == 0) trace(16);
       for (int kb = 0; kb < 4; ++kb) put(&P.map_x[g], kb * 64, m0, 0, kStageBytes);
       for (int kb = 1; kb < 4; ++kb) put_wo(kb);
-      auto fc1_items = [&](int j) {
+      auto fc1_items = [&](int i) {
+        const int j = chunk_of(i);
         for (int kb = 0; kb < 4; ++kb) put(&P.map_w1[g], kb * 64, j * 128, 0, b_lo ? kStageBytes : kTileBytes);
       };
-      auto fc2_items = [&](int j) {
+      auto fc2_items = [&](int i) {
+        const int j = chunk_of(i);
         for (int kb = 0; kb < 2; ++kb) {
           put(&P.map_w2[g], (2 * j + kb) * 64, 0, 0, kStageBytes);
           if (b_lo) put(&P.map_w2[g], (2 * j + kb) * 64, 0, 1, kStageBytes);
         }
       };
-      fc1_items(0);
-      for (int j = 1; j < nchunk; ++j) {
-        fc1_items(j);
-        fc2_items(j - 1);
+      if (nchunk > 0) {
+        fc1_items(0);
+        for (int i = 1; i < nchunk; ++i) {
+          fc1_items(i);
+          fc2_items(i - 1);
+        }
+        fc2_items(nchunk - 1);
       }
-      fc2_items(nchunk - 1);
       if (lane == 0 && ti == 0) trace(17);
     }
   } else if (warp == 1) {  // ========================================== MMA issuer
@@ -281,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       return s;
     };
     int ti = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+    for (int t = first_tile; t < total_tiles; t += tile_step, ++ti) {
       const uint32_t tpar = uint32_t(ti) & 1u;
       const uint32_t dO = tmem + kAccO;
       // ---- out_proj: accO[128 x 256] = ctx Wo^T (N = 256 MMAs), + x through the identity tiles (N = 32 MMAs).
@@ -407,12 +453,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       };
       // tcgen05.mma executes in issue order: fc1(j + 1) can be issued before fc2(j - 1) has read its operand chunk
       // because it writes the OTHER accumulator, and fc1(j + 2) after fc2(j) reuses that chunk's columns safely
-      issue_fc1(0);
-      for (int j = 1; j < nchunk; ++j) {
-        issue_fc1(j);
-        issue_fc2(j - 1, false);
+      if (nchunk > 0) {
+        issue_fc1(0);
+        for (int i = 1; i < nchunk; ++i) {
+          issue_fc1(i);
+          issue_fc2(i - 1, false);
+        }
+        issue_fc2(nchunk - 1, true);
+      } else {  // a cluster CTA without a hidden chunk (F = 128): its partial sum is the zero it started from
+        if (elect_one()) tc_commit(out_full);
+        __syncwarp();
       }
-      issue_fc2(nchunk - 1, true);
       if (lane == 0 && ti == 0) trace(4);
     }
   } else {  // ========================================================= epilogue warps 2..9
@@ -423,7 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     const int tid = threadIdx.x - 64;
     uint32_t fphase = 0;  // bit b: parity of the next completion of fc1_full[b]
     int ti = 0, cur_g = -1;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+    for (int t = first_tile; t < total_tiles; t += tile_step, ++ti) {
       const uint32_t tpar = uint32_t(ti) & 1u;
       const int g = t / P.tiles_m;
       const int64_t m0 = int64_t(t % P.tiles_m) * BM;
@@ -489,7 +540,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             *reinterpret_cast<uint4*>(kbp + off) = hi;
             *reinterpret_cast<uint4*>(kbp + kTileBytes + off) = lo;
           }
-          add_cols_g(v, Q.b2 + cl);
+          if (rank == 0) {  // fc2 accumulates on top of h + b2 (CTA 1 of a cluster: on top of zero, its sum is added later)
+            add_cols_g(v, Q.b2 + cl);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
           tc_st32(tmem + kAccO + lane_addr + cl, v);
         }
         fence_proxy_async();  // generic-proxy writes of h -> visible to the tensor core's operand reads
@@ -510,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         float va[32], vb[32];
         tc_ld32(ca, va);
         tc_ld32(ca + 32u, vb);
-        const float* bias = Q.b1 + j * 128 + hf * 64;
+        const float* bias = Q.b1 + chunk_of(j) * 128 + hf * 64;
         add_cols_g(va, bias);
         add_cols_g(vb, bias + 32);
         uint32_t whi[32], wlo[32];
@@ -530,12 +586,60 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       mbar_wait(out_full, tpar);
       tc_fence_after();
       if (tid == 0 && ti == 0) trace(7);
+      const uint32_t xbox = uint32_t(warp - 2) * 16384u;  // this warp's 4 partial-sum boxes of 32 rows x 128 B (swizzled) in hA
+      if constexpr (CL > 1) {
+        if (rank == 0) {
+          // all MMAs of this CTA have retired: hA (h, fc1's operand) is idle and the peer may copy its partial sum there
+          if (tid == 0) {
+            mbar_expect_tx(partial_full, kHABytes);  // 8 bulk copies of 16 KB complete it
+            mbar_arrive_remote(map_to_peer(peer_free, 1));
+          }
+          mbar_wait_cluster(partial_full, tpar);
+          if (tid == 0) mbar_arrive_remote(map_to_peer(xfer_done, 1));  // the peer's source boxes have been read
+        } else {
+          // partial sum -> this warp's boxes in the CTA's OWN hA (idle as well), then one bulk copy per warp into the
+          // same place of the peer's hA: scattered 16-byte st.shared::cluster took 16 k cycles for the 128 KB
+          float v[32];
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {
+            tc_ld32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
+            uint8_t* box = sm + xbox + i * 4096;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          mbar_wait_cluster(peer_free, tpar);
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             map_to_peer(hA + xbox, 0)),
+                         "r"(hA + xbox), "r"(16384u), "r"(map_to_peer(partial_full, 0))
+                         : "memory");
+          }
+          mbar_wait_cluster(xfer_done, tpar);  // copies landed => the source boxes were read: hA may take the next ctx
+          tc_fence_before();
+          epi_bar_sync();
+          if (tid == 0) mbar_arrive(tile_done);
+          if (tid == 0 && ti == 0) trace(8);
+          continue;
+        }
+      }
       {
         float v[32];
         float shift = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
           tc_ld32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
+          if constexpr (CL > 1) {  // + the peer's partial sum; the total goes back into accO for the second pass
+            const uint8_t* box = sm + xbox + i * 4096;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 pj = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4));
+              v[4 * j] += pj.x, v[4 * j + 1] += pj.y, v[4 * j + 2] += pj.z, v[4 * j + 3] += pj.w;
+            }
+            tc_st32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
+          }
           if (i == 0) shift = v[0];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -606,6 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still touch its shared memory
   if (tracing) {
     for (int i = threadIdx.x; i < kTraceSlots; i += kThreads) g_trace_blk[i] = (long long)trp[i];
   }
@@ -617,6 +722,17 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
 
 }  // namespace
 
+// 0 = pick by the number of row tiles, 1 | 2 = force the schedule (SCATT_BLOCK_CLUSTER or scatt_debug_set_block_cluster: A/B runs, tests)
+static std::atomic<int> g_block_cluster{[] {
+  const char* e = std::getenv("SCATT_BLOCK_CLUSTER");
+  return e ? std::atoi(e) : 0;
+}()};
+int debug_set_block_cluster(int cl) {
+  SCATT_REQUIRE(cl >= 0 && cl <= 2, "debug_set_block_cluster: 0 (automatic), 1 or 2");
+  g_block_cluster.store(cl, std::memory_order_relaxed);
+  return SCATT_OK;
+}
+
 int debug_set_trace_block(void* dev_buf) {
   long long* p = reinterpret_cast<long long*>(dev_buf);
   SCATT_CUDA(cudaMemcpyToSymbol(g_trace_blk, &p, sizeof(p)));
@@ -626,6 +742,7 @@ int debug_set_trace_block(void* dev_buf) {
 bool attn_block_supported(int64_t M, int D, int F) { return D == DM && F >= 128 && F <= kMaxF && F % 128 == 0 && M >= 1 && M < (int64_t(1) << 31); }
 
 int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D, int F, float eps, int fmt, int terms, cudaStream_t s) {
+  const int cluster_override = g_block_cluster.load(std::memory_order_relaxed);
   SCATT_REQUIRE(terms >= 1 && terms <= 3, "attn_block: terms must be 1, 2 or 3");
   if (M == 0) return SCATT_OK;
   SCATT_REQUIRE(attn_block_supported(M, D, F), "attn_block: needs D = %d and F a multiple of 128 in [128, %d] (got D=%d F=%d)", DM, kMaxF, D, F);
@@ -652,16 +769,27 @@ int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D,
   }
   static PerDeviceFlag attr_done;
   if (!attr_done.load()) {
-    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
-    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
     attr_done.store(true);
   }
   const int tiles = P.tiles_m * group;
-  dim3 grid(unsigned(tiles < 148 ? tiles : 148));
-  if (fmt == SCATT_PLANE_F16) (void)launch_kernel(attn_block_kernel<SCATT_PLANE_F16>, grid, dim3(kThreads), kSmemBytes, s, P);
-  else (void)launch_kernel(attn_block_kernel<SCATT_PLANE_BF16>, grid, dim3(kThreads), kSmemBytes, s, P);
+  // few row tiles (small batches): a 2-CTA cluster per tile, each CTA half of the hidden chunks - twice the SMs share the
+  // weight stream and the fc1 / fc2 MMAs; from 75 tiles on every SM has a tile of its own anyway
+  const int cl = cluster_override > 0 ? cluster_override : ((tiles <= 74 && P.nchunk >= 2) ? 2 : 1);
+  if (cl == 2) {
+    dim3 grid(unsigned(2 * (tiles < 74 ? tiles : 74)));
+    if (fmt == SCATT_PLANE_F16) (void)launch_kernel_cluster(attn_block_kernel<SCATT_PLANE_F16, 2>, grid, dim3(kThreads), kSmemBytes, s, 2, P);
+    else (void)launch_kernel_cluster(attn_block_kernel<SCATT_PLANE_BF16, 2>, grid, dim3(kThreads), kSmemBytes, s, 2, P);
+  } else {
+    dim3 grid(unsigned(tiles < 148 ? tiles : 148));
+    if (fmt == SCATT_PLANE_F16) (void)launch_kernel(attn_block_kernel<SCATT_PLANE_F16, 1>, grid, dim3(kThreads), kSmemBytes, s, P);
+    else (void)launch_kernel(attn_block_kernel<SCATT_PLANE_BF16, 1>, grid, dim3(kThreads), kSmemBytes, s, P);
+  }
   const int rc = after_launch("attn_block_kernel");
-  set_last_kernel("attn_block_kernel<%d>", fmt);
+  set_last_kernel("attn_block_kernel<%d, %d>", fmt, cl);
   return rc;
 }
 

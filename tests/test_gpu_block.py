@@ -54,9 +54,18 @@ def run_block(prec, ctxs, xs, layers, out_f32=True, out_planes=True):
                          [m["ln2"] for m in layers], out_f32=out_f32, out_planes=out_planes)
 
 
+@pytest.fixture(params=[0, 1, 2], ids=["auto", "cta", "cluster2"])
+def schedule(request):
+    """One CTA per row tile, a 2-CTA cluster per row tile (hidden chunks split, partial sums through DSMEM), or the
+    library's own choice."""
+    L.check(L.load().scatt_debug_set_block_cluster(request.param), "set_block_cluster")
+    yield request.param
+    L.check(L.load().scatt_debug_set_block_cluster(0), "set_block_cluster")
+
+
 @pytest.mark.parametrize("mode", list(MODE_TOL))
 @pytest.mark.parametrize("M,Fh,G", [(200, 768, 1), (1600, 768, 3), (333, 256, 2), (77, 128, 1), (129, 384, 1), (128, 1024, 1)])
-def test_attn_block_vs_fp64(mode, M, Fh, G):
+def test_attn_block_vs_fp64(mode, M, Fh, G, schedule):
     prec = F_.get_precision(mode)
     D = 256
     assert L.load().scatt_attn_block_supported(M, D, Fh)
@@ -75,7 +84,7 @@ def test_attn_block_vs_fp64(mode, M, Fh, G):
 
 
 @pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
-def test_attn_block_persistent_many_tiles(mode):
+def test_attn_block_persistent_many_tiles(mode, schedule):
     """More row tiles than SMs: every CTA walks several tiles (barrier phases, ring and TMEM reuse across tiles);
     the group index changes inside a CTA's walk (per-column parameters reloaded)."""
     prec = F_.get_precision(mode)
