@@ -371,9 +371,10 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
 
 FUSED_BLOCK = os.environ.get("SCATT_FUSED_BLOCK", "1") != "0"  # False: out_proj+LN, fc1, fc2+LN as three scatt_linear launches
 # Row tiles (128 rows, all streams of the group) from which the fused layer tail replaces the three GEMM launches.
-# One CTA runs a whole row tile through all three GEMMs, so a handful of tiles leaves most SMs idle where the
-# separate launches spread each GEMM over ~100 CTAs (measured cross-over: profiles/r02_sweep_batch_1gpu.md).
-FUSED_BLOCK_MIN_TILES = int(os.environ.get("SCATT_FUSED_BLOCK_MIN_TILES", "60"))
+# One CTA (a 2-CTA cluster up to 74 tiles) runs a whole row tile through all three GEMMs, so a handful of tiles leaves
+# most SMs idle where the separate launches spread each GEMM over ~100 CTAs.  Measured cross-over at T = 200
+# (profiles/r02_sweep_batch_1gpu.md): B = 4 (21 tiles) -4 %, B = 8 (39 tiles) +0.5..1 %, B = 16 +5 %, B = 24 +8 %.
+FUSED_BLOCK_MIN_TILES = int(os.environ.get("SCATT_FUSED_BLOCK_MIN_TILES", "36"))
 
 
 def attn_block_supported(prec: Precision, M: int, D: int, F: int, group: int = 1) -> bool:
