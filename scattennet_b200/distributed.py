@@ -130,20 +130,33 @@ def gather_logits_peer(local: torch.Tensor, group=None) -> torch.Tensor:
     key = (tuple(local.shape), local.dtype, str(local.device), id(group))
     pg = _peer_gathers.get(key)
     if pg is None:
+        # Agree on feasibility BEFORE the collective set-up (symmetric-memory allocation, rendezvous and barrier block
+        # until every rank takes part): each rank probes locally, the minimum decides, and only then do all ranks
+        # construct - a rank that cannot use peer memory sends everybody down the NCCL route instead of hanging them.
+        can = bool(local.is_cuda and os.environ.get("SCATT_PEER_GATHER", "1") != "0" and world <= 8
+                   and local.numel() * local.element_size() % 16 == 0)
+        if can:
+            try:
+                import importlib
+
+                importlib.import_module("torch.distributed._symmetric_memory")
+            except Exception:
+                can = False
+        ok = torch.tensor([1 if can else 0], device=local.device if local.is_cuda else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
         pg = False
-        if local.is_cuda and os.environ.get("SCATT_PEER_GATHER", "1") != "0":
+        if int(ok.item()) == 1:
             try:
                 pg = PeerGather(local.shape, local.dtype, local.device, group)
-            except Exception as exc:  # symmetric memory is not available here: keep NCCL (said once, on stderr)
+            except Exception as exc:  # set-up failed on this rank (said once, on stderr); the vote below settles the route
                 import sys
 
                 print(f"[scattennet_b200] peer-memory gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
                 pg = False
-        # every rank must take the same route
-        ok = torch.tensor([1 if pg else 0], device=local.device if local.is_cuda else "cpu")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) == 0:
-            pg = False
+            ok = torch.tensor([1 if pg else 0], device=local.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                pg = False
         _peer_gathers[key] = pg
     if pg is False:
         return gather_logits(local, group)
