@@ -62,13 +62,21 @@ def test_graph_replay_equals_eager(golden):
         assert torch.equal(eager[k], first[k]) and torch.equal(eager[k], again[k]), k
 
 
-def test_full_size_properties():
-    """C1-size run (B=8, T=200) checked without a stored answer:
+@pytest.mark.parametrize("min_tiles", [0, 10 ** 9], ids=["fused_tail", "three_launch_tail"])
+def test_full_size_properties(monkeypatch, min_tiles):
+    """The schedule is pinned (the fused layer tail, or the three GEMM launches, at every batch size): which one runs
+    normally depends on the number of row tiles, and bit-for-bit comparisons between a batch and its sub-batch only
+    make sense within one schedule.
+
+    C1-size run (B=8, T=200) checked without a stored answer:
     (1) valid rows do not depend on the content of padded frames (exactly);
     (2) outputs do not depend on the dead shortcut weights (exactly);
     (3) a sequence's outputs do not depend on its batch neighbours (exactly);
     (4) the causal branch is causal: perturbing frame t0 of the y coordinates leaves
         SeparativeCoordinateAttention outputs for frames < t0 unchanged."""
+    from scattennet_b200 import functional as F_
+
+    monkeypatch.setattr(F_, "FUSED_BLOCK_MIN_TILES", min_tiles)
     cfg = model_config("phoenix-2014t")
     B, T = 8, 200
     lengths = synth.parity_lengths(B, T)

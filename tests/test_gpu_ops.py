@@ -410,7 +410,8 @@ def test_frontend_gather_exact_and_embeddings():
     # a non-contiguous, unsorted index list must work too (the API is an arbitrary list)
     idxs[0] = torch.tensor([500, 3, 541, 0, 77, 12], dtype=torch.int32, device=DEV)
     prec = F_.get_precision("fp16x3")
-    s, c, gathered = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T, want_gathered=True)
+    s, c, gathered = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T, want_gathered=True, want_f32=True)
+    s2, c2, _ = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T)  # the hot path's form: split planes only
     for g, m in enumerate(mods):
         idx = idxs[g].cpu().long()
         region = kp[:, :, idx, :]
@@ -422,6 +423,7 @@ def test_frontend_gather_exact_and_embeddings():
         c_ref = O.layer_norm(sd, "m.sca.first_causal_norm", O.position_embed(sd, "m.sca.causal_pos_embed", c_in))
         assert float((s[g].f32.cpu().view(B, T, -1) - s_ref).abs().max()) <= 1e-5
         assert float((c[g].f32.cpu().view(B, T, -1) - c_ref).abs().max()) <= 1e-5
+        assert s2[g].f32 is None and torch.equal(s2[g].planes, s[g].planes) and torch.equal(c2[g].planes, c[g].planes)
     with pytest.raises(IndexError):
         big, _ = synth.synth_batch(1, 257, seed=2)
         frontend_forward(prec, mods, big.to(DEV), idxs, 1, 257)

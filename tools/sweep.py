@@ -134,7 +134,7 @@ def membound_sweep(args):
             else:
                 idx = model._joint_idx(torch.device(dev))
             kp = kp.to(dev).contiguous()
-            nbytes = B * T * (48 * 8 + 6 * 256 * 8)  # 384 B of used joints in, 6 branches x 256 x (fp32 + 2 planes) out
+            nbytes = B * T * (48 * 8 + 6 * 256 * 4)  # 384 B of used joints in, 6 branches x 256 x (hi + lo plane) out
             row("frontend_kernel" + (" (compact input)" if compact else ""), f"B={B} T={T} K={kp.shape[2]}", nbytes,
                 lambda: frontend_forward(prec, mods, kp, idx, B, T))
             del kp
