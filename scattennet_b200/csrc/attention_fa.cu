@@ -297,6 +297,9 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
     const int i = m0 + r;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     const int jmax = causal ? i : 0x7fffffff;
+    // a warp whose 32 rows all lie past Tq (the second query tile of T = 200 holds 72 rows: 1.75 of its 4 quadrants are
+    // dead) only takes part in the hand-shakes: its issue slots and MUFU cycles go to the SM's other resident CTA
+    const bool live = m0 + quad * 32 < Tq;
     const uint32_t* chunk_valid = reinterpret_cast<const uint32_t*>(sm + L.flag);
     float* xch = reinterpret_cast<float*>(sm + L.xch);
     uint32_t s_uses = 0;  // completed phases of bar_s
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       mbar_wait(bar_s, s_uses++ & 1);
       if (threadIdx.x == 0 && blk == 0) trace(4);
       tc_fence_after();
-      const int nch = (min(kbox, nk - blk * kbox) + 31) >> 5;  // chunks holding a key this tile may see
+      const int nch = live ? (min(kbox, nk - blk * kbox) + 31) >> 5 : 0;  // chunks holding a key this tile may see
 #pragma unroll 1
       for (int c = half; c < nch; c += 2) {
         tc_ld32(tmem_s + lane_addr + c * 32, v);
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
 #pragma unroll 1
       for (int it = 0; it < niter; ++it) {
         const int c = 2 * it + half;
-        if (c < nch) {
+        if (c < nch && live) {
           tc_ld32(tmem_s + lane_addr + c * 32, v);
           const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
           const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
