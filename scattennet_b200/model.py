@@ -257,10 +257,17 @@ class MSCAEncoder(nn.Module):
         torch.index_select(keypoints, 2, used, out=slot["kp_pin"])  # exact gather on the host
         slot["mask_pin"].copy_(mask != 0)
         try:
-            if self.use_graph and not gather and decode_beam <= 0 and HOST_GRAPH:
+            if self.use_graph and decode_beam <= 0 and HOST_GRAPH and (not gather or gather_to_host == "shard"):
                 # the whole step - both H2D copies, the encoder, the D2H copies of the requested heads - is ONE
-                # captured graph: a single launch instead of eight stream operations with the host in between
-                return self._host_graph_step(st, slot, heads, dev)
+                # captured graph: a single launch instead of eight stream operations with the host in between.
+                # Sharded jobs add one launch behind it: the NVLink push of this rank's logits (the read-back of the own
+                # shard is already inside the graph and overlaps it).
+                res, out_dev = self._host_graph_step(st, slot, heads, dev)
+                if gather:
+                    from .distributed import gather_logits_peer
+
+                    res[heads[0] + "/gathered_dev"] = gather_logits_peer(out_dev[heads[0]])
+                return res
             st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
             st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
             out = self.forward(st["kp_dev"], st["mask_dev"], compact=True)
@@ -331,9 +338,9 @@ class MSCAEncoder(nn.Module):
             if pool is None:
                 st["pool"] = graph.pool()
             ent = slot[key] = (graph, pins, out)
-        graph, pins, _ = ent
+        graph, pins, out = ent
         graph.replay()
-        return dict(pins)
+        return dict(pins), out
 
     # ------------------------------------------------------------------ CUDA graph replay
     def _run_graph(self, keypoints, mask, with_heads, compact=False):
