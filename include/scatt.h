@@ -267,6 +267,14 @@ int scatt_attention_planes(const scatt_attention_planes_problem* problems_host, 
 int scatt_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out,
                            void* out_planes, int plane_fmt, void* stream);
 
+/* Same contraction on the tensor cores (tcgen05): q / k / v are the split planes [2][B*T][D] written by the
+ * left_se / right_se / body_se GEMMs (`scatt_linear` with y_planes, GELU applied), `terms` product terms as in
+ * scatt_linear.  Requires T <= 256 and D a multiple of 256 (`scatt_fusion_attention_planes_supported`); longer
+ * sequences use scatt_fusion_attention. */
+int scatt_fusion_attention_planes_supported(int T, int D);
+int scatt_fusion_attention_planes(const void* q_planes, const void* k_planes, const void* v_planes, int B, int T, int D,
+                                  float* out, void* out_planes, int plane_fmt, int terms, void* stream);
+
 /* ------------------------------------------------------------------ K4: temporal pooling */
 
 /* MaxPool1d(2,2) over time of x[B,T,C] -> y[B,floor(T/2),C] (model/residual.py:40-43),

@@ -21,7 +21,10 @@ PARITY UNPINNED against TensorFlow itself (it cannot be run here, and the refere
 vectors for this path).  What pins this file instead (``tests/test_oracle_ctc.py``):
   * with a beam wide enough to hold every prefix, prefix beam search is exact: its best labelling and
     score must equal a brute-force enumeration of all alignments (known-answer check of the recursion);
-  * hand-computed 2-step cases; invariance of the result under the reference's rotation + ``+1``.
+  * hand-computed 2-step cases; invariance of the result under the reference's rotation + ``+1``;
+  * the input of TensorFlow's own op test (``ctc_decoder_ops_test.py::testCTCDecoderBeamSearch``: 5 x 6 probability
+    matrix, beam_width 2, top_paths 2) with the two decoded label sequences that test expects - REPRODUCED FROM
+    MEMORY (the file cannot be fetched offline), labels only, so it is supporting evidence, not a pin.
 """
 
 from __future__ import annotations
@@ -76,6 +79,11 @@ class _Entry:
 def beam_search(logits: np.ndarray, beam_width: int) -> Tuple[List[int], float]:
     """``logits [T, V]`` (raw, un-normalised; blank = class V-1, TensorFlow's convention) ->
     ``(best labelling, its log-probability)``.  One call = one batch element over its own length."""
+    return beam_search_top_paths(logits, beam_width, 1)[0]
+
+
+def beam_search_top_paths(logits: np.ndarray, beam_width: int, top_paths: int) -> List[Tuple[List[int], float]]:
+    """Same search, ``TopPaths(n)``: the ``n`` best leaves in descending total probability."""
     t_len, v = logits.shape
     blank = v - 1
     root = _Entry(None, -1)
@@ -127,8 +135,8 @@ def beam_search(logits: np.ndarray, beam_width: int) -> Tuple[List[int], float]:
                 else:
                     c.oldp = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
                     c.newp = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
-    best = max(leaves, key=lambda e: e.newp[0])
-    return best.labels(), best.newp[0]
+    ranked = sorted(leaves, key=lambda e: -e.newp[0])  # stable, like the single-best max() over the same order
+    return [(e.labels(), e.newp[0]) for e in ranked[:top_paths]]
 
 
 def ctc_decode(gloss_logits: np.ndarray, beam_size: int, input_lengths: Sequence[int]) -> List[List[int]]:

@@ -28,8 +28,8 @@ SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
     "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
-    "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_pool_pairs",
-    "scatt_pool_pairs_group",
+    "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_fusion_attention_planes",
+    "scatt_fusion_attention_planes_supported", "scatt_pool_pairs", "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
     "scatt_ctc_beam_decode", "scatt_peer_allgather",
 )
@@ -115,6 +115,10 @@ def _declare(lib):
     lib.scatt_attention_planes.argtypes = [C.POINTER(AttentionPlanesProblem), i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     lib.scatt_attention_planes.restype = i32
     lib.scatt_fusion_attention.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]
+    lib.scatt_fusion_attention_planes.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, vp]
+    lib.scatt_fusion_attention_planes.restype = i32
+    lib.scatt_fusion_attention_planes_supported.argtypes = [i32, i32]
+    lib.scatt_fusion_attention_planes_supported.restype = i32
     lib.scatt_pool_pairs.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp]
     lib.scatt_pool_pairs_group.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i32, i32, i32, i32, i32, vp]
     lib.scatt_pool_pairs_group.restype = i32

@@ -157,6 +157,15 @@ int scatt_fusion_attention(const float* q, const float* k, const float* v, int B
   return launch_fusion_attention(q, k, v, B, T, D, out, out_planes, plane_fmt, as_stream(stream));
 }
 
+int scatt_fusion_attention_planes_supported(int T, int D) { return fusion_attention_tc_supported(T, D) ? 1 : 0; }
+
+int scatt_fusion_attention_planes(const void* q_planes, const void* k_planes, const void* v_planes, int B, int T, int D,
+                                  float* out, void* out_planes, int plane_fmt, int terms, void* stream) {
+  SCATT_REQUIRE(q_planes && k_planes && v_planes && (out || out_planes) && fmt_ok(plane_fmt) && B >= 0,
+                "fusion_attention_planes: bad argument");
+  return launch_fusion_attention_tc(q_planes, k_planes, v_planes, B, T, D, out, out_planes, plane_fmt, terms, as_stream(stream));
+}
+
 int scatt_pool_pairs(const float* x, int B, int T, int C, float* y, void* y_planes, int plane_fmt, void* stream) {
   SCATT_REQUIRE(x && (y || y_planes) && fmt_ok(plane_fmt), "pool_pairs: bad argument");
   return launch_pool_pairs(x, B, T, C, y, y_planes, plane_fmt, as_stream(stream));

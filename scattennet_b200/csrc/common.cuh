@@ -242,6 +242,9 @@ int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths
 int launch_finite_check(const float* const* tensors, const int64_t* sizes, int count, int* flags, cudaStream_t s);
 int launch_peer_allgather(const void* src, int64_t bytes, void* const* peer_bufs, void* const* peer_flags, int world, int rank,
                           void* counter, uint64_t seq, cudaStream_t s);
+bool fusion_attention_tc_supported(int T, int D);
+int launch_fusion_attention_tc(const void* q_planes, const void* k_planes, const void* v_planes, int B, int T, int D, float* out,
+                               void* out_planes, int fmt, int terms, cudaStream_t s);
 int launch_fusion_attention(const float* q, const float* k, const float* v, int B, int T, int D, float* out, void* planes,
                             int fmt, cudaStream_t s);
 

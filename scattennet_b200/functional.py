@@ -479,6 +479,22 @@ def fusion_attention(prec: Precision, q: torch.Tensor, k: torch.Tensor, v: torch
     return Act(o, op)
 
 
+def fusion_attention_planes_supported(prec: Precision, T: int, D: int) -> bool:
+    return prec.uses_planes and bool(L.load().scatt_fusion_attention_planes_supported(T, D))
+
+
+def fusion_attention_planes(prec: Precision, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, T: int,
+                            out_f32: bool = False) -> Act:
+    """Fusion attention on the tensor cores; ``q / k / v`` are split planes ``[2, B*T, D]`` (outputs of the squeeze GEMMs)."""
+    D = q.shape[2]
+    o = torch.empty(B * T, D, dtype=torch.float32, device=q.device) if out_f32 else None
+    op = torch.empty(2, B * T, D, dtype=prec.plane_dtype, device=q.device)
+    with _timed("fusion_attention_tc_kernel", 4.0 * B * T * T * D, 4.0 * B * T * D * 4):
+        L.check(L.load().scatt_fusion_attention_planes(q.data_ptr(), k.data_ptr(), v.data_ptr(), B, T, D, _ptr(o), op.data_ptr(),
+                                                       prec.plane_fmt, max(prec.terms, 1), _stream()), "scatt_fusion_attention_planes")
+    return Act(o, op)
+
+
 def pool_pairs(prec: Precision, x: torch.Tensor, B: int, T: int) -> Act:
     Cc = x.shape[1]
     if T < 2:

@@ -67,11 +67,16 @@ class CoordinatesFusion(nn.Module):
 
 def coordinates_fusion_forward(prec: Precision, m: CoordinatesFusion, left: Act, right: Act, body: Act, B: int, T: int,
                                out_planes: bool = False) -> Act:
-    se = F_.linear(prec, [left, right, body],
-                   [F_.pack_of(m, "left_se", [m.left_se]), F_.pack_of(m, "right_se", [m.right_se]),
-                    F_.pack_of(m, "body_se", [m.body_se])],
-                   F_.make_epilogue(act_pre=L.ACT_GELU), out_planes=False)
-    l, r, bd = (s.f32 for s in se)
-    a = F_.fusion_attention(prec, r, l, bd, B, T)
+    packs = [F_.pack_of(m, "left_se", [m.left_se]), F_.pack_of(m, "right_se", [m.right_se]),
+             F_.pack_of(m, "body_se", [m.body_se])]
+    if F_.fusion_attention_planes_supported(prec, T, m.out_proj.in_features):
+        # tensor-core contraction: the squeeze GEMMs write the split planes the attention kernel's TMA loads consume
+        se = F_.linear(prec, [left, right, body], packs, F_.make_epilogue(act_pre=L.ACT_GELU), out_f32=False, out_planes=True)
+        l, r, bd = (s.planes for s in se)
+        a = F_.fusion_attention_planes(prec, r, l, bd, B, T)
+    else:
+        se = F_.linear(prec, [left, right, body], packs, F_.make_epilogue(act_pre=L.ACT_GELU), out_planes=False)
+        l, r, bd = (s.f32 for s in se)
+        a = F_.fusion_attention(prec, r, l, bd, B, T)
     f = F_.linear(prec, [a], [F_.pack_of(m, "out_proj", [m.out_proj])], F_.make_epilogue(layer_norm=True), lns=[m.norm])[0]
     return inverted_residual_forward(prec, m.inverted_res, f, out_planes)

@@ -368,6 +368,50 @@ def test_fusion_attention(B, T, D):
     assert float((out.double().cpu() - ref).abs().max()) <= 2e-4
 
 
+FUSION_TOL = {"fp16x3": 1e-4, "bf16x3": 1e-3, "fp16x1": 0.25}
+
+
+def _fusion_planes_case(mode, B, T, D, out_f32=False):
+    prec = F_.get_precision(mode)
+    acts = [F_.Act.from_f32(rnd(B * T, D, seed=s, scale=0.6).abs()).with_planes(prec) for s in (1, 2, 3)]
+    q, k, v = (a.planes for a in acts)
+    out = F_.fusion_attention_planes(prec, q, k, v, B, T, out_f32=out_f32)
+    # the kernel sees exactly hi + lo: compare against the fp64 contraction of the reconstructed operands
+    qd, kd, vd = ((p[0].double() + p[1].double()).cpu().view(B, T, D) for p in (q, k, v))
+    ref = (torch.softmax(qd @ kd.transpose(1, 2), -1) @ vd).reshape(B * T, D)
+    rec = (out.planes[0].double() + out.planes[1].double()).cpu()
+    assert torch.isfinite(rec).all()
+    err = float((rec - ref).abs().max())
+    if out_f32:
+        assert float((out.f32.double().cpu() - ref).abs().max()) <= FUSION_TOL[mode]
+    return err
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
+@pytest.mark.parametrize("B,T,D", [(2, 7, 1024), (8, 50, 1024), (2, 200, 1024), (3, 37, 512), (1, 256, 1024), (2, 129, 1024),
+                                   (1, 64, 256), (160, 50, 1024), (80, 130, 1024)])
+def test_fusion_attention_planes(mode, B, T, D):
+    """tcgen05 fusion attention (logits ~ 200, no scaling) against fp64; the last two shapes take the
+    all-slices-in-one-CTA schedule."""
+    assert F_.fusion_attention_planes_supported(F_.get_precision(mode), T, D)
+    assert _fusion_planes_case(mode, B, T, D, out_f32=(B == 2)) <= FUSION_TOL[mode]
+
+
+@pytest.mark.parametrize("ncols,spc", [(64, 1), (64, 4), (128, 1), (128, 2), (128, 8), (256, 1), (256, 2), (256, 4)])
+def test_fusion_attention_planes_schedules(ncols, spc, monkeypatch):
+    """Every (slice width, slices per CTA) schedule gives the same result (the launcher reads the override per launch)."""
+    monkeypatch.setenv("SCATT_FUSION_NCOLS", str(ncols))
+    monkeypatch.setenv("SCATT_FUSION_SPC", str(spc))
+    for B, T in ((3, 50), (2, 200), (2, 100)):
+        assert _fusion_planes_case("fp16x3", B, T, 1024) <= FUSION_TOL["fp16x3"]
+
+
+def test_fusion_attention_planes_rejects_long_sequences():
+    prec = F_.get_precision("fp16x3")
+    assert not F_.fusion_attention_planes_supported(prec, 257, 1024)
+    assert not F_.fusion_attention_planes_supported(F_.get_precision("fp32"), 50, 1024)
+
+
 @pytest.mark.parametrize("B,T,C", [(2, 21, 256), (8, 200, 256), (3, 5, 512), (1, 2, 512)])
 def test_pool_pairs_exact(B, T, C):
     prec = F_.get_precision("fp16x3")

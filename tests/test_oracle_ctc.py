@@ -61,3 +61,20 @@ def test_ctc_decode_wrapper_matches_reference_post_processing():
     peaked = np.full((1, 3, 3), -9.0, dtype=np.float32)
     peaked[0, 0, 2] = peaked[0, 1, 0] = peaked[0, 2, 2] = 9.0
     assert C.ctc_decode(peaked, 5, [3]) == [[2]]
+
+
+def test_tensorflow_op_test_vector_labels():
+    """Input and expected decodes of TensorFlow's ``ctc_decoder_ops_test.py::testCTCDecoderBeamSearch`` (depth 6, blank = 5,
+    sequence length 5, beam_width = 2, top_paths = 2, merge_repeated = False): beam 0 decodes to [1, 0], beam 1 to
+    [0, 1, 0].  The vector is written down FROM MEMORY of the public test (no network, no TensorFlow here), and only its label
+    sequences are asserted - weak evidence next to a TensorFlow-produced fixture, which is why DESIGN.md keeps the decode
+    'parity unpinned'."""
+    p = np.asarray([[0.30999, 0.309938, 0.0679938, 0.0673362, 0.0708352, 0.173908],
+                    [0.215136, 0.439699, 0.0370931, 0.0393967, 0.0381581, 0.230517],
+                    [0.199959, 0.489485, 0.0233221, 0.0251417, 0.0233289, 0.238763],
+                    [0.279611, 0.452966, 0.0204795, 0.0209126, 0.0194803, 0.20655],
+                    [0.51286, 0.288951, 0.0243026, 0.0220788, 0.0219297, 0.129878]], dtype=np.float32)
+    logits = np.log(p) + 2.0  # "arbitrary offset - this is fine": the search normalises every frame
+    (lab0, lp0), (lab1, lp1) = C.beam_search_top_paths(logits, beam_width=2, top_paths=2)
+    assert lab0 == [1, 0] and lab1 == [0, 1, 0]
+    assert lp0 > lp1

@@ -107,6 +107,35 @@ def kernel_sweep(args):
                 print(f"| {M} | {N} | {K} | {name} | {mode} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {by / us / 1e3:.0f} |", flush=True)
                 del xs, packs, res
 
+def fusion_sweep(args):
+    """K5 fusion attention (single head, D = 1024, no scaling): fp32 CUDA-core kernel vs the tcgen05 kernel, T' = the pooled
+    length the encoder hands to the fusion block (T / 4 for phoenix-2014t, T / 2 for phoenix-2014)."""
+    D = 1024
+    gen = torch.Generator().manual_seed(0)
+    scheds = [("", "")] + ([tuple(x.split(":")) for x in args.schedules.split(",")] if args.schedules else [])
+    print("### fusion attention softmax(q k^T) v, D = 1024 (us per launch, back-to-back in a CUDA graph)\n")
+    print("| T' | B | engine | schedule (ncols:spc) | us | TFLOP/s (4 B T'^2 D) | % bf16 peak |")
+    print("|---|---|---|---|---|---|---|")
+    for T, B in ((50, 8), (100, 8), (200, 8), (256, 8), (16, 256), (50, 256), (64, 200), (100, 128), (128, 100), (200, 64), (256, 50)):
+        q, k, v = (torch.randn(B * T, D, generator=gen).abs().mul_(0.6).to(dev) for _ in range(3))
+        fl = 4.0 * B * T * T * D
+        p32 = F_.get_precision("fp32")
+        us = graph_time(lambda: F_.fusion_attention(p32, q, k, v, B, T))
+        print(f"| {T} | {B} | fp32 cuda-core | - | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} |", flush=True)
+        for mode in ("fp16x3", "fp16x1"):
+            prec = F_.get_precision(mode)
+            pl = [F_.split_planes(t, prec) for t in (q, k, v)]
+            for nc, spc in scheds:
+                if mode == "fp16x1" and nc:
+                    continue
+                for kk, vv in (("SCATT_FUSION_NCOLS", nc), ("SCATT_FUSION_SPC", spc)):
+                    if vv: os.environ[kk] = vv
+                    else: os.environ.pop(kk, None)
+                us = graph_time(lambda: F_.fusion_attention_planes(prec, pl[0], pl[1], pl[2], B, T))
+                print(f"| {T} | {B} | {mode} tcgen05 | {nc + ':' + spc if nc else 'default'} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} |", flush=True)
+        os.environ.pop("SCATT_FUSION_NCOLS", None); os.environ.pop("SCATT_FUSION_SPC", None)
+
+
 def membound_sweep(args):
     """K1 front end, K4 temporal pool, the row-wise LayerNorm tail and the CTC log-softmax front against the
     measured HBM copy bandwidth.  Buffers are larger than the 126 MB L2 at the big sizes; every launch is timed
@@ -159,11 +188,12 @@ def membound_sweep(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["batch", "kernels", "membound"])
+    ap.add_argument("what", choices=["batch", "kernels", "membound", "fusion"])
     ap.add_argument("--precision", default="fp16x3,fp16x1")
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024")
     ap.add_argument("--T", type=int, default=200)
     ap.add_argument("--config", default="phoenix-2014t")
     ap.add_argument("--only", default="", help="kernels: 'linear' skips the attention section")
+    ap.add_argument("--schedules", default="", help="fusion: extra ncols:spc overrides, e.g. 128:1,256:1,256:4")
     a = ap.parse_args()
-    {"batch": batch_sweep, "kernels": kernel_sweep, "membound": membound_sweep}[a.what](a)
+    {"batch": batch_sweep, "kernels": kernel_sweep, "membound": membound_sweep, "fusion": fusion_sweep}[a.what](a)
