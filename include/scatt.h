@@ -164,6 +164,16 @@ int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M
                  int64_t ldres, int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms,
                  void* stream);
 
+/* scatt_linear with a caller-owned scratch buffer.  Launches over few row tiles with a long K loop (the fusion block of
+ * model/fusion.py at small batches: M = B*T' rows, K = 1024 / 3072) are split along K when the scratch is given: S
+ * slices run as S problem slots of one GEMM launch that writes fp32 partial sums into `workspace`, and a row-wise
+ * kernel adds them in slot order and applies the epilogue.  scatt_linear_workspace_bytes returns the bytes such a
+ * launch wants (0: the launch is not split; any buffer, or none, may be passed). */
+size_t scatt_linear_workspace_bytes(int group, int64_t M, int N, int K, int engine);
+int scatt_linear_ws(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx,
+                    int64_t ldres, int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt,
+                    int terms, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ K2b: fused row-local layer tail
  *
  * y = LayerNorm2(h + fc2(GELU(fc1(h)))),  h = LayerNorm1(x + ctx Wo^T + bo)

@@ -27,7 +27,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
-    "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
+    "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_fusion_attention_planes",
     "scatt_fusion_attention_planes_supported", "scatt_pool_pairs", "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
@@ -101,6 +101,11 @@ def _declare(lib):
     lib.scatt_posembed_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.scatt_linear.argtypes = [C.POINTER(LinearProblem), i32, i64, i32, i32, i64, i64, i64, C.POINTER(Epilogue), i32, i32,
                                  i32, vp]
+    lib.scatt_linear_ws.argtypes = [C.POINTER(LinearProblem), i32, i64, i32, i32, i64, i64, i64, C.POINTER(Epilogue), i32, i32,
+                                    i32, vp, C.c_size_t, vp]
+    lib.scatt_linear_ws.restype = i32
+    lib.scatt_linear_workspace_bytes.argtypes = [i32, i64, i32, i32, i32]
+    lib.scatt_linear_workspace_bytes.restype = C.c_size_t
     lib.scatt_attn_block.argtypes = [C.POINTER(BlockProblem), i32, i64, i32, i32, f32, i32, i32, vp]
     lib.scatt_attn_block.restype = i32
     lib.scatt_attn_block_supported.argtypes = [i64, i32, i32]

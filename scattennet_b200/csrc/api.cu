@@ -94,15 +94,26 @@ int scatt_posembed_layernorm(const float* x, const float* table, const float* ln
   return launch_posembed_ln(x, table, ln_g, ln_b, out, out_planes, B, T, D, plane_fmt, as_stream(stream));
 }
 
+size_t scatt_linear_workspace_bytes(int group, int64_t M, int N, int K, int engine) {
+  return (engine == SCATT_ENGINE_TCGEN05 && M >= 0 && N >= 1 && K >= 1) ? linear_tc_workspace_bytes(M, N, K, group) : 0;
+}
+
 int scatt_linear(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
                  int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms, void* stream) {
+  return scatt_linear_ws(problems_host, group, M, N, K, ldx, ldres, ldy, epilogue_host, engine, plane_fmt, terms, nullptr, 0, stream);
+}
+
+int scatt_linear_ws(const scatt_linear_problem* problems_host, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
+                    int64_t ldy, const scatt_epilogue* epilogue_host, int engine, int plane_fmt, int terms, void* workspace,
+                    size_t workspace_bytes, void* stream) {
   SCATT_REQUIRE(problems_host && epilogue_host && fmt_ok(plane_fmt), "linear: null pointer or bad plane format");
   SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "linear: group must be 1..%d", SCATT_MAX_GROUP);
   SCATT_REQUIRE(M >= 0 && N >= 1 && K >= 1, "linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
   if (engine == SCATT_ENGINE_SIMT)
     return launch_linear_simt(problems_host, group, M, N, K, ldx, ldres, ldy, *epilogue_host, plane_fmt, as_stream(stream));
   if (engine == SCATT_ENGINE_TCGEN05)
-    return launch_linear_tc(problems_host, group, M, N, K, ldres, ldy, *epilogue_host, plane_fmt, terms, as_stream(stream));
+    return launch_linear_tc(problems_host, group, M, N, K, ldres, ldy, *epilogue_host, plane_fmt, terms, workspace, workspace_bytes,
+                            as_stream(stream));
   set_error("linear: unknown engine %d", engine);
   return SCATT_ERR_INVALID;
 }

@@ -214,7 +214,11 @@ int launch_pool_pairs_group(const float* const* xs, float* const* ys, void* cons
 int launch_linear_simt(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldx, int64_t ldres,
                        int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s);
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
-                     const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s);
+                     const scatt_epilogue& ep, int fmt, int terms, void* workspace, size_t workspace_bytes, cudaStream_t s);
+int linear_tc_splitk(int64_t M, int N, int K, int group);
+size_t linear_tc_workspace_bytes(int64_t M, int N, int K, int group);
+int launch_rowwise_splitk(const float* partials, int nsplit, const scatt_linear_problem& p, int64_t M, int N, int64_t ldres,
+                          int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s);
 int linear_tc_ln_cluster(int64_t M, int N, int group, int layer_norm);
 bool attn_block_supported(int64_t M, int D, int F);
 int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D, int F, float eps, int fmt, int terms,

@@ -412,8 +412,10 @@ int launch_fusion_attention_tc(const void* q_planes, const void* k_planes, const
   P.tkp = (T + 15) & ~15;
   const int npq = terms >= 2 ? 2 : 1, npk = terms >= 3 ? 2 : 1;
   const int qtiles = (T + kFuQT - 1) / kFuQT;
-  // slices: all of a row's columns in one CTA (no recomputed S) once the (batch, tile) pairs alone fill the GPU;
-  // otherwise one slice per CTA, 256 columns wide (128 for the smallest grids)
+  // Schedule.  A CTA computes S once and then `spc` column slices of O against it; CTAs of the same (batch, tile) pair
+  // recompute S (Q and K come out of L2).  Cost model from profiles/r02_sweep_fusion.md: waves x (1 + 0.3 spc) with
+  // waves = ceil(pairs x slices / spc / 148) - few pairs: one slice per CTA (narrow slices for the smallest grids),
+  // many pairs: all of a row's columns in one CTA.
   const int env_ncols = [] { const char* e = std::getenv("SCATT_FUSION_NCOLS"); return e ? std::atoi(e) : 0; }();  // read per launch: tests / sweeps override the schedule
   const int env_spc = [] { const char* e = std::getenv("SCATT_FUSION_SPC"); return e ? std::atoi(e) : 0; }();
   const int pairs = B * qtiles;
@@ -421,7 +423,16 @@ int launch_fusion_attention_tc(const void* q_planes, const void* k_planes, const
   if (pairs * (D / 256) < 96) P.ncols = 128;
   if (env_ncols == 64 || env_ncols == 128 || env_ncols == 256) P.ncols = env_ncols;
   const int nslices = D / P.ncols;
-  P.spc = pairs >= 148 ? nslices : 1;
+  P.spc = 1;
+  {
+    float best = 1e30f;
+    for (int spc = 1; spc <= nslices; spc *= 2) {
+      if (nslices % spc) continue;
+      const int ctas = pairs * (nslices / spc);
+      const float cost = float((ctas + 147) / 148) * (1.0f + 0.3f * float(spc) * float(P.ncols) / 256.0f);
+      if (cost < best) best = cost, P.spc = spc;
+    }
+  }
   if (env_spc >= 1 && nslices % env_spc == 0) P.spc = env_spc;
   const uint32_t ring_budget = kFuSmemBudget - 1024u - kFuCtrlBytes - kFuSlackBytes;
   const uint32_t v_bytes = uint32_t(npk) * uint32_t(P.ncols >> 6) * 8192u;

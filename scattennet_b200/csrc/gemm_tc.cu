@@ -41,6 +41,7 @@
 // SCATT_PERSIST, SCATT_PERSIST_WIDE (all default to 1).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -94,6 +95,7 @@ struct alignas(64) TcParams {
   scatt_epilogue ep;
   int64_t M, ldres, ldy;
   int32_t N, K, stages, terms, fmt, fused_ln, pre_init, res_staged, res_in_ring, res_planes, groups;
+  int32_t kb0[SCATT_MAX_GROUP];  // split-K launches: first 64-element k-block of problem slot g (K is then the slot's share)
 };
 
 // Optional phase trace (dev tool, tools/trace_linear.py): when set, CTA (0,0,0)
@@ -592,10 +594,11 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
       const uint32_t st = base + s * kStageBytes;
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), tx);
-        tma_load_3d(st, &P.map_a[g], full_bar(s), kb * BK, int(m0), 0);
-        if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kb * BK, int(m0), 1);
-        tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kb * BK, nb, 0);
-        if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kb * BK, nb, 1);
+        const int kc = (P.kb0[g] + kb) * BK;
+        tma_load_3d(st, &P.map_a[g], full_bar(s), kc, int(m0), 0);
+        if (need_a_lo) tma_load_3d(st + kABytes, &P.map_a[g], full_bar(s), kc, int(m0), 1);
+        tma_load_3d(st + kBOff, &P.map_b[g], full_bar(s), kc, nb, 0);
+        if (need_b_lo) tma_load_3d(st + kBOff + kBBytes, &P.map_b[g], full_bar(s), kc, nb, 1);
       }
       __syncwarp();
       if (it == 0 && lane == 0) trace(2);
@@ -1165,8 +1168,57 @@ int linear_tc_ln_cluster(int64_t M, int N, int group, int layer_norm) {
   return 0;
 }
 
+// Split-K plan.  A GEMM over few row tiles with a long K loop (the fusion block at small batches: M = B T' = 400 rows,
+// K = 1024 / 3072) leaves most SMs idle while each CTA walks 16 - 48 k-blocks.  K is cut into S slices that run as S
+// problem slots of ONE plain GEMM launch (same operands, k-block offset per slot, fp32 partial sums into a caller
+// workspace); the row-wise reduce kernel adds them in slot order and runs the whole epilogue (bias, activation,
+// residual, LayerNorm, planes).  Returns S, or 1 when the launch stays as it is.
+int linear_tc_splitk(int64_t M, int N, int K, int group) {
+  static const bool off = [] { const char* e = std::getenv("SCATT_SPLITK"); return e && e[0] == '0'; }();
+  if (off || group != 1 || N > 1024 || N % 128 != 0 || K < 1024 || K % BK != 0 || M < 1) return 1;
+  const int64_t tiles = int64_t(N / 128) * ((M + BM - 1) / BM);
+  const int num_kb = K / BK;
+  for (int S = SCATT_MAX_GROUP; S >= 3; --S)
+    if (num_kb % S == 0 && tiles * S <= 148 && num_kb / S >= 4) return S;
+  return 1;
+}
+
+size_t linear_tc_workspace_bytes(int64_t M, int N, int K, int group) {
+  const int S = linear_tc_splitk(M, N, K, group);
+  return S > 1 ? size_t(S) * size_t(M) * size_t(N) * sizeof(float) : 0;
+}
+
+static int launch_linear_tc_impl(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
+                                 const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s, int Kmap, const int* kb0);
+
 int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
-                     const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s) {
+                     const scatt_epilogue& ep, int fmt, int terms, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const int S = linear_tc_splitk(M, N, K, group);
+  if (S > 1 && workspace && workspace_bytes >= linear_tc_workspace_bytes(M, N, K, group)) {
+    SCATT_REQUIRE(p[0].x_planes && p[0].w_planes && (p[0].y || p[0].y_planes), "linear(tcgen05): problem 0 lacks split planes or an output");
+    SCATT_REQUIRE(!ep.layer_norm || (p[0].ln_g && p[0].ln_b), "linear(tcgen05): LayerNorm needs gamma and beta");
+    SCATT_REQUIRE(ep.residual_mode == SCATT_RES_NONE || p[0].residual || p[0].residual_planes, "linear(tcgen05): residual missing");
+    scatt_linear_problem sp[SCATT_MAX_GROUP] = {};
+    int kb0[SCATT_MAX_GROUP] = {};
+    for (int i = 0; i < S; ++i) {
+      sp[i].x_planes = p[0].x_planes, sp[i].w_planes = p[0].w_planes;
+      sp[i].y = reinterpret_cast<float*>(workspace) + size_t(i) * size_t(M) * size_t(N);
+      kb0[i] = i * (K / BK / S);
+    }
+    const scatt_epilogue plain{};
+    const int rc = launch_linear_tc_impl(sp, S, M, N, K / S, N, N, plain, fmt, terms, s, K, kb0);
+    if (rc != SCATT_OK) return rc;
+    char gemm_symbol[128];
+    snprintf(gemm_symbol, sizeof(gemm_symbol), "%s", scatt_last_kernel());
+    const int rc2 = launch_rowwise_splitk(reinterpret_cast<const float*>(workspace), S, p[0], M, N, ldres, ldy, ep, fmt, s);
+    set_last_kernel("%s", gemm_symbol);  // the call's algorithmic flops belong to the GEMM (bench.py keys them by this symbol)
+    return rc2;
+  }
+  return launch_linear_tc_impl(p, group, M, N, K, ldres, ldy, ep, fmt, terms, s, K, nullptr);
+}
+
+static int launch_linear_tc_impl(const scatt_linear_problem* p, int group, int64_t M, int N, int K, int64_t ldres, int64_t ldy,
+                                 const scatt_epilogue& ep, int fmt, int terms, cudaStream_t s, int Kmap, const int* kb0) {
   SCATT_REQUIRE(terms >= 1 && terms <= 3, "linear(tcgen05): terms must be 1, 2 or 3");
   SCATT_REQUIRE(K % 8 == 0 && N % 32 == 0, "linear(tcgen05): K=%d must be a multiple of 8 and N=%d of 32", K, N);
   SCATT_REQUIRE(ep.scale_cols % 32 == 0, "linear(tcgen05): scale_cols must be a multiple of 32");
@@ -1235,9 +1287,10 @@ int launch_linear_tc(const scatt_linear_problem* p, int group, int64_t M, int N,
     SCATT_REQUIRE(!ep.layer_norm || (p[i].ln_g && p[i].ln_b), "linear(tcgen05): LayerNorm needs gamma and beta");
     SCATT_REQUIRE(!split_ln || p[i].y, "linear(tcgen05): LayerNorm that is not fused (scatt_linear_ln_fused) needs y as scratch");
     SCATT_REQUIRE(p[i].y || p[i].y_planes, "linear(tcgen05): no output");
-    int rc = encode_planes_map(&P.map_a[i], p[i].x_planes, M, K, BM, fmt);
+    P.kb0[i] = kb0 ? kb0[i] : 0;
+    int rc = encode_planes_map(&P.map_a[i], p[i].x_planes, M, Kmap, BM, fmt);
     if (rc != SCATT_OK) return rc;
-    rc = encode_planes_map(&P.map_b[i], p[i].w_planes, N, K, BN, fmt);
+    rc = encode_planes_map(&P.map_b[i], p[i].w_planes, N, Kmap, BN, fmt);
     if (rc != SCATT_OK) return rc;
     P.prob[i] = TcProblem{p[i].bias, p[i].residual, p[i].ln_g, p[i].ln_b, p[i].y,
                           split_ln ? nullptr : reinterpret_cast<uint16_t*>(p[i].y_planes),

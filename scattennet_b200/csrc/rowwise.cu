@@ -99,6 +99,101 @@ __global__ void __launch_bounds__(256) rowwise_kernel(RowwiseGroup grp, int64_t 
   }
 }
 
+// ---------------------------------------------------------------- split-K reduce + epilogue
+// z = sum of `nsplit` fp32 partial products [nsplit][M][N] (slot order: deterministic) - then exactly the chain of the
+// GEMM epilogue (gemm_tc.cu chunk_pre / LayerNorm pass): + bias, column scaling, act_pre, residual before LayerNorm,
+// LayerNorm, residual after it, act_post, clamp; fp32 and / or split-plane outputs.  One warp per row, N <= 1024.
+struct SplitKArgs {
+  const float* partials;
+  const float* bias;
+  const float* residual;
+  const uint16_t* res_planes;
+  const float* g;
+  const float* b;
+  float* y;
+  uint16_t* planes;
+};
+
+__global__ void __launch_bounds__(256) rowwise_splitk_kernel(SplitKArgs a, int nsplit, int64_t M, int N, int64_t ldres, scatt_epilogue ep,
+                                                             int64_t ldy, int fmt) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int nvec_row = N >> 2;
+  const int64_t mn = M * int64_t(N);
+  auto residual_at = [&](int64_t row, int c) -> float4 {
+    if (a.residual) return ld4(a.residual + row * ldres + c);
+    const uint2 h = *reinterpret_cast<const uint2*>(a.res_planes + row * N + c);
+    const uint2 l = *reinterpret_cast<const uint2*>(a.res_planes + mn + row * N + c);
+    float2 h0, h1, l0, l1;
+    if (fmt == SCATT_PLANE_F16) {
+      h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+    } else {
+      h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.x)), h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h.y));
+      l0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.x)), l1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l.y));
+    }
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+  };
+  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+    float4 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      if (lane + 32 * i < nvec_row) {
+        const int c = 4 * (lane + 32 * i);
+        float4 acc = ld4(a.partials + row * N + c);
+        for (int sp = 1; sp < nsplit; ++sp) {
+          const float4 t = ld4(a.partials + sp * mn + row * N + c);
+          acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+        }
+        if (a.bias) {
+          const float4 t = ld4(a.bias + c);
+          acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+        }
+        if (c < ep.scale_cols) acc.x *= ep.scale, acc.y *= ep.scale, acc.z *= ep.scale, acc.w *= ep.scale;
+        if (ep.act_pre != SCATT_ACT_NONE) {
+          acc.x = apply_act(acc.x, ep.act_pre), acc.y = apply_act(acc.y, ep.act_pre);
+          acc.z = apply_act(acc.z, ep.act_pre), acc.w = apply_act(acc.w, ep.act_pre);
+        }
+        if (ep.residual_mode == SCATT_RES_BEFORE_LN || (ep.residual_mode == SCATT_RES_AFTER_LN && !ep.layer_norm)) {
+          const float4 r = residual_at(row, c);
+          acc.x += r.x, acc.y += r.y, acc.z += r.z, acc.w += r.w;
+        }
+        v[i] = acc;
+      }
+    }
+    RowStats st{0.f, 1.f};
+    if (ep.layer_norm) st = row_stats(v, nvec_row, lane, N, ep.ln_eps);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (lane + 32 * i < nvec_row) {
+        float4 o = v[i];
+        if (ep.layer_norm) {
+          const float4 gg = ld4(a.g + c), bb = ld4(a.b + c);
+          o.x = (o.x - st.mean) * st.rstd * gg.x + bb.x;
+          o.y = (o.y - st.mean) * st.rstd * gg.y + bb.y;
+          o.z = (o.z - st.mean) * st.rstd * gg.z + bb.z;
+          o.w = (o.w - st.mean) * st.rstd * gg.w + bb.w;
+          if (ep.residual_mode == SCATT_RES_AFTER_LN) {
+            const float4 r = residual_at(row, c);
+            o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
+          }
+        }
+        o.x = apply_act(o.x, ep.act_post), o.y = apply_act(o.y, ep.act_post);
+        o.z = apply_act(o.z, ep.act_post), o.w = apply_act(o.w, ep.act_post);
+        if (ep.clamp > 0.f) {
+          o.x = fminf(fmaxf(o.x, -ep.clamp), ep.clamp), o.y = fminf(fmaxf(o.y, -ep.clamp), ep.clamp);
+          o.z = fminf(fmaxf(o.z, -ep.clamp), ep.clamp), o.w = fminf(fmaxf(o.w, -ep.clamp), ep.clamp);
+        }
+        if (a.y) st4(a.y + row * ldy + c, o);
+        if (a.planes) store_planes4(a.planes, mn, row * N + c, o, fmt);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- pos-embed + LayerNorm
 __global__ void __launch_bounds__(256) posembed_ln_kernel(const float* __restrict__ x, const float* __restrict__ table,
                                                           const float* __restrict__ g, const float* __restrict__ b,
@@ -384,6 +479,17 @@ int launch_rowwise_linear_tail(const scatt_linear_problem* p, int group, int64_t
   }
   (void)launch_kernel(rowwise_kernel, dim3(grid_for(M, 8, 148 * 8 / group), group), dim3(256), 0, s, grp, M, N, ldy, ldres, ep, ldy, fmt);
   return after_launch("rowwise_kernel");
+}
+
+int launch_rowwise_splitk(const float* partials, int nsplit, const scatt_linear_problem& p, int64_t M, int N, int64_t ldres,
+                          int64_t ldy, const scatt_epilogue& ep, int fmt, cudaStream_t s) {
+  SCATT_REQUIRE(N % 4 == 0 && N <= 1024 && N > 0 && nsplit >= 1, "rowwise(split-K): N=%d must be a multiple of 4 and <= 1024", N);
+  SCATT_REQUIRE(ldy % 4 == 0 && ldres % 4 == 0 && ep.scale_cols % 4 == 0, "rowwise(split-K): row strides must be multiples of 4");
+  if (M == 0) return SCATT_OK;
+  SplitKArgs a{partials, p.bias, p.residual, reinterpret_cast<const uint16_t*>(p.residual_planes), p.ln_g, p.ln_b, p.y,
+               reinterpret_cast<uint16_t*>(p.y_planes)};
+  (void)launch_kernel(rowwise_splitk_kernel, dim3(grid_for(M, 8)), dim3(256), 0, s, a, nsplit, M, N, ldres, ep, ldy, fmt);
+  return after_launch("rowwise_splitk_kernel");
 }
 
 int launch_posembed_ln(const float* x, const float* table, const float* g, const float* b, float* out, void* planes,

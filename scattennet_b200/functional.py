@@ -357,9 +357,13 @@ def linear(prec: Precision, xs: Sequence[Act], packs: Sequence[PackedLinear], ep
     else:
         in_bytes = (M * K + N * K) * 4.0
     out_bytes = M * N * 4.0 * ((1 if need_f32 else 0) + (1 if want_planes else 0)) + (M * N * 4.0 if residuals is not None else 0.0)
+    lib = L.load()
+    # few row tiles + a long K loop: the launch is split along K through a scratch buffer (scatt_linear_ws)
+    ws_bytes = int(lib.scatt_linear_workspace_bytes(G, M, N, K, prec.engine))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
     with _timed(name, 2.0 * G * M * N * K, G * (in_bytes + out_bytes)):
-        L.check(L.load().scatt_linear(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
-                                      max(prec.terms, 1), _stream()), "scatt_linear")
+        L.check(lib.scatt_linear_ws(probs, G, M, N, K, ldx, ldres, N, C.byref(ep), prec.engine, prec.plane_fmt,
+                                    max(prec.terms, 1), _ptr(ws), ws_bytes, _stream()), "scatt_linear")
     for g in range(G):
         nv = getattr(packs[g], "n_valid", N)
         if nv != N:  # drop the zero-padded columns (plumbing copy; only for widths that are not a multiple of 32)

@@ -119,7 +119,7 @@ def test_linear_n256_large_m_single_cta_path(mode, epi):
 
 @pytest.mark.parametrize("mode", ["fp16x3", "fp16x1"])
 @pytest.mark.parametrize("epi", ["ln_relu", "ln_res_relu", "gelu_res_ln", "res_ln"])
-@pytest.mark.parametrize("G,M,N,K", [(3, 800, 512, 256), (3, 400, 512, 512), (1, 400, 1024, 1024), (1, 2300, 1024, 512),
+@pytest.mark.parametrize("G,M,N,K", [(3, 800, 512, 256), (3, 400, 512, 512), (1, 400, 1024, 1024), (1, 400, 1024, 512), (1, 2300, 1024, 512),
                                      (3, 128 * 13, 512, 256), (1, 128 * 19 + 3, 1024, 256)])
 def test_linear_wide_layernorm_cluster_and_tail(mode, epi, G, M, N, K):
     """Rows of 512 / 1024 columns are normalised inside the GEMM by 4- / 8-CTA clusters (DSMEM statistics
@@ -149,6 +149,43 @@ def test_linear_wide_layernorm_cluster_and_tail(mode, epi, G, M, N, K):
                 assert outs[g].f32 is None  # planes only: no fp32 round trip when the LayerNorm is fused
             err = float((got - ref).abs().max())
             assert err <= MODE_TOL[mode] * 4.0 * max(1.0, math.sqrt(K / 256)), (mode, epi, G, M, N, K, out_f32, err)
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "fp16x1", "bf16x3"])
+@pytest.mark.parametrize("epi", list(EPILOGUES))
+@pytest.mark.parametrize("shape", [(400, 1024, 1024), (400, 1024, 3072), (130, 512, 2048), (400, 1024, 1536), (77, 640, 1024)])
+def test_linear_split_k(mode, epi, shape):
+    """Few row tiles and a long K loop (the fusion block at B = 8): K is cut into slices that run as problem slots of one
+    GEMM launch, the row-wise reduce kernel adds the fp32 partial sums in slot order and runs the epilogue."""
+    M, N, K = shape
+    kw = EPILOGUES[epi]
+    prec = F_.get_precision(mode)
+    assert L.load().scatt_linear_workspace_bytes(1, M, N, K, prec.engine) >= 3 * M * N * 4  # the split path is the one tested
+    x = rnd(M, K, seed=1)
+    lin = make_linear(N, K, 2)
+    ln = torch.nn.LayerNorm(N)
+    with torch.no_grad():
+        ln.weight.copy_(1.0 + 0.2 * (torch.rand(N, generator=torch.Generator().manual_seed(3)) - 0.5))
+        ln.bias.copy_(0.1 * (torch.rand(N, generator=torch.Generator().manual_seed(4)) - 0.5))
+    ln = ln.to(DEV)
+    res = rnd(M, N, seed=4) if kw.get("residual_mode", 0) else None
+    pk = F_.PackedLinear([lin], None, None)
+    for res_as_planes in ((False, True) if res is not None else (False,)):
+        r = None if res is None else [Act(None, F_.split_planes(res, prec)) if res_as_planes else res]
+        out = F_.linear(prec, [Act(x)], [pk], F_.make_epilogue(**kw), residuals=r, lns=[ln] if kw.get("layer_norm") else None)[0]
+        ref = ref_chain(x, lin, kw, res, ln)
+        tol = MODE_TOL[mode] * (4.0 if kw.get("layer_norm") else 1.0) * max(1.0, math.sqrt(K / 256))
+        assert float((out.f32.double() - ref).abs().max()) <= tol, (mode, epi, shape, res_as_planes)
+        rec = out.planes[0].float() + out.planes[1].float()
+        rel = 2.0 ** (-21 if mode.startswith("fp16") else -15)
+        assert float((rec - out.f32).abs().max()) <= rel * float(out.f32.abs().max()) + 1e-7
+    # planes-only outputs (what the encoder asks for)
+    if res is None:
+        out = F_.linear(prec, [Act(x)], [pk], F_.make_epilogue(**kw), lns=[ln] if kw.get("layer_norm") else None, out_f32=False)[0]
+        if out.f32 is None:
+            ref = ref_chain(x, lin, kw, res, ln)
+            rec = out.planes[0].double() + out.planes[1].double()
+            assert float((rec - ref).abs().max()) <= MODE_TOL[mode] * (4.0 if kw.get("layer_norm") else 1.0) * max(1.0, math.sqrt(K / 256)) * 2
 
 
 @pytest.mark.parametrize("mode", ["fp16x3", "fp16x1", "bf16x3"])
@@ -368,7 +405,9 @@ def test_fusion_attention(B, T, D):
     assert float((out.double().cpu() - ref).abs().max()) <= 2e-4
 
 
-FUSION_TOL = {"fp16x3": 1e-4, "bf16x3": 1e-3, "fp16x1": 0.25}
+# logits reach ~235 here (1024 positive products, no scaling): one fp32 ulp of the accumulator is 1.5e-5 and a logit error e
+# is a relative error e of the probability - the fp32 CUDA-core kernel above is held to 2e-4 on the same operands
+FUSION_TOL = {"fp16x3": 3e-4, "bf16x3": 2e-3, "fp16x1": 0.25}
 
 
 def _fusion_planes_case(mode, B, T, D, out_f32=False):
