@@ -114,15 +114,31 @@ struct SplitKArgs {
   uint16_t* planes;
 };
 
+// One CTA per row, one float4 of the row per thread (N / 4 <= 256 threads): every load of a thread - the nsplit partials,
+// bias, residual - is independent and in flight at once; with a warp per row the 4 x 8 dependent L2 round trips took
+// 17 us per launch.  LayerNorm statistics: two-pass (mean, then centred squares) through warp shuffles + shared memory.
+__device__ __forceinline__ float block_sum(float v, float* red, int nwarps) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // red may still be read from the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nwarps; ++w) t += red[w];  // same order in every thread
+  return t;
+}
+
 __global__ void __launch_bounds__(256) rowwise_splitk_kernel(SplitKArgs a, int nsplit, int64_t M, int N, int64_t ldres, scatt_epilogue ep,
                                                              int64_t ldy, int fmt) {
+  __shared__ float red[8];
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  const int nvec_row = N >> 2;
   const int64_t mn = M * int64_t(N);
-  auto residual_at = [&](int64_t row, int c) -> float4 {
+  const int64_t row = blockIdx.x;
+  const int c = 4 * threadIdx.x;
+  const bool in = c < N;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  auto residual_at = [&]() -> float4 {
     if (a.residual) return ld4(a.residual + row * ldres + c);
     const uint2 h = *reinterpret_cast<const uint2*>(a.res_planes + row * N + c);
     const uint2 l = *reinterpret_cast<const uint2*>(a.res_planes + mn + row * N + c);
@@ -136,62 +152,47 @@ __global__ void __launch_bounds__(256) rowwise_splitk_kernel(SplitKArgs a, int n
     }
     return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
   };
-  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
-    float4 v[kMaxVec];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), res = acc, gg = acc, bb = acc;
+  if (in) {
+    float4 part[SCATT_MAX_GROUP];
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      if (lane + 32 * i < nvec_row) {
-        const int c = 4 * (lane + 32 * i);
-        float4 acc = ld4(a.partials + row * N + c);
-        for (int sp = 1; sp < nsplit; ++sp) {
-          const float4 t = ld4(a.partials + sp * mn + row * N + c);
-          acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
-        }
-        if (a.bias) {
-          const float4 t = ld4(a.bias + c);
-          acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
-        }
-        if (c < ep.scale_cols) acc.x *= ep.scale, acc.y *= ep.scale, acc.z *= ep.scale, acc.w *= ep.scale;
-        if (ep.act_pre != SCATT_ACT_NONE) {
-          acc.x = apply_act(acc.x, ep.act_pre), acc.y = apply_act(acc.y, ep.act_pre);
-          acc.z = apply_act(acc.z, ep.act_pre), acc.w = apply_act(acc.w, ep.act_pre);
-        }
-        if (ep.residual_mode == SCATT_RES_BEFORE_LN || (ep.residual_mode == SCATT_RES_AFTER_LN && !ep.layer_norm)) {
-          const float4 r = residual_at(row, c);
-          acc.x += r.x, acc.y += r.y, acc.z += r.z, acc.w += r.w;
-        }
-        v[i] = acc;
-      }
-    }
-    RowStats st{0.f, 1.f};
-    if (ep.layer_norm) st = row_stats(v, nvec_row, lane, N, ep.ln_eps);
+    for (int sp = 0; sp < SCATT_MAX_GROUP; ++sp)
+      part[sp] = sp < nsplit ? ld4(a.partials + sp * mn + row * N + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bias = a.bias ? ld4(a.bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.residual_mode != SCATT_RES_NONE) res = residual_at();
+    if (ep.layer_norm) gg = ld4(a.g + c), bb = ld4(a.b + c);
+    acc = part[0];
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int c = 4 * (lane + 32 * i);
-      if (lane + 32 * i < nvec_row) {
-        float4 o = v[i];
-        if (ep.layer_norm) {
-          const float4 gg = ld4(a.g + c), bb = ld4(a.b + c);
-          o.x = (o.x - st.mean) * st.rstd * gg.x + bb.x;
-          o.y = (o.y - st.mean) * st.rstd * gg.y + bb.y;
-          o.z = (o.z - st.mean) * st.rstd * gg.z + bb.z;
-          o.w = (o.w - st.mean) * st.rstd * gg.w + bb.w;
-          if (ep.residual_mode == SCATT_RES_AFTER_LN) {
-            const float4 r = residual_at(row, c);
-            o.x += r.x, o.y += r.y, o.z += r.z, o.w += r.w;
-          }
-        }
-        o.x = apply_act(o.x, ep.act_post), o.y = apply_act(o.y, ep.act_post);
-        o.z = apply_act(o.z, ep.act_post), o.w = apply_act(o.w, ep.act_post);
-        if (ep.clamp > 0.f) {
-          o.x = fminf(fmaxf(o.x, -ep.clamp), ep.clamp), o.y = fminf(fmaxf(o.y, -ep.clamp), ep.clamp);
-          o.z = fminf(fmaxf(o.z, -ep.clamp), ep.clamp), o.w = fminf(fmaxf(o.w, -ep.clamp), ep.clamp);
-        }
-        if (a.y) st4(a.y + row * ldy + c, o);
-        if (a.planes) store_planes4(a.planes, mn, row * N + c, o, fmt);
-      }
+    for (int sp = 1; sp < SCATT_MAX_GROUP; ++sp)  // slot order; absent slots add +0
+      acc.x += part[sp].x, acc.y += part[sp].y, acc.z += part[sp].z, acc.w += part[sp].w;
+    acc.x += bias.x, acc.y += bias.y, acc.z += bias.z, acc.w += bias.w;
+    if (c < ep.scale_cols) acc.x *= ep.scale, acc.y *= ep.scale, acc.z *= ep.scale, acc.w *= ep.scale;
+    if (ep.act_pre != SCATT_ACT_NONE) {
+      acc.x = apply_act(acc.x, ep.act_pre), acc.y = apply_act(acc.y, ep.act_pre);
+      acc.z = apply_act(acc.z, ep.act_pre), acc.w = apply_act(acc.w, ep.act_pre);
     }
+    if (ep.residual_mode == SCATT_RES_BEFORE_LN || (ep.residual_mode == SCATT_RES_AFTER_LN && !ep.layer_norm))
+      acc.x += res.x, acc.y += res.y, acc.z += res.z, acc.w += res.w;
   }
+  float4 o = acc;
+  if (ep.layer_norm) {
+    const float mean = block_sum(in ? (acc.x + acc.y) + (acc.z + acc.w) : 0.f, red, nwarps) / float(N);
+    const float dx = acc.x - mean, dy = acc.y - mean, dz = acc.z - mean, dw = acc.w - mean;
+    const float var = block_sum(in ? (dx * dx + dy * dy) + (dz * dz + dw * dw) : 0.f, red, nwarps) / float(N);
+    const float rstd = rsqrtf(var + ep.ln_eps);
+    o.x = dx * rstd * gg.x + bb.x, o.y = dy * rstd * gg.y + bb.y;
+    o.z = dz * rstd * gg.z + bb.z, o.w = dw * rstd * gg.w + bb.w;
+    if (ep.residual_mode == SCATT_RES_AFTER_LN) o.x += res.x, o.y += res.y, o.z += res.z, o.w += res.w;
+  }
+  if (!in) return;
+  o.x = apply_act(o.x, ep.act_post), o.y = apply_act(o.y, ep.act_post);
+  o.z = apply_act(o.z, ep.act_post), o.w = apply_act(o.w, ep.act_post);
+  if (ep.clamp > 0.f) {
+    o.x = fminf(fmaxf(o.x, -ep.clamp), ep.clamp), o.y = fminf(fmaxf(o.y, -ep.clamp), ep.clamp);
+    o.z = fminf(fmaxf(o.z, -ep.clamp), ep.clamp), o.w = fminf(fmaxf(o.w, -ep.clamp), ep.clamp);
+  }
+  if (a.y) st4(a.y + row * ldy + c, o);
+  if (a.planes) store_planes4(a.planes, mn, row * N + c, o, fmt);
 }
 
 // ---------------------------------------------------------------- pos-embed + LayerNorm
@@ -488,7 +489,9 @@ int launch_rowwise_splitk(const float* partials, int nsplit, const scatt_linear_
   if (M == 0) return SCATT_OK;
   SplitKArgs a{partials, p.bias, p.residual, reinterpret_cast<const uint16_t*>(p.residual_planes), p.ln_g, p.ln_b, p.y,
                reinterpret_cast<uint16_t*>(p.y_planes)};
-  (void)launch_kernel(rowwise_splitk_kernel, dim3(grid_for(M, 8)), dim3(256), 0, s, a, nsplit, M, N, ldres, ep, ldy, fmt);
+  SCATT_REQUIRE(nsplit <= SCATT_MAX_GROUP && M <= 0x7fffffff, "rowwise(split-K): at most %d slices", SCATT_MAX_GROUP);
+  const int threads = ((N / 4) + 31) & ~31;  // one float4 per thread
+  (void)launch_kernel(rowwise_splitk_kernel, dim3(unsigned(M)), dim3(threads), 0, s, a, nsplit, M, N, ldres, ep, ldy, fmt);
   return after_launch("rowwise_splitk_kernel");
 }
 
