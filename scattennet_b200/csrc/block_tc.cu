@@ -38,10 +38,13 @@
 // CL = 2 (few row tiles: the small-batch regime): a 2-CTA cluster shares one row tile.  Both CTAs compute out_proj +
 // LayerNorm1 (identical results - nothing to exchange), then CTA r takes the hidden chunks j = r, r + 2, ... : half of
 // the W1 / W2 stream and half of the fc1 / fc2 MMAs each.  fc2 is thereby split along K: CTA 1 accumulates its partial
-// sum on top of zeros, CTA 0 on top of h + b2; at the end CTA 1's epilogue warps push their 128 x 256 fp32 partial into
-// CTA 0's (by then idle) hA through distributed shared memory, and CTA 0 adds it in LayerNorm2's statistics pass.
-// (staged in its own hA, then one cp.async.bulk shared::cta -> shared::cluster per warp).  Hand-shake: mbarriers with
-// cluster-scope release / acquire: CTA 0 -> 1 "hA is free", the copies' complete_tx on CTA 0, CTA 0 -> 1 "copied".
+// sum on top of zeros, CTA 0 on top of h + b2.  LayerNorm2 and the output are split by COLUMNS: CTA r owns columns
+// [128 r, 128 r + 128); each CTA ships the other half of its 128 x 256 fp32 partial sum to the peer through distributed
+// shared memory (staged in its own idle hA, one cp.async.bulk shared::cta -> shared::cluster of 8 KB per warp, both
+// directions at once), adds what it receives, exchanges the row statistics of its 128 columns (st.shared::cluster into
+// the peer's staging zone) and normalises and stores its half.  Hand-shake: mbarriers with cluster-scope release /
+// acquire - "landing zone free" (peer_free), the copies' complete_tx (partial_full), "staging read" (xfer_done),
+// "statistics written" (stats_full).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   const uint32_t fc1_full = h_ready + 8u;   // [2]
   const uint32_t g_ready = fc1_full + 16u;  // [2]
   const uint32_t out_full = g_ready + 16u, tile_done = out_full + 8u;
-  const uint32_t peer_free = tile_done + 8u, partial_full = peer_free + 8u, xfer_done = partial_full + 8u, tmem_ptr_addr = xfer_done + 8u;
+  const uint32_t peer_free = tile_done + 8u, partial_full = peer_free + 8u, xfer_done = partial_full + 8u, stats_full = xfer_done + 8u;
+  const uint32_t tmem_ptr_addr = stats_full + 8u;
   volatile uint32_t* trp = reinterpret_cast<volatile uint32_t*>(sm + kTraceOff);
   const bool tracing = SCATT_BLOCK_TRACE && g_trace_blk != nullptr && blockIdx.x == 0;
   (void)trp, (void)tracing;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     mbar_init(peer_free, 1);
     mbar_init(partial_full, 1);
     mbar_init(xfer_done, 1);
+    mbar_init(stats_full, 4 * 32);  // one arrival per row: the peer's warps of column half 0
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int g = 0; g < P.groups; ++g) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_ctx[g]) : "memory");
@@ -586,44 +591,151 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       mbar_wait(out_full, tpar);
       tc_fence_after();
       if (tid == 0 && ti == 0) trace(7);
-      const uint32_t xbox = uint32_t(warp - 2) * 16384u;  // this warp's 4 partial-sum boxes of 32 rows x 128 B (swizzled) in hA
       if constexpr (CL > 1) {
-        if (rank == 0) {
-          // all MMAs of this CTA have retired: hA (h, fc1's operand) is idle and the peer may copy its partial sum there
-          if (tid == 0) {
-            mbar_expect_tx(partial_full, kHABytes);  // 8 bulk copies of 16 KB complete it
-            mbar_arrive_remote(map_to_peer(peer_free, 1));
+        // Both CTAs hold a partial sum of the whole 128 x 256 tile (CTA 0 on top of h + b2, CTA 1 on top of zero).
+        // CTA r owns columns [128 r, 128 r + 128) of LayerNorm2 and of the output: each CTA ships the OTHER half of
+        // its partial sum to the peer (64 KB each way, at the same time - the one-way 128 KB transfer took 9 k
+        // cycles while CTA 1 idled), both normalise and store 64 KB.  hA (idle: every MMA of this CTA has retired)
+        // is cut in two: [0, 64 KB) landing zone - the peer's copies, later this CTA's output boxes; [64 KB, 128 KB)
+        // staging zone - the boxes the peer's columns are copied from, later the peer's row statistics.
+        const uint32_t peer = rank ^ 1u, wq = uint32_t(warp - 2);
+        const uint32_t land = wq * 8192u, stag = 65536u + wq * 8192u;  // this warp's two 32 x 32 fp32 boxes in each zone
+        float v0[32], v1[32];
+        {
+          const uint32_t sc = peer * 128u + uint32_t(hf) * 64u;  // the peer's columns this warp ships
+          tc_ld32(tmem + kAccO + lane_addr + sc, v0);
+          tc_ld32(tmem + kAccO + lane_addr + sc + 32u, v1);
+          uint8_t* box = sm + stag;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t o = uint32_t(lane * 128 + ((j ^ (lane & 7)) << 4));
+            *reinterpret_cast<float4*>(box + o) = make_float4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+            *reinterpret_cast<float4*>(box + 4096 + o) = make_float4(v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
           }
-          mbar_wait_cluster(partial_full, tpar);
-          if (tid == 0) mbar_arrive_remote(map_to_peer(xfer_done, 1));  // the peer's source boxes have been read
-        } else {
-          // partial sum -> this warp's boxes in the CTA's OWN hA (idle as well), then one bulk copy per warp into the
-          // same place of the peer's hA: scattered 16-byte st.shared::cluster took 16 k cycles for the 128 KB
-          float v[32];
-#pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
-            tc_ld32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
-            uint8_t* box = sm + xbox + i * 4096;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (tid == 0 && ti == 0) trace(58);
+        if (tid == 0) {
+          mbar_expect_tx(partial_full, 65536u);  // 8 bulk copies of 8 KB complete it
+          mbar_arrive_remote(map_to_peer(peer_free, peer));  // this CTA's landing zone may be written
+        }
+        mbar_wait_cluster(peer_free, tpar);
+        if (tid == 0 && ti == 0) trace(59);
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           map_to_peer(hA + land, peer)),
+                       "r"(hA + stag), "r"(8192u), "r"(map_to_peer(partial_full, peer))
+                       : "memory");
+        }
+        const uint32_t oc = rank * 128u + uint32_t(hf) * 64u;  // this warp's 64 owned columns
+        tc_ld32(tmem + kAccO + lane_addr + oc, v0);
+        tc_ld32(tmem + kAccO + lane_addr + oc + 32u, v1);
+        mbar_wait_cluster(partial_full, tpar);
+        // the peer's partial sum of the owned columns has landed, hence the peer's staging boxes have been read
+        if (tid == 0) mbar_arrive_remote(map_to_peer(xfer_done, peer));
+        {
+          const uint8_t* box = sm + land;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t o = uint32_t(lane * 128 + ((j ^ (lane & 7)) << 4));
+            const float4 a = *reinterpret_cast<const float4*>(box + o), b = *reinterpret_cast<const float4*>(box + 4096 + o);
+            v0[4 * j] += a.x, v0[4 * j + 1] += a.y, v0[4 * j + 2] += a.z, v0[4 * j + 3] += a.w;
+            v1[4 * j] += b.x, v1[4 * j + 1] += b.y, v1[4 * j + 2] += b.z, v1[4 * j + 3] += b.w;
+          }
+        }
+        if (tid == 0 && ti == 0) trace(60);
+        // statistics: 64 columns per thread -> the CTA's 128 (partner warp, through TMEM) -> the row's 256 (peer CTA)
+        const float shift = v0[0];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float d0 = v0[j] - shift, d1 = v1[j] - shift;
+          s1 += d0 + d1;
+          s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+        }
+        const float dm = s1 * (1.0f / 64.0f);
+        const float my_mean = shift + dm, my_m2 = fmaxf(s2 - s1 * dm, 0.f);
+        tc_st2(tmem_x + uint32_t(hf * 2), my_mean, my_m2);
+        tc_fence_before();
+        epi_bar_sync();
+        tc_fence_after();
+        float om, oq;
+        tc_ld2(tmem_x + uint32_t((hf ^ 1) * 2), om, oq);
+        const float mean_c = 0.5f * (my_mean + om);
+        const float m2_c = my_m2 + oq + 64.0f * ((my_mean - mean_c) * (my_mean - mean_c) + (om - mean_c) * (om - mean_c));
+        // the peer's staging zone is free (its boxes were read before this CTA's partial_full completed): row statistics go there
+        if (hf == 0) {
+          st_peer_f32x2(hA + 65536u + uint32_t(row) * 8u, peer, mean_c, m2_c);
+          mbar_arrive_remote(map_to_peer(stats_full, peer));
+        }
+        mbar_wait_cluster(stats_full, tpar);
+        float2 ps;  // written by the peer through DSMEM: the acquire above orders this read behind it
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(ps.x), "=f"(ps.y) : "r"(hA + 65536u + uint32_t(row) * 8u) : "memory");
+        const float mean = 0.5f * (mean_c + ps.x);
+        const float m2 = m2_c + ps.y + 128.0f * ((mean_c - mean) * (mean_c - mean) + (ps.x - mean) * (ps.x - mean));
+        const float rstd = rsqrtf(m2 * (1.0f / float(DM)) + P.eps);
+        if (tid == 0 && ti == 0) trace(61);
+        const uint32_t poff = Q.y ? 4096u : 0u;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          float* v = i == 0 ? v0 : v1;
+          const int cl = int(oc) + i * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(Q.g2 + cl + j));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(Q.be2 + cl + j));
+            v[j] = (v[j] - mean) * rstd * gg.x + bb.x;
+            v[j + 1] = (v[j + 1] - mean) * rstd * gg.y + bb.y;
+            v[j + 2] = (v[j + 2] - mean) * rstd * gg.z + bb.z;
+            v[j + 3] = (v[j + 3] - mean) * rstd * gg.w + bb.w;
+          }
+          // output boxes in this warp's landing boxes (read above): planes only - one 4 KB box pair per chunk; with an
+          // fp32 output as well the 8 KB buffer is reused after the first chunk's boxes have been read out
+          const uint32_t buf = Q.y ? 0u : uint32_t(i) * 4096u;
+          if (Q.y && i == 1) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+          uint8_t* box = sm + land + buf;
+          if (Q.y) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
+          if (Q.y_planes) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 hi, lo;
+              split8<FMT>(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
+                          make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
+              const uint32_t off = uint32_t(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(box + poff + off) = hi;
+              *reinterpret_cast<uint4*>(box + poff + 2048 + off) = lo;
+            }
+          }
           fence_proxy_async();
           __syncwarp();
-          mbar_wait_cluster(peer_free, tpar);
           if (lane == 0) {
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             map_to_peer(hA + xbox, 0)),
-                         "r"(hA + xbox), "r"(16384u), "r"(map_to_peer(partial_full, 0))
-                         : "memory");
+            const uint32_t src = hA + land + buf;
+            if (Q.y) tma_store_2d(&P.map_y[g], src, cl, int(row0));
+            if (Q.y_planes) {
+              tma_store_3d(&P.map_p[g], src + poff, cl, int(row0), 0);
+              tma_store_3d(&P.map_p[g], src + poff + 2048u, cl, int(row0), 1);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          mbar_wait_cluster(xfer_done, tpar);  // copies landed => the source boxes were read: hA may take the next ctx
-          tc_fence_before();
-          epi_bar_sync();
-          if (tid == 0) mbar_arrive(tile_done);
-          if (tid == 0 && ti == 0) trace(8);
-          continue;
         }
+        if (tid == 0 && ti == 0) trace(62);
+        // hA takes the next tile's ctx once the output boxes have been read out and the peer has copied the staging boxes
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        mbar_wait_cluster(xfer_done, tpar);
+        tc_fence_before();
+        epi_bar_sync();
+        if (tid == 0) mbar_arrive(tile_done);
+        if (tid == 0 && ti == 0) trace(8);
+        continue;
       }
       {
         float v[32];
@@ -631,15 +743,6 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
           tc_ld32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
-          if constexpr (CL > 1) {  // + the peer's partial sum; the total goes back into accO for the second pass
-            const uint8_t* box = sm + xbox + i * 4096;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 pj = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4));
-              v[4 * j] += pj.x, v[4 * j + 1] += pj.y, v[4 * j + 2] += pj.z, v[4 * j + 3] += pj.w;
-            }
-            tc_st32(tmem + kAccO + lane_addr + hf * 128 + i * 32, v);
-          }
           if (i == 0) shift = v[0];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {

@@ -23,7 +23,8 @@ lib = L.load()
 NAMES = {0: "setup done", 15: "P: first Wo tiles issued",
          10: "M: ctx kb0 landed", 11: "M: ctx kb1", 12: "M: ctx kb2", 13: "M: ctx kb3", 16: "P: ctx issued", 2: "M: out_proj issued",
          5: "E: out_proj complete", 6: "E: h written", 3: "M: h seen", 17: "P: all tiles issued", 4: "M: all MMAs issued",
-         7: "E: fc2 complete", 8: "E: tile done", 18: "E: LN1 pass 1 done", 19: "E: LN1 stats combined"}
+         7: "E: fc2 complete", 8: "E: tile done", 18: "E: LN1 pass 1 done", 19: "E: LN1 stats combined",
+         58: "E: staged (cluster)", 59: "E: landing free seen", 60: "E: peer partial added", 61: "E: LN2 stats combined", 62: "E: LN2 stores issued"}
 for j in range(8):
     NAMES[20 + j] = f"M: fc1({j}) issue starts"
     NAMES[30 + j] = f"M: g({j}) seen"
@@ -40,7 +41,7 @@ def lin(n, k):
 D, Fh = 256, 768
 for mode in [a for a in sys.argv[1:] if not a.startswith("--")] or ("fp16x3", "fp16x1"):
     prec = F_.get_precision(mode)
-    for M, G in ((1600, 3), (51200, 3)):
+    for M, G in ((1600, 3),) if "--small" in sys.argv else ((1600, 3), (51200, 3)):
         g = torch.Generator().manual_seed(0)
         ctx = [Act(torch.randn(M, D, generator=g).to(dev)).with_planes(prec) for _ in range(G)]
         xs = [Act(torch.randn(M, D, generator=g).to(dev)).with_planes(prec) for _ in range(G)]
