@@ -162,6 +162,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {  // re
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  #pragma unroll 1  // the compiler otherwise unrolls every spin loop four-fold: 40 % of the fused tail kernel was wait code
   for (uint32_t it = 0; it < kWaitLimit; ++it) {
     uint32_t ok;
     asm volatile(
@@ -434,9 +435,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t g_hi = gbase + uint32_t(kb * 64 + kk * 8);
+                const uint32_t g_hi = gbase + uint32_t(kb * 64 + kk * 16);  // k-step 4 kb + kk: hi pairs, lo pairs 8 columns on
                 tc_mma_f16_ts(dO, g_hi, bh + uint64_t(kk * 2), idesc256, 1);
-                if (a_lo) tc_mma_f16_ts(dO, g_hi + 32u, bh + uint64_t(kk * 2), idesc256, 1);
+                if (a_lo) tc_mma_f16_ts(dO, g_hi + 8u, bh + uint64_t(kk * 2), idesc256, 1);
               }
               tc_commit(empty_bar(s));
               if (last && kb == 1 && !b_lo) tc_commit(out_full);
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             const uint64_t bl = umma_desc_sw128(ring + s * kStageBytes);
             if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) tc_mma_f16_ts(dO, gbase + uint32_t(kb * 64 + kk * 8), bl + uint64_t(kk * 2), idesc256, 1);
+              for (int kk = 0; kk < 4; ++kk) tc_mma_f16_ts(dO, gbase + uint32_t(kb * 64 + kk * 16), bl + uint64_t(kk * 2), idesc256, 1);
               tc_commit(empty_bar(s));
               if (last && kb == 1) tc_commit(out_full);
             }
@@ -568,20 +569,24 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         tc_fence_after();
         if (tid == 0 && ti == 0 && j < 8) trace(40 + j);
         const uint32_t ca = tmem + kAccB + b * 128u + lane_addr + uint32_t(hf * 64);
-        float va[32], vb[32];
-        tc_ld32(ca, va);
-        tc_ld32(ca + 32u, vb);
         const float* bias = Q.b1 + chunk_of(j) * 128 + hf * 64;
-        add_cols_g(va, bias);
-        add_cols_g(vb, bias + 32);
-        uint32_t whi[32], wlo[32];
+        // 32 columns at a time, rewritten in place: the 16 fp32 columns of MMA k-step q become 8 words of hi pairs
+        // followed by 8 words of lo pairs.  A rolled loop on purpose: the fully unrolled 64-column body was 23 KB of
+        // straight-line code that every warp fetched cold (stall_no_inst was the top stall reason of this phase).
+#pragma unroll 1
+        for (int i = 0; i < 2; ++i) {
+          float v[32];
+          tc_ld32(ca + uint32_t(32 * i), v);
+          add_cols_g(v, bias + 32 * i);
+          uint32_t w[32];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          split_pair_rt(gelu_fast(va[2 * e]), gelu_fast(va[2 * e + 1]), FMT, whi[e], wlo[e]);
-          split_pair_rt(gelu_fast(vb[2 * e]), gelu_fast(vb[2 * e + 1]), FMT, whi[16 + e], wlo[16 + e]);
+          for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              split_pair_rt(gelu_fast(v[16 * q + 2 * e]), gelu_fast(v[16 * q + 2 * e + 1]), FMT, w[16 * q + e], w[16 * q + 8 + e]);
+          }
+          tc_st32(ca + uint32_t(32 * i), reinterpret_cast<const float*>(w));
         }
-        tc_st32(ca, reinterpret_cast<const float*>(whi));        // K elements [64 hf, 64 hf + 64): hi pairs
-        tc_st32(ca + 32u, reinterpret_cast<const float*>(wlo));  // ... and their lo pairs
         tc_fence_before();
         mbar_arrive(g_ready + 8u * b);
         if (tid == 0 && ti == 0 && j < 8) trace(50 + j);

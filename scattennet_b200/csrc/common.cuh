@@ -115,18 +115,23 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. at the
-// fp32 rounding level of the exact form) - ~14 instructions instead of ~40 for
-// erff(); used in the tensor-core epilogues where code size matters.
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. at the fp32 rounding level of the exact
+// form); used in the tensor-core epilogues, where the instruction count per element is the critical path of the
+// fused layer tail (profiles/r02_ncu_attn_block_cluster2.txt: a quarter of the stall samples were instruction
+// fetches inside the GELU code).  Written as
+//   gelu(x) = max(x, 0) - |x| * (p(t) t / 2) * exp(-x^2 / 2),   t = 1 / (1 + 0.3275911 |x| / sqrt 2)
+// (1 - erf is what 7.1.26 produces, so neither the "1 +" nor the sign select is needed): 11 fma-pipe instructions
+// and two MUFU (rcp.approx.ftz / ex2.approx.ftz - no denormal fix-up code) per element.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * e;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+  const float u = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, u, 1.0f)));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * (-0.5f * 1.4426950408889634f)));
+  return fmaf(-(p * t * u), e, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
