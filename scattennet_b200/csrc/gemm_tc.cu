@@ -451,13 +451,8 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     const float var = m2 / float(LN >= 2 ? LN * BN : BN);
     const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
-    float4 r[2][8];
     const bool res_global = res_after && E.res_box == nullptr;  // cluster kernels find the residual staged in smem
-    if (res_global) tile_fetch(E, Q.residual, P.ldres, n0 + half * kMine * 32, r[0]);
-#pragma unroll 2
-    for (int i = 0; i < kMine; ++i) {
-      const int cl = (half * kMine + i) * 32;
-      if (res_global && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
+    auto normalise = [&](int cl) {
       tc_ld32(tmem_acc + cl, v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -468,10 +463,39 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
         v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
         v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
       }
-      if (res_global) tile_add(E, r[i & 1], v);
-      else if (res_after && P.res_planes) box_add_planes(E, E.res_box + i * 4096, v, P.fmt);
-      else if (res_after) box_add(E, E.res_box + i * 4096, v);
-      chunk_store<FMT>(P, Q, E, v, n0 + cl);
+    };
+    if constexpr (LN >= 2) {
+      // Small-batch kernels run this code once or twice per CTA: it is kept ROLLED (one copy of the normalise /
+      // residual / store code instead of two) - instruction fetches were 28-30 % of the stall samples of these
+      // kernels (profiles/r02_ncu_step_kernels.txt), every line of an unrolled copy is a cold miss.
+#pragma unroll 1
+      for (int i = 0; i < kMine; ++i) {
+        const int cl = (half * kMine + i) * 32;
+        normalise(cl);
+        if (res_global) {  // only with SCATT_RES_STAGED=0 builds
+          float4 r1[8];
+          tile_fetch(E, Q.residual, P.ldres, n0 + cl, r1);
+          tile_add(E, r1, v);
+        } else if (res_after && P.res_planes) {
+          box_add_planes(E, E.res_box + i * 4096, v, P.fmt);
+        } else if (res_after) {
+          box_add(E, E.res_box + i * 4096, v);
+        }
+        chunk_store<FMT>(P, Q, E, v, n0 + cl);
+      }
+    } else {
+      float4 r[2][8];
+      if (res_global) tile_fetch(E, Q.residual, P.ldres, n0 + half * kMine * 32, r[0]);
+#pragma unroll 2
+      for (int i = 0; i < kMine; ++i) {
+        const int cl = (half * kMine + i) * 32;
+        if (res_global && i + 1 < kMine) tile_fetch(E, Q.residual, P.ldres, n0 + cl + 32, r[(i + 1) & 1]);
+        normalise(cl);
+        if (res_global) tile_add(E, r[i & 1], v);
+        else if (res_after && P.res_planes) box_add_planes(E, E.res_box + i * 4096, v, P.fmt);
+        else if (res_after) box_add(E, E.res_box + i * 4096, v);
+        chunk_store<FMT>(P, Q, E, v, n0 + cl);
+      }
     }
   }
 }
