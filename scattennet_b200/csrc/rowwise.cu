@@ -6,6 +6,8 @@
 // All of them are "one warp owns one row of <= 1024 fp32" kernels: the row
 // lives in registers as float4 chunks, reductions are warp shuffles, every
 // global access is a coalesced 16-byte vector.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace scatt {
@@ -517,6 +519,13 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
     if (streams[i].n_joints > max_nj) max_nj = streams[i].n_joints;
   }
   if (int64_t(B) * T == 0) return SCATT_OK;
+  {  // planes-only output on the tensor-core engine: the mapping runs on tcgen05 (frontend_tc.cu); SCATT_FRONTEND_TC=0 keeps the CUDA-core kernel
+    static const bool tc_off = [] { const char* e = std::getenv("SCATT_FRONTEND_TC"); return e && e[0] == '0'; }();
+    if (!tc_off) {
+      const int rc = launch_frontend_tc(kp, B, T, K, streams, n, fmt, s);
+      if (rc <= 0) return rc;  // launched (or failed); > 0: outside that kernel's envelope
+    }
+  }
   const int wt_stride = max_nj * D;
   const size_t smem = size_t(2) * wt_stride * sizeof(float) + kFeStageBytes;
   static PerDeviceFlag attr_done;

@@ -477,6 +477,44 @@ def test_rowwise_layernorm_widths():
         assert float((out.f32.double() - ref).abs().max()) <= 1e-5
 
 
+@pytest.mark.parametrize("B,T", [(8, 200), (3, 50), (5, 77), (1, 128), (2, 300)])
+def test_frontend_tensor_core(B, T):
+    """Planes-only output of >= 128 frames runs the mapping on tcgen05 (frontend_tc_kernel): oracle parity within the
+    split-plane class (hi + lo carries 22 bits), every tile shape: M tail, sequences wrapping inside a tile, one and
+    two k-steps (6 / 21 joints), an unsorted index list, both self_attn_x settings."""
+    from scattennet_b200.config import model_config
+    from scattennet_b200.keypoint_module import KeypointModule, frontend_forward
+
+    cfg = model_config("phoenix-2014t")
+    if T > cfg["max_position_embeddings"]:
+        cfg = dict(cfg, max_position_embeddings=512)
+    kp, _ = synth.synth_batch(B, T, seed=5)
+    mods, idxs = [], []
+    for i, part in enumerate(("body", "left", "right")):
+        m = KeypointModule(cfg[part + "_idx"], cfg["num_frame"], dict(cfg, self_attn_x=(i != 1))).eval()
+        synth.load_synth_(m, 40 + i)
+        mods.append(m.to(DEV))
+        idxs.append(torch.tensor(cfg[part + "_idx"], dtype=torch.int32, device=DEV))
+    idxs[0] = torch.tensor([500, 3, 541, 0, 77, 12], dtype=torch.int32, device=DEV)
+    prec = F_.get_precision("fp16x3")
+    s, c, _ = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T)
+    assert L.load().scatt_last_kernel().decode() == "frontend_tc_kernel"
+    sf, cf, _ = frontend_forward(prec, mods, kp.to(DEV), idxs, B, T, want_f32=True)  # the CUDA-core kernel (exact fp32 order)
+    assert L.load().scatt_last_kernel().decode().startswith("frontend_kernel")
+    for g, m in enumerate(mods):
+        region = kp[:, :, idxs[g].cpu().long(), :]
+        sd = {"m." + k: v.cpu() for k, v in m.state_dict().items()}
+        xe, ye = O.coordinate_mapping(sd, "m.coordinate_mapping", region)
+        s_in, c_in = (xe, ye) if m.sca.x_self else (ye, xe)
+        s_ref = O.layer_norm(sd, "m.sca.first_self_norm", O.position_embed(sd, "m.sca.self_pos_embed", s_in))
+        c_ref = O.layer_norm(sd, "m.sca.first_causal_norm", O.position_embed(sd, "m.sca.causal_pos_embed", c_in))
+        for act, ref, f32 in ((s[g], s_ref, sf[g]), (c[g], c_ref, cf[g])):
+            assert act.f32 is None
+            got = act.planes[0].float() + act.planes[1].float()
+            assert float((got.cpu().view(B, T, -1) - ref).abs().max()) <= 2e-5
+            assert float((got - f32.f32).abs().max()) <= 2e-5
+
+
 def test_frontend_gather_exact_and_embeddings():
     from scattennet_b200.config import model_config
     from scattennet_b200.keypoint_module import KeypointModule, frontend_forward

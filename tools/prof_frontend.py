@@ -20,4 +20,4 @@ idx = model._joint_idx(torch.device("cuda"))
 for _ in range(4):
     out = frontend_forward(prec, mods, kp, idx, B, T)
 torch.cuda.synchronize()
-print("ok", out[0][0].f32.shape)
+print("ok", out[0][0].planes.shape)
