@@ -204,7 +204,8 @@ __device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t plane_st
 // ---------------------------------------------------------------- launchers implemented in the .cu files
 int launch_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int fmt,
                         cudaStream_t s);
-int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_frontend_stream* streams, int n, int fmt, cudaStream_t s);
+int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_frontend_stream* streams, int n, int max_pos, int fmt, bool force,
+                       cudaStream_t s);
 int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_frontend_stream* streams, int n, int max_pos,
                     int fmt, cudaStream_t s);
 int launch_posembed_ln(const float* x, const float* table, const float* g, const float* b, float* out, void* planes,

@@ -8,18 +8,28 @@
 // K_s -> 256 mapping and is bound by instruction issue at 23-26 % of the HBM copy rate (profiles/r02_sweep_membound.md).
 // Here the mapping is a [128 frames x 32] x [32 x 256] product on tcgen05 (coordinates and weights as fp16 hi / lo
 // split planes, three product terms, fp32 accumulation: ~2^-22 relative, the same class as every other GEMM of the
-// path), so the SM only gathers, normalises, splits and stores.
+// path), so the SM only gathers, normalises, splits and stores.  The mapping bias rides in the product too: column
+// n_joints of the A tile is 1, row n_joints of W^T is the bias.
 //
-// One CTA works on ONE (stream, branch) pair - its mapping weight (B operand, 32 KB) and column parameters are staged
-// once - and walks 128-frame tiles of it.  352 threads:
-//   warps 0-7  epilogue, two per TMEM lane quadrant (128 columns each): pass 1 adds bias + position row and
-//              accumulates the row statistics (values written back to TMEM), pass 2 normalises, splits into hi / lo
-//              and hands 64-column boxes (hi tile | lo tile, 128-byte swizzle) to the TMA engine - one store per 8 KB.
-//   warp 8     TMEM allocation + tcgen05.mma issue: <= 6 MMAs (N = 256, K = 16) per tile into one of TWO accumulators,
-//              so the MMAs of tile i + 1 run under the epilogue of tile i.
-//   warps 9-10 loaders: the region gather (thread = frame, 4-byte loads of the used joints' coordinate straight from
-//              keypoints[B,T,K,2]), split into fp16 hi / lo and written as K-major, 32-byte-swizzled A tiles
-//              (double-buffered) - a tile ahead of the MMAs.
+// One CTA works on ONE (stream, branch) pair - its mapping weight (B operand, 32 KB) and LayerNorm parameters are
+// staged once - and walks 128-frame tiles of it.  416 threads:
+//   warps 0-7   epilogue, two per TMEM lane quadrant (128 columns each), thread = frame.  Pass 1 adds the frame's
+//               position row and accumulates shifted sums (values written back to TMEM); pass 2 normalises, splits
+//               into hi / lo and hands 32-column boxes (hi box | lo box, 64-byte swizzle, double-buffered) to the TMA
+//               engine.  Packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2) throughout: ~7 instructions per element.  The position rows of a warp's 32 frames are consecutive table rows (t = frame mod T), so
+//               they arrive as 32 x 32 fp32 TMA boxes through a two-slot ring per warp that runs two chunks ahead,
+//               across tile boundaries; thread-per-row global loads (32 cache lines per request) kept the L1 at
+//               60-70 % busy in the first version (profiles/r02_ncu_frontend_tc.txt).  Warps whose 32 frames straddle a
+//               sequence boundary take the per-thread loads.
+//   warp 8      TMEM allocation + tcgen05.mma issue: <= 6 MMAs (N = 256, K = 16) per tile into one of TWO accumulators,
+//               so the MMAs of tile i + 1 run under the epilogue of tile i.
+//   warps 9-12  loaders: the region gather straight from keypoints[B,T,K,2] (lane = joint, one request per frame),
+//               split into fp16 hi / lo and written as K-major, 32-byte-swizzled A tiles (double-buffered) - a tile
+//               ahead of the MMAs.
+// Measured (profiles/r02_frontend_tc_ablation.txt, B = 256, T = 200: 334 MB of planes): 133 us = 2.5 TB/s = 38 % of the
+// HBM copy rate (the CUDA-core kernel: 221 us).  Without position rows, gather and stores the kernel still takes 90 us:
+// each element is read from TMEM twice (statistics, then normalisation) at the ~64 B/clk/SM the TMEM read path gives,
+// and ~7 issue slots per element on 8 epilogue warps - that, not HBM, is the bound of this version.
 // Algorithmic traffic per frame and stream: 8 n_joints bytes read (sector granularity makes that up to 32 n_joints),
 // 2 x 256 x 4 bytes written.
 #include <cuda.h>
@@ -39,7 +49,7 @@ using namespace tc;
 
 constexpr int kFtEpiWarps = 8;
 constexpr int kFtMmaWarp = kFtEpiWarps;
-constexpr int kFtLoadWarps = 2;
+constexpr int kFtLoadWarps = 4;
 constexpr int kFtThreads = 32 * (kFtEpiWarps + 1 + kFtLoadWarps);
 constexpr int kFtD = 256;
 constexpr uint32_t kFtATile = 128 * 32;  // [128 frames x 16 joints] fp16, 32-byte rows
@@ -47,13 +57,14 @@ constexpr uint32_t kFtWTile = 256 * 32;  // [256 channels x 16 joints]
 // shared memory map (relative to the 1024-aligned base)
 constexpr uint32_t kFtWOff = 0;                             // [ks 2][plane 2] W tiles
 constexpr uint32_t kFtAOff = kFtWOff + 4 * kFtWTile;        // [stage 2][ks 2][plane 2] A tiles
-constexpr uint32_t kFtOutOff = kFtAOff + 2 * 4 * kFtATile;  // [warp 8][buffer 2][hi 4 KB | lo 4 KB] output boxes
-constexpr uint32_t kFtColOff = kFtOutOff + kFtEpiWarps * 2 * 8192;  // float[3][256]: bias, gamma, beta
-constexpr uint32_t kFtIdxOff = kFtColOff + 3 * kFtD * 4;    // int[32] joint indices
+constexpr uint32_t kFtWarpOff = kFtAOff + 2 * 4 * kFtATile; // per epilogue warp: position ring 2 x 4 KB | output box pair 8 KB
+constexpr uint32_t kFtWarpBytes = 16384;
+constexpr uint32_t kFtColOff = kFtWarpOff + kFtEpiWarps * kFtWarpBytes;  // float[2][256]: gamma, beta
+constexpr uint32_t kFtIdxOff = kFtColOff + 2 * kFtD * 4;    // int[32] joint indices
 constexpr uint32_t kFtStatOff = kFtIdxOff + 128;            // float2[parity 2][half 2][128] row statistics of the two column halves
-constexpr uint32_t kFtBarOff = kFtStatOff + 2 * 2 * 128 * 8;    // a_full[2], a_empty[2], acc_full[2], acc_empty[2], tmem ptr
-constexpr uint32_t kFtSmemBytes = kFtBarOff + 128 + 1024;   // + alignment slack
-static_assert(kFtOutOff % 1024 == 0, "128-byte-swizzled boxes need 1024-byte alignment");
+constexpr uint32_t kFtBarOff = kFtStatOff + 2 * 2 * 128 * 8;  // a_full[2], a_empty[2], acc_full[2], acc_empty[2], tmem ptr, pos_full[8][2]
+constexpr uint32_t kFtSmemBytes = kFtBarOff + 256 + 1024;   // + alignment slack
+static_assert(kFtWarpOff % 1024 == 0, "128-byte-swizzled boxes need 1024-byte alignment");
 static_assert(kFtSmemBytes <= 227 * 1024, "frontend_tc: shared memory map exceeds 227 KB");
 
 struct FtPair {  // one (stream, branch)
@@ -67,12 +78,13 @@ struct FtPair {  // one (stream, branch)
 };
 
 struct alignas(64) FtParams {
-  CUtensorMap map_out[2 * SCATT_MAX_GROUP];  // planes [2][M][256]: box 64 x 32 x 2
+  CUtensorMap map_out[2 * SCATT_MAX_GROUP];  // planes [2][M][256]: box 32 x 32 x 1, 64-byte swizzle
+  CUtensorMap map_pos[2 * SCATT_MAX_GROUP];  // fp32 [max_pos + 2][256]: box 32 x 32, 128-byte swizzle
   FtPair pair[2 * SCATT_MAX_GROUP];
   const float* kp;
   int64_t M;
   int32_t T, K, npairs, ctas_per_pair, tiles_m;
-  int32_t ablate;  // dev builds (-DSCATT_FT_ABLATE=1, env SCATT_FT_DBG): 1 = no position loads, 2 = no gather loads, 4 = no stores
+  int32_t ablate;  // dev builds (-DSCATT_FT_ABLATE=1, env SCATT_FT_DBG): 1 = no position rows, 2 = no gather loads, 4 = no stores
 };
 #ifndef SCATT_FT_ABLATE
 #define SCATT_FT_ABLATE 0
@@ -95,6 +107,15 @@ __device__ __forceinline__ uint32_t ft_chunk_off(int r, int q) {
 
 __device__ __forceinline__ void ft_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * kFtEpiWarps) : "memory"); }
 
+// hi / lo split of a pair with packed conversions and a packed subtraction
+__device__ __forceinline__ void ft_split2(float2 y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __float22half2_rn(y);
+  const float2 back = __half22float2(h);
+  const __half2 l = __float22half2_rn(__fadd2_rn(y, make_float2(-back.x, -back.y)));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid_constant__ FtParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -106,11 +127,12 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
   auto acc_full = [&](uint32_t s) { return bar0 + 32u + 8u * s; };
   auto acc_empty = [&](uint32_t s) { return bar0 + 48u + 8u * s; };
   const uint32_t tmem_ptr_addr = bar0 + 64u;
+  auto pos_full = [&](uint32_t w, uint32_t s) { return bar0 + 80u + 16u * w + 8u * s; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pi = int(blockIdx.x) / P.ctas_per_pair, slot = int(blockIdx.x) % P.ctas_per_pair;
   const FtPair& Q = P.pair[pi];
-  const int nj = Q.n_joints, nks = nj > 16 ? 2 : 1;
+  const int nj = Q.n_joints, nks = nj >= 16 ? 2 : 1;  // + 1 column for the bias
   const int ntiles = slot < P.tiles_m ? (P.tiles_m - slot + P.ctas_per_pair - 1) / P.ctas_per_pair : 0;
 
   if (threadIdx.x == 0) {
@@ -120,14 +142,20 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), 32 * kFtEpiWarps);
     }
+    for (uint32_t w = 0; w < uint32_t(kFtEpiWarps); ++w) {
+      mbar_init(pos_full(w, 0), 1);
+      mbar_init(pos_full(w, 1), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_out[pi]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&P.map_pos[pi]) : "memory");
   }
   if (warp == kFtMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    // static data of the pair: W^T [nj][256] fp32 -> [ks][plane] K-major tiles (zero beyond nj), column parameters, indices
+    // static data of the pair: W^T [nj][256] fp32 (+ the bias as row nj) -> [ks][plane] K-major tiles (zero beyond),
+    // LayerNorm parameters, joint indices
     const int tid = warp < kFtMmaWarp ? int(threadIdx.x) : int(threadIdx.x) - 32;
     constexpr int kStagers = kFtThreads - 32;
     for (int item = tid; item < kFtD * 2 * nks; item += kStagers) {
@@ -136,7 +164,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = ks * 16 + q * 8 + e;
-        w[e] = k < nj ? Q.wt[k * kFtD + n] : 0.f;
+        w[e] = k < nj ? Q.wt[k * kFtD + n] : (k == nj ? Q.bias[n] : 0.f);
       }
       uint4 hi, lo;
       split8<SCATT_PLANE_F16>(make_float4(w[0], w[1], w[2], w[3]), make_float4(w[4], w[5], w[6], w[7]), hi, lo);
@@ -146,10 +174,10 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
     }
     float* col = reinterpret_cast<float*>(sm + kFtColOff);
     for (int i = tid; i < kFtD; i += kStagers) {
-      col[i] = Q.bias[i];
-      col[kFtD + i] = Q.ln_g[i];
-      col[2 * kFtD + i] = Q.ln_b[i];
+      col[i] = Q.ln_g[i];
+      col[kFtD + i] = Q.ln_b[i];
     }
+    for (int i = tid; i < int(2 * 4 * kFtATile / 16); i += kStagers) reinterpret_cast<uint4*>(sm + kFtAOff)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 32) reinterpret_cast<int32_t*>(sm + kFtIdxOff)[tid] = tid < nj ? Q.joint_idx[tid] : 0;
     fence_proxy_async();
   }
@@ -161,32 +189,39 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + kFtBarOff + 64);
 
   if (warp > kFtMmaWarp) {  // ================================================= loaders: gather + split -> A tiles
-    const int tid = int(threadIdx.x) - 32 * (kFtMmaWarp + 1);  // 0..63: frames tid and tid + 64 of the tile
+    // lane = joint (lane n_joints carries the constant 1 of the bias column), warp w takes frames 32 w .. 32 w + 31 of the
+    // tile: one request per frame spans the stream's joints (168 contiguous bytes for a hand) instead of one request
+    // per joint spanning 32 frames (32 cache lines) - the L1 tag stage is shared with the epilogue's LDS / STS traffic.
+    // The tiles' columns beyond n_joints were zeroed once; each lane writes only its own 2-byte hi and lo elements.
+    const int lw = warp - (kFtMmaWarp + 1);
     const int32_t* idx = reinterpret_cast<const int32_t*>(sm + kFtIdxOff);
-    const float* kpc = P.kp + Q.coord;
+    const bool mine = lane < nj;
+    const float* kpc = P.kp + Q.coord + (mine ? idx[lane] * 2 : 0);
+    const uint32_t koff = uint32_t(lane >> 4) * 2u * kFtATile + uint32_t(lane & 7) * 2u;  // k-step tile + position inside the 16-byte chunk
+    const int q = (lane >> 3) & 1;
     for (int it = 0; it < ntiles; ++it) {
       const uint32_t s = uint32_t(it) & 1u;
-      const int64_t m0 = int64_t(slot + it * P.ctas_per_pair) * 128;
+      const int64_t row0 = int64_t(slot + it * P.ctas_per_pair) * 128 + lw * 32;
       if (it >= 2) mbar_wait(a_empty(s), ((uint32_t(it) >> 1) & 1u) ^ 1u);
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int r = tid + 64 * h;
-        const int64_t row = m0 + r;
-        const float* src = kpc + row * int64_t(P.K) * 2;
-        const bool valid = row < P.M;
-#pragma unroll 1
-        for (int c = 0; c < 2 * nks; ++c) {
-          float v[8];
+      for (int f0 = 0; f0 < 32; f0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int64_t row = row0 + f0 + e;
+          const bool valid = row < P.M && !(SCATT_FT_ABLATE && (P.ablate & 2));
+          v[e] = (valid && mine) ? __ldg(kpc + row * int64_t(P.K) * 2) : ((valid && lane == nj) ? 1.0f : 0.f);
+        }
+        if (lane <= nj) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int k = c * 8 + e;
-            v[e] = (valid && k < nj && !(SCATT_FT_ABLATE && (P.ablate & 2))) ? __ldg(src + idx[k] * 2) : 0.f;
+            const int r = lw * 32 + f0 + e;
+            const __half h = __float2half_rn(v[e]);
+            const __half l = __float2half_rn(v[e] - __half2float(h));
+            const uint32_t off = kFtAOff + s * 4u * kFtATile + koff + ft_chunk_off(r, q);
+            *reinterpret_cast<__half*>(sm + off) = h;
+            *reinterpret_cast<__half*>(sm + off + kFtATile) = l;
           }
-          uint4 hi, lo;
-          split8<SCATT_PLANE_F16>(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
-          const uint32_t off = kFtAOff + s * 4u * kFtATile + uint32_t(c >> 1) * 2u * kFtATile + ft_chunk_off(r, c & 1);
-          *reinterpret_cast<uint4*>(sm + off) = hi;
-          *reinterpret_cast<uint4*>(sm + off + kFtATile) = lo;
         }
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's operand reads
@@ -223,41 +258,87 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
     const float* col = reinterpret_cast<const float*>(sm + kFtColOff);
     float2* stats = reinterpret_cast<float2*>(sm + kFtStatOff);
-    uint8_t* obuf = sm + kFtOutOff + uint32_t(warp) * 16384u;
-    const uint32_t obuf_addr = base + kFtOutOff + uint32_t(warp) * 16384u;
+    uint8_t* wsm = sm + kFtWarpOff + uint32_t(warp) * kFtWarpBytes;          // position ring [2][4 KB]
+    const uint32_t wsm_addr = base + kFtWarpOff + uint32_t(warp) * kFtWarpBytes;
+    uint8_t* obuf = wsm + 8192;                                              // output box pair
+    const uint32_t obuf_addr = wsm_addr + 8192u;
+    const bool no_pos = SCATT_FT_ABLATE && (P.ablate & 1);
+    // first frame of this warp's 32 in tile `it`, and whether their position rows are 32 consecutive table rows
+    auto warp_row0 = [&](int it) { return int64_t(slot + it * P.ctas_per_pair) * 128 + quad * 32; };
+    auto t_first = [&](int it) { return int(warp_row0(it) % P.T); };
+    auto boxed = [&](int it) { return it < ntiles && t_first(it) + 31 < P.T && !no_pos; };
+    uint32_t pos_par = 0u;  // bit sl: parity of the next completion of ring slot sl
+    auto issue_pos = [&](int it, int c) {  // chunk c (32 columns) of tile it -> ring slot c & 1
+      if (lane == 0) {
+        const uint32_t sl = uint32_t(c) & 1u;
+        mbar_expect_tx(pos_full(uint32_t(warp), sl), 4096u);
+        tma_load_2d(wsm_addr + sl * 4096u, &P.map_pos[pi], pos_full(uint32_t(warp), sl), half * 128 + 32 * c, t_first(it) + 2);
+      }
+    };
+    bool pre = false;  // chunks 0 and 1 of the coming tile have been requested
     uint32_t stores = 0;
     for (int it = 0; it < ntiles; ++it) {
       const uint32_t s = uint32_t(it) & 1u, ph = (uint32_t(it) >> 1) & 1u;
       const int64_t m0 = int64_t(slot + it * P.ctas_per_pair) * 128;
       const int64_t row = m0 + r;
       const bool valid = row < P.M;
+      const bool use_box = boxed(it), next_box = boxed(it + 1);
+      if (use_box && !pre) {
+        issue_pos(it, 0);
+        issue_pos(it, 1);
+      }
       const float* prow = Q.pos + (int64_t(valid ? row % P.T : 0) + 2) * kFtD + half * 128;
       mbar_wait(acc_full(s), ph);
       tc_fence_after();
       const uint32_t acc = tmem + s * 256u + lane_addr + uint32_t(half * 128);
       float v[32];
-      // ---- pass 1: (dot + bias) + position row, as the reference adds them; shifted sums of the 128 columns
-      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      // ---- pass 1: (dot + bias) + position row; shifted sums of the 128 columns
+      float shift = 0.f;
+      float2 s1 = make_float2(0.f, 0.f), s2 = s1;
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        tc_ld32(acc + uint32_t(32 * i), v);
-        add_cols(v, col + half * 128 + 32 * i);
+      for (int c = 0; c < 4; ++c) {
+        float4 p[8];
+        if (use_box) {
+          const uint32_t sl = uint32_t(c) & 1u;
+          mbar_wait(pos_full(uint32_t(warp), sl), (pos_par >> sl) & 1u);
+          pos_par ^= 1u << sl;
+          const uint8_t* box = wsm + sl * 4096u;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 p = (valid && !(SCATT_FT_ABLATE && (P.ablate & 1))) ? __ldg(reinterpret_cast<const float4*>(prow + 32 * i + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[j] += p.x, v[j + 1] += p.y, v[j + 2] += p.z, v[j + 3] += p.w;
-        }
-        if (i == 0) shift = v[0];
+          for (int j = 0; j < 8; ++j) p[j] = *reinterpret_cast<const float4*>(box + lane * 128 + ((j ^ (lane & 7)) << 4));
+          __syncwarp();  // every lane has read the slot: it may be refilled
+          if (c < 2) issue_pos(it, c + 2);
+          else if (next_box) issue_pos(it + 1, c - 2);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = v[j] - shift;
-          s1 += d;
-          s2 = fmaf(d, d, s2);
+          for (int j = 0; j < 8; ++j)
+            p[j] = (valid && !no_pos) ? __ldg(reinterpret_cast<const float4*>(prow + 32 * c + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        tc_st32(acc + uint32_t(32 * i), v);
+        tc_ld32(acc + uint32_t(32 * c), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 a = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(p[j].x, p[j].y));
+          const float2 b = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(p[j].z, p[j].w));
+          v[4 * j] = a.x, v[4 * j + 1] = a.y, v[4 * j + 2] = b.x, v[4 * j + 3] = b.y;
+        }
+        if (c == 0) shift = v[0];
+        const float2 ns = make_float2(-shift, -shift);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 d = __fadd2_rn(make_float2(v[2 * j], v[2 * j + 1]), ns);
+          s1 = __fadd2_rn(s1, d);
+          s2 = __ffma2_rn(d, d, s2);
+        }
+        tc_st32(acc + uint32_t(32 * c), v);
       }
-      const float dm = s1 * (1.0f / 128.0f);
-      const float my_mean = shift + dm, my_m2 = fmaxf(s2 - s1 * dm, 0.f);
+      pre = use_box ? next_box : false;
+      if (!use_box && next_box) {  // (a tile that took the per-thread loads leaves the ring idle)
+        issue_pos(it + 1, 0);
+        issue_pos(it + 1, 1);
+        pre = true;
+      }
+      const float sum1 = s1.x + s1.y, sum2 = s2.x + s2.y;
+      const float dm = sum1 * (1.0f / 128.0f);
+      const float my_mean = shift + dm, my_m2 = fmaxf(sum2 - sum1 * dm, 0.f);
       float2* st = stats + (it & 1) * 256;  // alternating buffers: a warp may be a whole tile ahead of its partner's read
       st[half * 128 + r] = make_float2(my_mean, my_m2);
       ft_epi_bar();
@@ -266,45 +347,43 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
       const float da = my_mean - mean, db = other.x - mean;
       const float m2 = my_m2 + other.y + 128.0f * (da * da + db * db);  // Chan et al.
       const float rstd = rsqrtf(m2 * (1.0f / float(kFtD)) + 1e-5f);
-      // ---- pass 2: normalise, split, 64 columns per TMA store (hi tile | lo tile of 32 rows x 128 bytes)
+      const float2 nm = make_float2(-mean, -mean), rs = make_float2(rstd, rstd);
+      // ---- pass 2: normalise, split, 32 columns per pair of TMA stores (hi box | lo box of 32 rows x 64 bytes), two
+      // box pairs per warp: the stores of chunk c drain under the arithmetic of chunk c + 1
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t buf = (stores & 1u) * 8192u;
+      for (int c = 0; c < 4; ++c) {
+        const int cl = half * 128 + 32 * c;
+        tc_ld32(acc + uint32_t(32 * c), v);
+        if (c == 3) {  // last TMEM read of this tile: the accumulator may be overwritten by tile it + 2
+          tc_fence_before();
+          mbar_arrive(acc_empty(s));
+        }
+        uint32_t wh[16], wl[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = *reinterpret_cast<const float4*>(col + cl + 4 * j);
+          const float4 b = *reinterpret_cast<const float4*>(col + kFtD + cl + 4 * j);
+          const float2 y0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), nm), rs), make_float2(g.x, g.y), make_float2(b.x, b.y));
+          const float2 y1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), nm), rs), make_float2(g.z, g.w), make_float2(b.z, b.w));
+          ft_split2(y0, wh[2 * j], wl[2 * j]);
+          ft_split2(y1, wh[2 * j + 1], wl[2 * j + 1]);
+        }
+        const uint32_t buf = (stores & 1u) * 4096u;
         if (stores >= 2) {  // the box pair last written into this buffer has been read out
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int cl = half * 128 + 64 * i + 32 * hh;
-          tc_ld32(acc + uint32_t(64 * i + 32 * hh), v);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 g = *reinterpret_cast<const float4*>(col + kFtD + cl + j);
-            const float4 b = *reinterpret_cast<const float4*>(col + 2 * kFtD + cl + j);
-            v[j] = (v[j] - mean) * rstd * g.x + b.x;
-            v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
-            v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
-            v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 hi, lo;
-            split8<SCATT_PLANE_F16>(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]),
-                                    make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]), hi, lo);
-            const uint32_t off = uint32_t(lane * 128 + (((4 * hh + j) ^ (lane & 7)) << 4));
-            *reinterpret_cast<uint4*>(obuf + buf + off) = hi;
-            *reinterpret_cast<uint4*>(obuf + buf + 4096u + off) = lo;
-          }
-        }
-        if (i == 1) {  // last TMEM read of this tile: the accumulator may be overwritten by tile it + 2
-          tc_fence_before();
-          mbar_arrive(acc_empty(s));
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = uint32_t(lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(obuf + buf + off) = make_uint4(wh[4 * j], wh[4 * j + 1], wh[4 * j + 2], wh[4 * j + 3]);
+          *reinterpret_cast<uint4*>(obuf + buf + 2048u + off) = make_uint4(wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !(SCATT_FT_ABLATE && (P.ablate & 4))) {
-          tma_store_3d(&P.map_out[pi], obuf_addr + buf, half * 128 + 64 * i, int(m0) + quad * 32, 0);  // rows past M are clipped
+          tma_store_3d(&P.map_out[pi], obuf_addr + buf, cl, int(m0) + quad * 32, 0);  // rows past M are clipped
+          tma_store_3d(&P.map_out[pi], obuf_addr + buf + 2048u, cl, int(m0) + quad * 32, 1);
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         ++stores;
@@ -326,10 +405,15 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
 
 // Returns SCATT_OK after launching, or a positive value when the request is outside this kernel's envelope
 // (the caller then runs the CUDA-core kernel): fp32 outputs, the exact gathered copy, bf16 planes, tiny inputs.
-int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_frontend_stream* streams, int n, int fmt, cudaStream_t s) {
+int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_frontend_stream* streams, int n, int max_pos, int fmt, bool force,
+                       cudaStream_t s) {
   const int64_t M = int64_t(B) * T;
-  if (fmt != SCATT_PLANE_F16 || M < 128 || M > 0x7fffffff - 128) return 1;
+  // below two tiles per CTA the one-off staging of the pair's weights and the serial gather -> MMA -> epilogue chain of a
+  // CTA's only tile cost more than the CUDA-core kernel takes (B = 8: 30 us against 25 us)
+  const int64_t min_rows = force ? 128 : int64_t(2) * 128 * (148 / (2 * n));
+  if (fmt != SCATT_PLANE_F16 || M < min_rows || M > 0x7fffffff - 128) return 1;
   for (int i = 0; i < n; ++i) {
+    if (streams[i].n_joints > 31) return 1;  // one A column carries the bias
     if (streams[i].gathered || streams[i].out[0] || streams[i].out[1] || !streams[i].out_planes[0] || !streams[i].out_planes[1]) return 1;
     if ((reinterpret_cast<uintptr_t>(streams[i].pos[0]) | reinterpret_cast<uintptr_t>(streams[i].pos[1])) & 15) return 1;
   }
@@ -346,8 +430,10 @@ int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_fronten
       q.joint_idx = streams[i].joint_idx, q.n_joints = streams[i].n_joints, q.coord = streams[i].coord[br];
       q.wt = streams[i].map_wt[br], q.bias = streams[i].map_b[br], q.pos = streams[i].pos[br];
       q.ln_g = streams[i].ln_g[br], q.ln_b = streams[i].ln_b[br];
-      const int rc = encode_planes_map(&P.map_out[2 * i + br], streams[i].out_planes[br], M, kFtD, 32, fmt, 2);
+      const int rc = encode_out_maps(nullptr, &P.map_out[2 * i + br], nullptr, 0, streams[i].out_planes[br], M, kFtD, fmt);
       if (rc != SCATT_OK) return rc;
+      const int rc2 = encode_out_maps(&P.map_pos[2 * i + br], nullptr, const_cast<float*>(q.pos), kFtD, nullptr, int64_t(max_pos) + 2, kFtD, fmt);
+      if (rc2 != SCATT_OK) return rc2;
     }
   static PerDeviceFlag attr_done;
   if (!attr_done.load()) {

@@ -519,10 +519,12 @@ int launch_frontend(const float* kp, int B, int T, int K, int D, const scatt_fro
     if (streams[i].n_joints > max_nj) max_nj = streams[i].n_joints;
   }
   if (int64_t(B) * T == 0) return SCATT_OK;
-  {  // planes-only output on the tensor-core engine: the mapping runs on tcgen05 (frontend_tc.cu); SCATT_FRONTEND_TC=0 keeps the CUDA-core kernel
-    static const bool tc_off = [] { const char* e = std::getenv("SCATT_FRONTEND_TC"); return e && e[0] == '0'; }();
-    if (!tc_off) {
-      const int rc = launch_frontend_tc(kp, B, T, K, streams, n, fmt, s);
+  {  // planes-only output of large batches: the mapping runs on tcgen05 (frontend_tc.cu).  SCATT_FRONTEND_TC=0 keeps the
+     // CUDA-core kernel, =2 takes the tensor-core kernel from 128 frames up (tests, sweeps); read per launch
+    const char* e = std::getenv("SCATT_FRONTEND_TC");
+    const int mode = e ? std::atoi(e) : 1;
+    if (mode != 0) {
+      const int rc = launch_frontend_tc(kp, B, T, K, streams, n, max_pos, fmt, mode == 2, s);
       if (rc <= 0) return rc;  // launched (or failed); > 0: outside that kernel's envelope
     }
   }

@@ -477,8 +477,9 @@ def test_rowwise_layernorm_widths():
         assert float((out.f32.double() - ref).abs().max()) <= 1e-5
 
 
-@pytest.mark.parametrize("B,T", [(8, 200), (3, 50), (5, 77), (1, 128), (2, 300)])
-def test_frontend_tensor_core(B, T):
+@pytest.mark.parametrize("B,T", [(8, 200), (3, 50), (5, 77), (1, 128), (2, 300), (40, 200)])
+def test_frontend_tensor_core(B, T, monkeypatch):
+    monkeypatch.setenv("SCATT_FRONTEND_TC", "2")  # from 128 frames up (the default hands batches below ~31 x 200 to the CUDA-core kernel)
     """Planes-only output of >= 128 frames runs the mapping on tcgen05 (frontend_tc_kernel): oracle parity within the
     split-plane class (hi + lo carries 22 bits), every tile shape: M tail, sequences wrapping inside a tile, one and
     two k-steps (6 / 21 joints), an unsorted index list, both self_attn_x settings."""

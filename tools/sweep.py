@@ -164,7 +164,9 @@ def membound_sweep(args):
                 idx = model._joint_idx(torch.device(dev))
             kp = kp.to(dev).contiguous()
             nbytes = B * T * (48 * 8 + 6 * 256 * 4)  # 384 B of used joints in, 6 branches x 256 x (hi + lo plane) out
-            row("frontend_kernel" + (" (compact input)" if compact else ""), f"B={B} T={T} K={kp.shape[2]}", nbytes,
+            frontend_forward(prec, mods, kp, idx, B, T)
+            sym = L.load().scatt_last_kernel().decode()  # frontend_kernel<R> (CUDA cores) or frontend_tc_kernel (tcgen05, large batches)
+            row(sym + (" (compact input)" if compact else ""), f"B={B} T={T} K={kp.shape[2]}", nbytes,
                 lambda: frontend_forward(prec, mods, kp, idx, B, T))
             del kp
     for B in (8, 256, 1024):
