@@ -88,6 +88,12 @@ int scatt_debug_set_trace(void* dev_buf);
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale,
                        void* planes, int plane_fmt, void* stream);
 
+/* Hint: pull `n` static device buffers (packed weight planes; 16-byte aligned, < 2 GiB each) into L2 with
+ * cp.async.bulk.prefetch.L2, one launch per 1024 buffers.  The reference has no counterpart (ATen leaves cache
+ * residency to the hardware); MSCAEncoder issues it on a parallel graph branch at the top of a small-batch step so
+ * that the ~60 dependent launches that follow do not each pay DRAM latency on their first weight tile. */
+int scatt_l2_prefetch(const void* const* ptrs, const int64_t* nbytes, int n, void* stream);
+
 /* ------------------------------------------------------------------ K1: front end */
 
 /* One anatomical stream of the fused front end.  Replaces, in one pass over

@@ -27,7 +27,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
-    "scatt_split_planes", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
+    "scatt_split_planes", "scatt_l2_prefetch", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_fusion_attention_planes",
     "scatt_fusion_attention_planes_supported", "scatt_pool_pairs", "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
@@ -97,6 +97,7 @@ def _declare(lib):
     lib.scatt_debug_set_trace.argtypes = [vp]
     lib.scatt_debug_set_trace.restype = i32
     lib.scatt_split_planes.argtypes = [vp, i64, i64, i64, f32, vp, i32, vp]
+    lib.scatt_l2_prefetch.argtypes = [C.POINTER(vp), C.POINTER(C.c_int64), i32, vp]
     lib.scatt_frontend.argtypes = [vp, i32, i32, i32, i32, C.POINTER(FrontendStream), i32, i32, i32, vp]
     lib.scatt_posembed_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.scatt_linear.argtypes = [C.POINTER(LinearProblem), i32, i64, i32, i32, i64, i64, i64, C.POINTER(Epilogue), i32, i32,

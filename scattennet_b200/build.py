@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscatt.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["api.cu", "rowwise.cu", "frontend_tc.cu", "gemm_simt.cu", "gemm_tc.cu", "block_tc.cu", "attention.cu", "attention_tc.cu", "attention_fa.cu", "fusion_tc.cu", "lstm.cu", "heads.cu", "ctc.cu", "peer.cu"]
+SOURCES = ["api.cu", "rowwise.cu", "frontend_tc.cu", "prefetch.cu", "gemm_simt.cu", "gemm_tc.cu", "block_tc.cu", "attention.cu", "attention_tc.cu", "attention_fa.cu", "fusion_tc.cu", "lstm.cu", "heads.cu", "ctc.cu", "peer.cu"]
 HEADERS = ["common.cuh", "tc_ptx.cuh", "tc_epi.cuh", "tc_host.cuh", os.path.join("..", "..", "include", "scatt.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

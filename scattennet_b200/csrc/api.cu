@@ -80,6 +80,11 @@ int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, 
   return launch_split_planes(x, rows, cols, ldx, scale, planes, plane_fmt, as_stream(stream));
 }
 
+int scatt_l2_prefetch(const void* const* ptrs, const int64_t* nbytes, int n, void* stream) {
+  SCATT_REQUIRE(n == 0 || (ptrs && nbytes), "l2_prefetch: null argument");
+  return launch_l2_prefetch(ptrs, nbytes, n, as_stream(stream));
+}
+
 int scatt_frontend(const float* keypoints, int B, int T, int K, int D, const scatt_frontend_stream* streams_host,
                    int n_streams, int max_pos, int plane_fmt, void* stream) {
   SCATT_REQUIRE(keypoints && streams_host && fmt_ok(plane_fmt), "frontend: null pointer or bad plane format");

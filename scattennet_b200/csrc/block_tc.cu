@@ -75,6 +75,7 @@ constexpr uint32_t kStageBytes = 32768;  // [256 x 64] one plane, or [128 x 64] 
 constexpr uint32_t kKbBytes = 32768;     // one A k-block: hi tile + lo tile
 constexpr uint32_t kHABytes = 4 * kKbBytes;
 constexpr uint32_t kTmemCols = 512, kAccO = 0, kAccB = 256;
+__device__ constexpr int kOrder[4] = {0, 2, 1, 3};  // k-blocks of h in the order LayerNorm1 completes them (both column halves advance together)
 constexpr int kTraceSlots = 160;  // 32-bit stamps: 0..63 phases, 64 + i / 112 + i ring item i issued / taken (i < 48)
 
 struct BlkProblem {
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
   auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (kStages + s); };
   const uint32_t ctx_bar = bar0 + 8u * 2 * kStages;  // [4], one per ctx k-block
-  const uint32_t oproj_full = ctx_bar + 32u, h_ready = oproj_full + 8u;
-  const uint32_t fc1_full = h_ready + 8u;   // [2]
+  const uint32_t oproj_full = ctx_bar + 32u, h_ready = oproj_full + 8u;  // h_ready [2]: k-blocks {0, 2} / {1, 3} of h are in hA
+  const uint32_t fc1_full = h_ready + 16u;  // [2]
   const uint32_t g_ready = fc1_full + 16u;  // [2]
   const uint32_t out_full = g_ready + 16u, tile_done = out_full + 8u;
   const uint32_t peer_free = tile_done + 8u, partial_full = peer_free + 8u, xfer_done = partial_full + 8u, stats_full = xfer_done + 8u;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     for (uint32_t k = 0; k < 4; ++k) mbar_init(ctx_bar + 8u * k, 1);
     mbar_init(oproj_full, 1);
     mbar_init(h_ready, 32 * kEpiWarps);
+    mbar_init(h_ready + 8u, 32 * kEpiWarps);
     for (uint32_t b = 0; b < 2; ++b) {
       mbar_init(fc1_full + 8u * b, 1);
       mbar_init(g_ready + 8u * b, 32 * kEpiWarps);
@@ -298,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       for (int kb = 1; kb < 4; ++kb) put_wo(kb);
       auto fc1_items = [&](int i) {
         const int j = chunk_of(i);
-        for (int kb = 0; kb < 4; ++kb) put(&P.map_w1[g], kb * 64, j * 128, 0, b_lo ? kStageBytes : kTileBytes);
+        for (int q = 0; q < 4; ++q) put(&P.map_w1[g], kOrder[q] * 64, j * 128, 0, b_lo ? kStageBytes : kTileBytes);  // the order LayerNorm1 finishes them in
       };
       auto fc2_items = [&](int i) {
         const int j = chunk_of(i);
@@ -389,18 +391,23 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       if (elect_one()) tc_commit(oproj_full);
       __syncwarp();
       if (lane == 0 && ti == 0) trace(2);
-      mbar_wait(h_ready, tpar);  // h is in hA (A operand of fc1), h + b2 in accO
-      tc_fence_after();
-      if (lane == 0 && ti == 0) trace(3);
-      auto issue_fc1 = [&](int j) {  // accB[j & 1][128 x 128] = h W1[chunk j]^T
+      // h arrives in hA in two halves: LayerNorm1 finishes k-blocks {0, 2} (columns [0, 64) and [128, 192)) half way through
+      // its second pass - the first chunk's MMAs over those start under the rest of the pass
+      auto issue_fc1 = [&](int j, bool first) {  // accB[j & 1][128 x 128] = h W1[chunk j]^T
         const uint32_t d = tmem + kAccB + uint32_t((j & 1) * 128);
         if (lane == 0 && ti == 0 && j < 8) trace(20 + j);
-        for (int kb = 0; kb < 4; ++kb) {
+        for (int q = 0; q < 4; ++q) {
+          const int kb = kOrder[q];
+          if (first && (q == 0 || q == 2)) {
+            mbar_wait(h_ready + 8u * uint32_t(q >> 1), tpar);
+            tc_fence_after();
+            if (lane == 0 && ti == 0 && q == 2) trace(3);
+          }
           const uint32_t s = take();
           const uint64_t ah = umma_desc_sw128(hA + kb * kKbBytes), al = umma_desc_sw128(hA + kb * kKbBytes + kTileBytes);
           const uint64_t bh = umma_desc_sw128(ring + s * kStageBytes), bl = umma_desc_sw128(ring + s * kStageBytes + kTileBytes);
           if (elect_one()) {
-            uint32_t acc = kb > 0 ? 1u : 0u;
+            uint32_t acc = q > 0 ? 1u : 0u;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t adv = uint64_t(kk * 2);
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
               acc = 1;
             }
             tc_commit(empty_bar(s));
-            if (kb == 3) tc_commit(fc1_full + 8u * uint32_t(j & 1));
+            if (q == 3) tc_commit(fc1_full + 8u * uint32_t(j & 1));
           }
           __syncwarp();
         }
@@ -460,13 +467,16 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       // tcgen05.mma executes in issue order: fc1(j + 1) can be issued before fc2(j - 1) has read its operand chunk
       // because it writes the OTHER accumulator, and fc1(j + 2) after fc2(j) reuses that chunk's columns safely
       if (nchunk > 0) {
-        issue_fc1(0);
+        issue_fc1(0, true);
         for (int i = 1; i < nchunk; ++i) {
-          issue_fc1(i);
+          issue_fc1(i, false);
           issue_fc2(i - 1, false);
         }
         issue_fc2(nchunk - 1, true);
       } else {  // a cluster CTA without a hidden chunk (F = 128): its partial sum is the zero it started from
+        mbar_wait(h_ready, tpar);
+        mbar_wait(h_ready + 8u, tpar);
+        tc_fence_after();
         if (elect_one()) tc_commit(out_full);
         __syncwarp();
       }
@@ -502,23 +512,28 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       if (tid == 0 && ti == 0) trace(5);
       {
         float v[32];
-        float shift = 0.f, s1 = 0.f, s2 = 0.f;
+        float shift = 0.f;
+        float2 s1 = make_float2(0.f, 0.f), s2 = s1;
+        // pass 1: + bo (written back, so that the second pass does not fetch it again), shifted sums; packed fp32 arithmetic
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
           const int cl = hf * 128 + i * 32;
           tc_ld32(tmem + kAccO + lane_addr + cl, v);
           add_cols_g(v, Q.bo + cl);
           if (i == 0) shift = v[0];
+          const float2 ns = make_float2(-shift, -shift);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = v[j] - shift;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
+          for (int j = 0; j < 32; j += 2) {
+            const float2 d = __fadd2_rn(make_float2(v[j], v[j + 1]), ns);
+            s1 = __fadd2_rn(s1, d);
+            s2 = __ffma2_rn(d, d, s2);
           }
+          tc_st32(tmem + kAccO + lane_addr + cl, v);
         }
         if (tid == 0 && ti == 0) trace(18);
-        const float2 mr = combine_stats(tmem_x, hf, shift, s1, s2, P.eps);
+        const float2 mr = combine_stats(tmem_x, hf, shift, s1.x + s1.y, s2.x + s2.y, P.eps);
         if (tid == 0 && ti == 0) trace(19);
+        const float2 nm = make_float2(-mr.x, -mr.x), rs = make_float2(mr.y, mr.y);
         uint8_t* hrow = sm + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll 1
         for (int i = 0; i < 4; ++i) {
@@ -526,13 +541,11 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
           tc_ld32(tmem + kAccO + lane_addr + cl, v);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bo = __ldg(reinterpret_cast<const float4*>(Q.bo + cl + j));
             const float4 gg = __ldg(reinterpret_cast<const float4*>(Q.g1 + cl + j));
             const float4 bb = __ldg(reinterpret_cast<const float4*>(Q.be1 + cl + j));
-            v[j] = (v[j] + bo.x - mr.x) * mr.y * gg.x + bb.x;
-            v[j + 1] = (v[j + 1] + bo.y - mr.x) * mr.y * gg.y + bb.y;
-            v[j + 2] = (v[j + 2] + bo.z - mr.x) * mr.y * gg.z + bb.z;
-            v[j + 3] = (v[j + 3] + bo.w - mr.x) * mr.y * gg.w + bb.w;
+            const float2 y0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+            const float2 y1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+            v[j] = y0.x, v[j + 1] = y0.y, v[j + 2] = y1.x, v[j + 3] = y1.y;
           }
           // K-major 128-byte-swizzled A tiles: k-block cl / 64, 16-byte chunk (cl % 64) / 8 + q of row `row`
           uint8_t* kbp = hrow + (cl >> 6) * kKbBytes;
@@ -553,10 +566,12 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           tc_st32(tmem + kAccO + lane_addr + cl, v);
+          if (i & 1) {  // k-blocks {0, 2} after the first two chunks, {1, 3} after the last two
+            fence_proxy_async();  // generic-proxy writes of h -> visible to the tensor core's operand reads
+            tc_fence_before();
+            mbar_arrive(h_ready + 8u * uint32_t(i >> 1));
+          }
         }
-        fence_proxy_async();  // generic-proxy writes of h -> visible to the tensor core's operand reads
-        tc_fence_before();
-        mbar_arrive(h_ready);
       }
       if (tid == 0 && ti == 0) trace(6);
 
@@ -682,6 +697,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         const float rstd = rsqrtf(m2 * (1.0f / float(DM)) + P.eps);
         if (tid == 0 && ti == 0) trace(61);
         const uint32_t poff = Q.y ? 4096u : 0u;
+        const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           float* v = i == 0 ? v0 : v1;
@@ -690,10 +706,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
           for (int j = 0; j < 32; j += 4) {
             const float4 gg = __ldg(reinterpret_cast<const float4*>(Q.g2 + cl + j));
             const float4 bb = __ldg(reinterpret_cast<const float4*>(Q.be2 + cl + j));
-            v[j] = (v[j] - mean) * rstd * gg.x + bb.x;
-            v[j + 1] = (v[j + 1] - mean) * rstd * gg.y + bb.y;
-            v[j + 2] = (v[j + 2] - mean) * rstd * gg.z + bb.z;
-            v[j + 3] = (v[j + 3] - mean) * rstd * gg.w + bb.w;
+            const float2 y0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), nm2), rs2), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+            const float2 y1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), nm2), rs2), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+            v[j] = y0.x, v[j + 1] = y0.y, v[j + 2] = y1.x, v[j + 3] = y1.y;
           }
           // output boxes in this warp's landing boxes (read above): planes only - one 4 KB box pair per chunk; with an
           // fp32 output as well the 8 KB buffer is reused after the first chunk's boxes have been read out
@@ -757,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
           }
         }
         const float2 mr = combine_stats(tmem_x, hf, shift, s1, s2, P.eps);
+        const float2 nm2 = make_float2(-mr.x, -mr.x), rs2 = make_float2(mr.y, mr.y);
         const uint32_t obase = uint32_t(warp - 2) * 16384u;  // 2 x 8 KB: [fp32 box 4 KB][hi 2 KB][lo 2 KB]
         const uint32_t poff = Q.y ? 4096u : 0u;
 #pragma unroll 1
@@ -767,10 +783,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
           for (int j = 0; j < 32; j += 4) {
             const float4 gg = __ldg(reinterpret_cast<const float4*>(Q.g2 + cl + j));
             const float4 bb = __ldg(reinterpret_cast<const float4*>(Q.be2 + cl + j));
-            v[j] = (v[j] - mr.x) * mr.y * gg.x + bb.x;
-            v[j + 1] = (v[j + 1] - mr.x) * mr.y * gg.y + bb.y;
-            v[j + 2] = (v[j + 2] - mr.x) * mr.y * gg.z + bb.z;
-            v[j + 3] = (v[j + 3] - mr.x) * mr.y * gg.w + bb.w;
+            const float2 y0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), nm2), rs2), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y));
+            const float2 y1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), nm2), rs2), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w));
+            v[j] = y0.x, v[j + 1] = y0.y, v[j + 2] = y1.x, v[j + 3] = y1.y;
           }
           const uint32_t buf = uint32_t(i & 1) * 8192u;
           if (i >= 2) {  // the box written two chunks ago must have been read out by the TMA engine

@@ -37,13 +37,15 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
     if (FMT == SCATT_PLANE_F16) {
       const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
       const float2 back = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
+      const float2 d = __fadd2_rn(make_float2(x[2 * e], x[2 * e + 1]), make_float2(-back.x, -back.y));  // packed: one FADD2
+      const __half2 ll = __floats2half2_rn(d.x, d.y);
       h[e] = *reinterpret_cast<const uint32_t*>(&hh);
       l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     } else {
       const __nv_bfloat162 hh = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
       const float2 back = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - back.x, x[2 * e + 1] - back.y);
+      const float2 d = __fadd2_rn(make_float2(x[2 * e], x[2 * e + 1]), make_float2(-back.x, -back.y));
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(d.x, d.y);
       h[e] = *reinterpret_cast<const uint32_t*>(&hh);
       l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }

@@ -295,6 +295,31 @@ def pack_of(owner: torch.nn.Module, tag: str, linears: Sequence[torch.nn.Linear]
     return ent
 
 
+L2_PREFETCH = os.environ.get("SCATT_L2_PREFETCH", "1") != "0"  # False: no weight prefetch branch at the top of a small-batch step
+
+
+def weight_planes_of(root: torch.nn.Module, prec: Precision) -> List[torch.Tensor]:
+    """The split-plane copies of every packed weight under ``root`` that exist for this precision (module order)."""
+    out = []
+    for m in root.modules():
+        for pk in m.__dict__.get("_scatt_packs", {}).values():
+            p = pk._planes.get(prec.plane_fmt)
+            if p is not None:
+                out.append(p)
+    return out
+
+
+def l2_prefetch(tensors: Sequence[torch.Tensor]) -> None:
+    """``scatt_l2_prefetch``: hint the listed device buffers into L2 (one launch per 1024 buffers, no data dependency)."""
+    n = len(tensors)
+    if n == 0:
+        return
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    sizes = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in tensors])
+    with _timed("l2_prefetch_kernel", 0.0, float(sum(sizes))):
+        L.check(L.load().scatt_l2_prefetch(ptrs, sizes, n, _stream()), "scatt_l2_prefetch")
+
+
 # ----------------------------------------------------------------------------- ops
 
 

@@ -147,6 +147,15 @@ class MSCAEncoder(nn.Module):
         mods = [self.body_encoder, self.left_encoder, self.right_encoder]
         # a compact tensor (only the joints the three streams use, see forward_host) carries remapped indices
         idx = self._compact_idx(keypoints.device)[1] if compact else self._joint_idx(keypoints.device)
+        # small batches: ~60 dependent launches each pay DRAM latency on their first weight tile when the step starts with
+        # a cold L2; one launch on a parallel branch hints all weight planes (~35 MB) into L2 (csrc/prefetch.cu).  Large
+        # batches stream more activations through L2 than it holds - the hint would be evicted before use.
+        pf = None
+        if F_.L2_PREFETCH and prec.uses_planes and b * t <= 8192:
+            planes = F_.weight_planes_of(self, prec)
+            if planes:
+                with F_.SideBranch([]) as pf:
+                    F_.l2_prefetch(planes)
         blocks = streams_forward(prec, mods, keypoints, idx, key_mask, b, t)
         (body, left, right), tp = blocks[-1]
         lg, heads_branch = None, None
@@ -172,6 +181,8 @@ class MSCAEncoder(nn.Module):
             if self.alignment:
                 al = alignment_forward(prec, rh.fuse_alignment_head, fuse, b, tp, clamp=50.0)
                 out["alignment_gloss_logits"] = al.f32.view(b, tp, -1)
+        if pf is not None:
+            pf.join()
         return out
 
     def forward(self, keypoints: torch.Tensor, mask: torch.Tensor, with_heads: bool = True,
