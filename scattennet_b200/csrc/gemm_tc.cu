@@ -212,7 +212,9 @@ __device__ __forceinline__ void box_add(const EpiCtx& E, const uint8_t* box, flo
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 t = *reinterpret_cast<const float4*>(box + r * 128 + ((j ^ (r & 7)) << 4));
-    v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
+    const float2 a = __fadd2_rn(make_float2(v[4 * j], v[4 * j + 1]), make_float2(t.x, t.y));
+    const float2 b = __fadd2_rn(make_float2(v[4 * j + 2], v[4 * j + 3]), make_float2(t.z, t.w));
+    v[4 * j] = a.x, v[4 * j + 1] = a.y, v[4 * j + 2] = b.x, v[4 * j + 3] = b.y;
   }
 }
 
@@ -397,20 +399,23 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     // with the peer CTA's half of the row.
     constexpr float kHalfN = float(BN / 2);
     const bool late_res = late_res_any && ep.residual_mode == SCATT_RES_BEFORE_LN;
-    float shift = 0.f, s1 = 0.f, s2 = 0.f;
+    float shift = 0.f;
+    float2 s1p = make_float2(0.f, 0.f), s2p = s1p;
 #pragma unroll 1
     for (int i = 0; i < kMine; ++i) {
       const int cl = (half * kMine + i) * 32;
       tc_ld32(tmem_acc + cl, v);
       if (chunk_pre(P, Q, E, v, cl, n0 + cl, late_res)) tc_st32(tmem_acc + cl, v);
       if (i == 0) shift = v[0];
+      const float2 ns = make_float2(-shift, -shift);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float d = v[j] - shift;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 d = __fadd2_rn(make_float2(v[j], v[j + 1]), ns);
+        s1p = __fadd2_rn(s1p, d);
+        s2p = __ffma2_rn(d, d, s2p);
       }
     }
+    const float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
     const float dm = s1 / kHalfN;
     const float my_mean = shift + dm, my_m2 = fmaxf(s2 - s1 * dm, 0.f);
     stats[half * BM + row_in_tile] = make_float2(my_mean, my_m2);
@@ -452,16 +457,16 @@ __device__ __forceinline__ void epilogue_rows(const TcParams& P, const TcProblem
     const float rstd = rsqrtf(var + ep.ln_eps);
     const bool res_after = ep.residual_mode == SCATT_RES_AFTER_LN;
     const bool res_global = res_after && E.res_box == nullptr;  // cluster kernels find the residual staged in smem
+    const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);  // packed fp32 arithmetic: half the issue slots
     auto normalise = [&](int cl) {
       tc_ld32(tmem_acc + cl, v);
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 g = *reinterpret_cast<const float4*>(E.col_g + cl + j);
         const float4 b = *reinterpret_cast<const float4*>(E.col_b + cl + j);
-        v[j] = (v[j] - mean) * rstd * g.x + b.x;
-        v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
-        v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
-        v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
+        const float2 y0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), nm2), rs2), make_float2(g.x, g.y), make_float2(b.x, b.y));
+        const float2 y1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), nm2), rs2), make_float2(g.z, g.w), make_float2(b.z, b.w));
+        v[j] = y0.x, v[j + 1] = y0.y, v[j + 2] = y1.x, v[j + 3] = y1.y;
       }
     };
     if constexpr (LN >= 2) {

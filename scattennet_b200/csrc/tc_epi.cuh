@@ -24,7 +24,9 @@ __device__ __forceinline__ void add_cols(float* v, const float* __restrict__ p) 
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 t = *reinterpret_cast<const float4*>(p + j);
-    v[j] += t.x, v[j + 1] += t.y, v[j + 2] += t.z, v[j + 3] += t.w;
+    const float2 a = __fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(t.x, t.y));
+    const float2 b = __fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(t.z, t.w));
+    v[j] = a.x, v[j + 1] = a.y, v[j + 2] = b.x, v[j + 3] = b.y;
   }
 }
 
