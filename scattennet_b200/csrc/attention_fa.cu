@@ -322,12 +322,19 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
         } else {
+          // 8-key groups past the last key of the tile (T = 200: 24 of the 32 keys of the last chunk) are skipped
+          const int live = min(kbox, nk - blk * kbox) - c * 32;  // keys of this chunk the tile may see (warp-uniform)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float kc = cls[cc * 32 + j];
-            float s = kc == 0.f ? v[j] : kc;
-            if (key0 + j > jmax) s = -INFINITY;
-            mx = fmaxf(mx, s);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            if (8 * g8 < live) {
+#pragma unroll
+              for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+                const float kc = cls[cc * 32 + j];
+                float s = kc == 0.f ? v[j] : kc;
+                if (key0 + j > jmax) s = -INFINITY;
+                mx = fmaxf(mx, s);
+              }
+            }
           }
         }
       }
@@ -366,14 +373,23 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
               v[j] = p0, v[j + 1] = p1, v[j + 2] = p2, v[j + 3] = p3;
             }
           } else {
+            const int live = min(kbox, nk - blk * kbox) - c * 32;  // as in the max pass: absent keys have probability 0
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float kc = cls[cc * 32 + j];
-              float s = kc == 0.f ? v[j] : kc;
-              if (key0 + j > jmax) s = -INFINITY;
-              const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
-              l += p;
-              v[j] = p;
+            for (int g8 = 0; g8 < 4; ++g8) {
+              if (8 * g8 < live) {
+#pragma unroll
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+                  const float kc = cls[cc * 32 + j];
+                  float s = kc == 0.f ? v[j] : kc;
+                  if (key0 + j > jmax) s = -INFINITY;
+                  const float p = ex2((s - mx) * kLog2e);  // subtract first: s and mx may both be -FLT_MAX
+                  l += p;
+                  v[j] = p;
+                }
+              } else {
+#pragma unroll
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j) v[j] = 0.f;
+              }
             }
           }
           float w[32];
