@@ -311,7 +311,9 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
       mbar_wait(bar_s, s_uses++ & 1);
       if (threadIdx.x == 0 && blk == 0) trace(4);
       tc_fence_after();
-      const int nch = live ? (min(kbox, nk - blk * kbox) + 31) >> 5 : 0;  // chunks holding a key this tile may see
+      int nch = live ? (min(kbox, nk - blk * kbox) + 31) >> 5 : 0;  // chunks holding a key this tile may see
+      // causal: a chunk that starts past this warp's last query row holds future keys only (probability 0 for every row)
+      if (causal) nch = min(nch, max(0, (m0 + quad * 32 + 31 - blk * kbox) >> 5) + 1);
 #pragma unroll 1
       for (int c = half; c < nch; c += 2) {
         tc_ld32(tmem_s + lane_addr + c * 32, v);
@@ -359,7 +361,12 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
 #pragma unroll 1
       for (int it = 0; it < niter; ++it) {
         const int c = 2 * it + half;
-        if (c < nch && live) {
+        if (c < nch && live && causal && blk * kbox + c * 32 > m0 + quad * 32 + 31) {
+          float z[32];  // future keys only for this warp's rows: P = 0 without reading S
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0.f;
+          tc_st32(tmem_s + lane_addr + c * 32, z);
+        } else if (c < nch && live) {
           tc_ld32(tmem_s + lane_addr + c * 32, v);
           const int cc = blk * nchunk + c, key0 = blk * kbox + c * 32;
           const bool fast = chunk_valid[cc] != 0u && (!causal || key0 + 31 <= m0 + quad * 32);
