@@ -477,6 +477,21 @@ def test_rowwise_layernorm_widths():
         assert float((out.f32.double() - ref).abs().max()) <= 1e-5
 
 
+def test_l2_prefetch_is_a_pure_hint():
+    """scatt_l2_prefetch touches no data: buffers of any 16-byte-multiple size (also > one 16 KB piece, also empty),
+    one launch for hundreds of buffers; a misaligned buffer is refused."""
+    ts = [torch.arange(n, dtype=torch.float32, device=DEV) for n in (4, 4096, 5000, 70000)] + [torch.empty(0, device=DEV)]
+    ts += [torch.full((256,), float(i), device=DEV) for i in range(300)]
+    before = [t.clone() for t in ts]
+    n0 = L.launch_count()
+    F_.l2_prefetch(ts)
+    torch.cuda.synchronize()
+    assert L.launch_count() - n0 == 1 and L.load().scatt_last_kernel().decode() == "l2_prefetch_kernel"
+    assert all(torch.equal(a, b) for a, b in zip(ts, before))
+    with pytest.raises(L.ScattError):
+        F_.l2_prefetch([torch.zeros(64, device=DEV)[1:]])
+
+
 @pytest.mark.parametrize("B,T", [(8, 200), (3, 50), (5, 77), (1, 128), (2, 300), (40, 200)])
 def test_frontend_tensor_core(B, T, monkeypatch):
     monkeypatch.setenv("SCATT_FRONTEND_TC", "2")  # from 128 frames up (the default hands batches below ~31 x 200 to the CUDA-core kernel)
