@@ -4,7 +4,7 @@
 // when the step starts with a cold L2 (every bench step does: L2 is flushed between steps; a serving loop whose
 // activations of other requests passed through L2 sees the same): every launch pays DRAM latency on the first
 // stage of its operand ring.  One launch on a parallel graph branch at the top of the step issues
-// cp.async.bulk.prefetch.L2 over all weight planes (~35 MB: 6 us of HBM time) in module order, so the GEMMs that
+// cp.async.bulk.prefetch.L2 over all weight planes (~70 MB: 11 us of HBM time) in module order, so the GEMMs that
 // follow find them in the 126 MB L2.  No data moves into an SM, nothing waits on it: it is a hint, the step is
 // correct without it.
 #include "common.cuh"
