@@ -209,6 +209,27 @@ typedef struct scatt_block_problem {
 int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_t M, int D, int F, float ln_eps,
                      int plane_fmt, int terms, void* stream);
 int scatt_attn_block_supported(int64_t M, int D, int F);
+/* The causal layer in front of a merge layer as ONE launch: out_proj + residual + attn_layer_norm of
+ * CoordinateAttention(causal) (model/keypoint_module.py:62-66, no FeedForward on that branch) and the q_proj of the
+ * CoordinatesMerge layer that consumes it (CrossAttention.forward, model/attention.py:99-101: q = q_proj(h) * scaling).
+ *   h = LayerNorm(x + ctx Wo^T + bo) -> h_planes,   q = (h Wq^T + bq) * q_scale -> q_planes
+ * Same kernel as scatt_attn_block (h stays in shared memory as the A operand of the second product). D = N = 256. */
+typedef struct scatt_outq_problem {
+  const void* ctx_planes;      /* [2][M][D] attention output of the causal layer */
+  const void* residual_planes; /* [2][M][D] the causal layer's input x */
+  const void* wo_planes;       /* [2][D][D] out_proj.weight */
+  const float* bo;             /* [D] */
+  const float* ln_g;           /* [D] attn_layer_norm */
+  const float* ln_b;
+  const void* wq_planes;       /* [2][N][D] the merge layer's q_proj.weight */
+  const float* bq;             /* [N] */
+  void* h_planes;              /* out [2][M][D] */
+  void* q_planes;              /* out [2][M][N] */
+} scatt_outq_problem;
+
+int scatt_attn_out_q(const scatt_outq_problem* problems_host, int group, int64_t M, int D, int N, float ln_eps, float q_scale,
+                     int plane_fmt, int terms, void* stream);
+int scatt_attn_out_q_supported(int64_t M, int D, int N);
 /* Developer aid: 1 | 2 forces one CTA / a 2-CTA cluster per 128-row tile in scatt_attn_block, 0 restores the automatic
  * choice (clusters while there are at most 74 row tiles). */
 int scatt_debug_set_block_cluster(int cluster);

@@ -27,7 +27,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
-    "scatt_split_planes", "scatt_l2_prefetch", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_debug_set_block_cluster",
+    "scatt_split_planes", "scatt_l2_prefetch", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_attn_out_q", "scatt_attn_out_q_supported", "scatt_debug_set_block_cluster",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_fusion_attention_planes",
     "scatt_fusion_attention_planes_supported", "scatt_pool_pairs", "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
@@ -51,6 +51,11 @@ class LinearProblem(C.Structure):
         ("x", C.c_void_p), ("x_planes", C.c_void_p), ("w", C.c_void_p), ("w_planes", C.c_void_p), ("bias", C.c_void_p),
         ("residual", C.c_void_p), ("ln_g", C.c_void_p), ("ln_b", C.c_void_p), ("y", C.c_void_p), ("y_planes", C.c_void_p), ("residual_planes", C.c_void_p),
     ]
+
+
+class OutQProblem(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ctx_planes", "residual_planes", "wo_planes", "bo", "ln_g", "ln_b", "wq_planes", "bq",
+                                          "h_planes", "q_planes")]
 
 
 class BlockProblem(C.Structure):
@@ -109,6 +114,9 @@ def _declare(lib):
     lib.scatt_linear_workspace_bytes.restype = C.c_size_t
     lib.scatt_attn_block.argtypes = [C.POINTER(BlockProblem), i32, i64, i32, i32, f32, i32, i32, vp]
     lib.scatt_attn_block.restype = i32
+    lib.scatt_attn_out_q.argtypes = [C.POINTER(OutQProblem), i32, i64, i32, i32, f32, f32, i32, i32, vp]
+    lib.scatt_attn_out_q_supported.argtypes = [i64, i32, i32]
+    lib.scatt_attn_out_q_supported.restype = i32
     lib.scatt_attn_block_supported.argtypes = [i64, i32, i32]
     lib.scatt_attn_block_supported.restype = i32
     lib.scatt_debug_set_block_cluster.argtypes = [i32]

@@ -69,11 +69,12 @@ class BaseAttention(nn.Module):
 
 def attention_core(prec: Precision, mods: Sequence[BaseAttention], xq: List[Act], xkv: Optional[List[Act]], B: int, Tq: int,
                    Tk: int, kind: int, key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None,
-                   kv_views=None) -> List[Act]:
+                   kv_views=None, q_planes: Optional[List[Act]] = None) -> List[Act]:
     """Projections + softmax(QK^T + mask) V for a group of same-shaped modules
     (one per anatomical stream).  Returns the per-head context ``[B*Tq, D]``
     *before* ``out_proj``.  ``kv_views`` supplies precomputed ``(k, v)`` fp32
-    views (the merge ladder projects K/V of all layers in one GEMM)."""
+    views (the merge ladder projects K/V of all layers in one GEMM); ``q_planes`` an already projected and scaled q
+    (fast path only)."""
     d, h = mods[0].d_model, mods[0].num_heads
     scale = mods[0].scaling
     if (prec.uses_planes and additive is None and d // h == 16 and Tk <= F_.ATTN_PLANES_MAX_T
@@ -87,8 +88,11 @@ def attention_core(prec: Precision, mods: Sequence[BaseAttention], xq: List[Act]
             ks = [(t.planes, d) for t in qkv]
             vs = [(t.planes, 2 * d) for t in qkv]
         else:
-            packs = [F_.pack_of(m, "q", [m.q_proj]) for m in mods]
-            q = F_.linear(prec, xq, packs, ep_q, out_f32=False)
+            if q_planes is not None:  # already projected and scaled (scatt_attn_out_q: fused into the producing layer's tail)
+                q = q_planes
+            else:
+                packs = [F_.pack_of(m, "q", [m.q_proj]) for m in mods]
+                q = F_.linear(prec, xq, packs, ep_q, out_f32=False)
             qs = [(t.planes, 0) for t in q]
             if kv_views is None:
                 kv = cross_kv(prec, mods, xkv, planes=True)
@@ -97,6 +101,8 @@ def attention_core(prec: Precision, mods: Sequence[BaseAttention], xq: List[Act]
             else:
                 ks, vs = [kv[0] for kv in kv_views], [kv[1] for kv in kv_views]
         return F_.stream_attention_planes(prec, qs, ks, vs, B, Tq, Tk, h, kind, key_mask)
+    if q_planes is not None:
+        raise ValueError("attention_core: a precomputed q needs the plane path (tensor-core engine, key mask, T within range)")
     if xkv is None and kv_views is None:  # self / causal: one N = 3D GEMM
         packs = [F_.pack_of(m, "qkv", [m.q_proj, m.k_proj, m.v_proj]) for m in mods]
         qkv = F_.linear(prec, xq, packs, F_.make_epilogue(scale_cols=d, scale=scale), out_planes=False)

@@ -131,6 +131,16 @@ int scatt_attn_block(const scatt_block_problem* problems_host, int group, int64_
   return launch_attn_block(problems_host, group, M, D, F, ln_eps, plane_fmt, terms, as_stream(stream));
 }
 
+int scatt_attn_out_q(const scatt_outq_problem* problems_host, int group, int64_t M, int D, int N, float ln_eps, float q_scale,
+                     int plane_fmt, int terms, void* stream) {
+  SCATT_REQUIRE(problems_host && fmt_ok(plane_fmt), "attn_out_q: null pointer or bad plane format");
+  SCATT_REQUIRE(group >= 1 && group <= SCATT_MAX_GROUP, "attn_out_q: group must be 1..%d", SCATT_MAX_GROUP);
+  SCATT_REQUIRE(M >= 0, "attn_out_q: bad shape M=%lld", (long long)M);
+  return launch_attn_out_q(problems_host, group, M, D, N, ln_eps, q_scale, plane_fmt, terms, as_stream(stream));
+}
+
+int scatt_attn_out_q_supported(int64_t M, int D, int N) { return attn_out_q_supported(M, D, N) ? 1 : 0; }
+
 int scatt_debug_set_block_cluster(int cluster) { return debug_set_block_cluster(cluster); }
 
 int scatt_attn_block_supported(int64_t M, int D, int F) { return attn_block_supported(M, D, F) ? 1 : 0; }

@@ -96,6 +96,7 @@ struct alignas(64) BlkParams {
   int64_t M;
   int32_t F, nchunk, terms, fmt, groups, tiles_m;
   float eps;
+  float qscale;  // MODE 1: q = (h Wq^T + bq) * qscale
 };
 
 // shared memory map relative to the (1024-aligned) start of dynamic shared memory
@@ -178,8 +179,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
   __trap();
 }
 
-template <int FMT, int CL>
+// MODE 0: the whole layer tail (above).  MODE 1 (scatt_attn_out_q, the causal layer in front of a merge layer, reference
+// model/keypoint_module.py:62-66 followed by the q_proj of model/attention.py:99-101): out_proj + residual + LayerNorm as in
+// mode 0, h is ALSO stored to global memory (TMA stores straight out of the operand tiles in hA), and the "fc1 chunks" are
+// the merge layer's q projection - bias, q scaling, hi / lo split and TMA stores instead of GELU + fc2.  No second LayerNorm,
+// and in a 2-CTA cluster nothing to exchange: CTA r computes q columns [128 r, 128 r + 128).  Two ring stages; the third
+// stage's 32 KB are the epilogue warps' output boxes.
+template <int FMT, int CL, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_constant__ BlkParams P) {
+  constexpr uint32_t kNst = MODE == 1 ? 2u : uint32_t(kStages);  // ring stages in use
   extern __shared__ __align__(1024) uint8_t sm[];
   const uint32_t base = smem_u32(sm);
   const uint32_t hA = base, ring = base + kRingOff, bar0 = base + kBarOff;
@@ -266,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   if (warp == 0) {  // ================================================= TMA producer
     uint32_t it = 0;  // ring items issued so far (the ring runs across tile boundaries)
     auto put = [&](const CUtensorMap* map, int c0, int c1, int c2, uint32_t bytes) {  // one TMA operation into the next stage
-      const uint32_t s = it % kStages;
-      mbar_wait(empty_bar(s), ((it / kStages) & 1u) ^ 1u);
+      const uint32_t s = it % kNst;
+      mbar_wait(empty_bar(s), ((it / kNst) & 1u) ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), bytes);
         tma_load_3d(ring + s * kStageBytes, map, full_bar(s), c0, c1, c2);
@@ -313,9 +321,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         fc1_items(0);
         for (int i = 1; i < nchunk; ++i) {
           fc1_items(i);
-          fc2_items(i - 1);
+          if (MODE == 0) fc2_items(i - 1);
         }
-        fc2_items(nchunk - 1);
+        if (MODE == 0) fc2_items(nchunk - 1);
       }
       if (lane == 0 && ti == 0) trace(17);
     }
@@ -327,8 +335,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
     uint32_t it = 0;
     uint32_t gphase = 0;  // bit b: parity of the next completion of g_ready[b]
     auto take = [&]() -> uint32_t {  // waits for the next ring item; returns its stage
-      const uint32_t s = it % kStages;
-      mbar_wait(full_bar(s), (it / kStages) & 1u);
+      const uint32_t s = it % kNst;
+      mbar_wait(full_bar(s), (it / kNst) & 1u);
       if (lane == 0 && it < 48) trace(112 + int(it));
       ++it;
       tc_fence_after();
@@ -470,9 +478,9 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
         issue_fc1(0, true);
         for (int i = 1; i < nchunk; ++i) {
           issue_fc1(i, false);
-          issue_fc2(i - 1, false);
+          if (MODE == 0) issue_fc2(i - 1, false);
         }
-        issue_fc2(nchunk - 1, true);
+        if (MODE == 0) issue_fc2(nchunk - 1, true);
       } else {  // a cluster CTA without a hidden chunk (F = 128): its partial sum is the zero it started from
         mbar_wait(h_ready, tpar);
         mbar_wait(h_ready + 8u, tpar);
@@ -559,13 +567,15 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
             *reinterpret_cast<uint4*>(kbp + off) = hi;
             *reinterpret_cast<uint4*>(kbp + kTileBytes + off) = lo;
           }
-          if (rank == 0) {  // fc2 accumulates on top of h + b2 (CTA 1 of a cluster: on top of zero, its sum is added later)
-            add_cols_g(v, Q.b2 + cl);
-          } else {
+          if constexpr (MODE == 0) {
+            if (rank == 0) {  // fc2 accumulates on top of h + b2 (CTA 1 of a cluster: on top of zero, its sum is added later)
+              add_cols_g(v, Q.b2 + cl);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            tc_st32(tmem + kAccO + lane_addr + cl, v);
           }
-          tc_st32(tmem + kAccO + lane_addr + cl, v);
           if (i & 1) {  // k-blocks {0, 2} after the first two chunks, {1, 3} after the last two
             fence_proxy_async();  // generic-proxy writes of h -> visible to the tensor core's operand reads
             tc_fence_before();
@@ -575,6 +585,72 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
       }
       if (tid == 0 && ti == 0) trace(6);
 
+      if constexpr (MODE == 1) {
+        // ---- h -> global memory, straight out of the operand tiles (hi tile | lo tile of a k-block = one 64 x 128 x 2 box);
+        // CTA r of a cluster stores k-blocks 2 r and 2 r + 1 (both CTAs hold the same h)
+        if (tid == 0) {
+          mbar_wait(h_ready, tpar);
+          mbar_wait(h_ready + 8u, tpar);  // every warp's writes (each followed by fence.proxy.async) have been made
+          const int kb0 = CL > 1 ? 2 * int(rank) : 0, nkb = CL > 1 ? 2 : 4;
+          for (int kb = kb0; kb < kb0 + nkb; ++kb) tma_store_3d(&P.map_y[g], hA + uint32_t(kb) * kKbBytes, kb * 64, int(m0), 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        // ---- q chunks: (acc + bq) * qscale -> hi / lo planes, 32 columns per pair of TMA stores out of this warp's 4 KB box
+        // (the third ring stage is not used as a ring in this mode)
+        uint8_t* qbox = sm + kRingOff + 2 * kStageBytes + uint32_t(warp - 2) * 4096u;
+        const uint32_t qbox_addr = ring + 2 * kStageBytes + uint32_t(warp - 2) * 4096u;
+        const float2 qs2 = make_float2(P.qscale, P.qscale);
+#pragma unroll 1
+        for (int j = 0; j < nchunk; ++j) {
+          const uint32_t b = uint32_t(j & 1);
+          mbar_wait(fc1_full + 8u * b, (fphase >> b) & 1u);
+          fphase ^= 1u << b;
+          tc_fence_after();
+          if (tid == 0 && ti == 0 && j < 8) trace(40 + j);
+          const uint32_t ca = tmem + kAccB + b * 128u + lane_addr + uint32_t(hf * 64);
+          const int col0 = chunk_of(j) * 128 + hf * 64;
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            float v[32];
+            tc_ld32(ca + uint32_t(32 * i), v);
+            add_cols_g(v, Q.b1 + col0 + 32 * i);
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float2 t = __fmul2_rn(make_float2(v[e], v[e + 1]), qs2);
+              v[e] = t.x, v[e + 1] = t.y;
+            }
+            if (j + i > 0) {  // the box's previous contents must have been read out
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint4 hi, lo;
+              split8<FMT>(make_float4(v[8 * e], v[8 * e + 1], v[8 * e + 2], v[8 * e + 3]),
+                          make_float4(v[8 * e + 4], v[8 * e + 5], v[8 * e + 6], v[8 * e + 7]), hi, lo);
+              const uint32_t off = uint32_t(lane * 64 + ((e ^ ((lane >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(qbox + off) = hi;
+              *reinterpret_cast<uint4*>(qbox + 2048 + off) = lo;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&P.map_p[g], qbox_addr, col0 + 32 * i, int(row0), 0);
+              tma_store_3d(&P.map_p[g], qbox_addr + 2048u, col0 + 32 * i, int(row0), 1);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          if (tid == 0 && ti == 0 && j < 8) trace(50 + j);
+        }
+        // hA takes the next tile's ctx (and the boxes their next contents) once everything has been read out
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        tc_fence_before();
+        epi_bar_sync();
+        if (tid == 0) mbar_arrive(tile_done);
+        if (tid == 0 && ti == 0) trace(8);
+        continue;
+      }
       // ---- hidden chunks: accB[j & 1] <- packed hi | lo of GELU(acc + b1), in place (64 columns per warp)
 #pragma unroll 1
       for (int j = 0; j < nchunk; ++j) {
@@ -912,7 +988,59 @@ int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D,
     else (void)launch_kernel(attn_block_kernel<SCATT_PLANE_BF16, 1>, grid, dim3(kThreads), kSmemBytes, s, P);
   }
   const int rc = after_launch("attn_block_kernel");
-  set_last_kernel("attn_block_kernel<%d, %d>", fmt, cl);
+  set_last_kernel("attn_block_kernel<%d, %d, 0>", fmt, cl);
+  return rc;
+}
+
+bool attn_out_q_supported(int64_t M, int D, int N) { return D == DM && N == DM && M >= 1 && M < (int64_t(1) << 31); }
+
+// MODE 1 of attn_block_kernel: h = LayerNorm(x + ctx Wo^T + bo) -> h_planes, q = (h Wq^T + bq) * q_scale -> q_planes
+int launch_attn_out_q(const scatt_outq_problem* p, int group, int64_t M, int D, int N, float eps, float q_scale, int fmt, int terms,
+                      cudaStream_t s) {
+  const int cluster_override = g_block_cluster.load(std::memory_order_relaxed);
+  SCATT_REQUIRE(terms >= 1 && terms <= 3, "attn_out_q: terms must be 1, 2 or 3");
+  if (M == 0) return SCATT_OK;
+  SCATT_REQUIRE(attn_out_q_supported(M, D, N), "attn_out_q: needs D = N = %d (got D=%d N=%d)", DM, D, N);
+  BlkParams P{};
+  P.M = M, P.F = N, P.nchunk = N / 128, P.terms = terms, P.fmt = fmt, P.groups = group, P.eps = eps, P.qscale = q_scale;
+  P.tiles_m = int((M + BM - 1) / BM);
+  for (int i = 0; i < group; ++i) {
+    const scatt_outq_problem& a = p[i];
+    SCATT_REQUIRE(a.ctx_planes && a.residual_planes && a.wo_planes && a.wq_planes && a.h_planes && a.q_planes, "attn_out_q: problem %d lacks an operand or an output", i);
+    SCATT_REQUIRE(a.bo && a.ln_g && a.ln_b && a.bq, "attn_out_q: problem %d lacks a bias or LayerNorm parameter", i);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a.bo) | reinterpret_cast<uintptr_t>(a.ln_g) | reinterpret_cast<uintptr_t>(a.ln_b) | reinterpret_cast<uintptr_t>(a.bq);
+    SCATT_REQUIRE((al & 15) == 0, "attn_out_q: biases and LayerNorm parameters must be 16-byte aligned");
+    int rc = encode_planes_map(&P.map_ctx[i], a.ctx_planes, M, DM, BM, fmt, terms >= 2 ? 2 : 1);
+    if (rc == SCATT_OK) rc = encode_planes_map(&P.map_x[i], a.residual_planes, M, DM, BM, fmt, 2);
+    if (rc == SCATT_OK) rc = encode_planes_map(&P.map_wo[i], a.wo_planes, DM, DM, 256, fmt, 1);
+    if (rc == SCATT_OK) rc = encode_planes_map(&P.map_w1[i], a.wq_planes, N, DM, 128, fmt, terms >= 3 ? 2 : 1);
+    if (rc == SCATT_OK) rc = encode_planes_map(&P.map_y[i], a.h_planes, M, DM, BM, fmt, 2);  // h: k-block boxes, hi tile | lo tile
+    if (rc == SCATT_OK) rc = encode_out_maps(nullptr, &P.map_p[i], nullptr, 0, a.q_planes, M, N, fmt);
+    if (rc != SCATT_OK) return rc;
+    P.map_w2[i] = P.map_wo[i];  // never used in this mode; a valid descriptor for the prefetch
+    P.prob[i] = BlkProblem{a.bo, a.ln_g, a.ln_b, a.bq, a.bo, a.bo, a.bo, nullptr, reinterpret_cast<uint16_t*>(a.q_planes)};
+  }
+  static PerDeviceFlag attr_done;
+  if (!attr_done.load()) {
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_F16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    SCATT_CUDA(cudaFuncSetAttribute(attn_block_kernel<SCATT_PLANE_BF16, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes)));
+    attr_done.store(true);
+  }
+  const int tiles = P.tiles_m * group;
+  const int cl = cluster_override > 0 ? cluster_override : (tiles <= 74 ? 2 : 1);
+  if (cl == 2) {
+    dim3 grid(unsigned(2 * (tiles < 74 ? tiles : 74)));
+    if (fmt == SCATT_PLANE_F16) (void)launch_kernel_cluster(attn_block_kernel<SCATT_PLANE_F16, 2, 1>, grid, dim3(kThreads), kSmemBytes, s, 2, P);
+    else (void)launch_kernel_cluster(attn_block_kernel<SCATT_PLANE_BF16, 2, 1>, grid, dim3(kThreads), kSmemBytes, s, 2, P);
+  } else {
+    dim3 grid(unsigned(tiles < 148 ? tiles : 148));
+    if (fmt == SCATT_PLANE_F16) (void)launch_kernel(attn_block_kernel<SCATT_PLANE_F16, 1, 1>, grid, dim3(kThreads), kSmemBytes, s, P);
+    else (void)launch_kernel(attn_block_kernel<SCATT_PLANE_BF16, 1, 1>, grid, dim3(kThreads), kSmemBytes, s, P);
+  }
+  const int rc = after_launch("attn_block_kernel");
+  set_last_kernel("attn_block_kernel<%d, %d, 1>", fmt, cl);
   return rc;
 }
 

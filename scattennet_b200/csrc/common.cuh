@@ -204,6 +204,9 @@ __device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t plane_st
 // ---------------------------------------------------------------- launchers implemented in the .cu files
 int launch_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int fmt,
                         cudaStream_t s);
+int launch_attn_out_q(const scatt_outq_problem* p, int group, int64_t M, int D, int N, float eps, float q_scale, int fmt, int terms,
+                      cudaStream_t s);
+bool attn_out_q_supported(int64_t M, int D, int N);
 int launch_l2_prefetch(const void* const* ptrs, const int64_t* nbytes, int n, cudaStream_t s);
 int launch_frontend_tc(const float* kp, int B, int T, int K, const scatt_frontend_stream* streams, int n, int max_pos, int fmt, bool force,
                        cudaStream_t s);

@@ -443,6 +443,47 @@ def attn_block(prec: Precision, ctx: Sequence[Act], residuals: Sequence[Act], ou
     return outs
 
 
+FUSED_OUT_Q = os.environ.get("SCATT_FUSED_OUT_Q", "1") != "0"  # False: the causal layer's out_proj+LN and the merge layer's q_proj as two launches
+
+
+def attn_out_q_supported(prec: Precision, M: int, D: int, N: int, group: int = 1) -> bool:
+    """Same small-batch / shape envelope as the fused layer tail (it is the same kernel in another mode)."""
+    if not (FUSED_BLOCK and FUSED_OUT_Q and prec.uses_planes) or ((M + 127) // 128) * group < FUSED_BLOCK_MIN_TILES:
+        return False
+    return bool(L.load().scatt_attn_out_q_supported(M, D, N))
+
+
+def attn_out_q(prec: Precision, ctx: Sequence[Act], residuals: Sequence[Act], out_packs: Sequence[PackedLinear],
+               norms: Sequence[torch.nn.LayerNorm], q_packs: Sequence[PackedLinear], q_scale: float):
+    """Grouped ``h = LN(x + ctx Wo^T + bo)`` and ``q = (h Wq^T + bq) * q_scale`` as ONE launch (``scatt_attn_out_q``):
+    the tail of a causal layer and the q projection of the merge layer that consumes it.  Returns ``(h, q)`` as
+    planes-only :class:`Act` lists."""
+    G = len(ctx)
+    M, D, N = ctx[0].rows, ctx[0].cols, q_packs[0].N
+    dev = ctx[0].planes.device
+    probs = (L.OutQProblem * G)()
+    hs: List[Act] = []
+    qs: List[Act] = []
+    for g in range(G):
+        residuals[g].with_planes(prec)
+        hp = torch.empty(2, M, D, dtype=prec.plane_dtype, device=dev)
+        qp = torch.empty(2, M, N, dtype=prec.plane_dtype, device=dev)
+        p = probs[g]
+        p.ctx_planes, p.residual_planes = ctx[g].planes.data_ptr(), residuals[g].planes.data_ptr()
+        p.wo_planes, p.bo = out_packs[g].planes(prec).data_ptr(), out_packs[g].b32.data_ptr()
+        p.ln_g, p.ln_b = norms[g].weight.data_ptr(), norms[g].bias.data_ptr()
+        p.wq_planes, p.bq = q_packs[g].planes(prec).data_ptr(), q_packs[g].b32.data_ptr()
+        p.h_planes, p.q_planes = hp.data_ptr(), qp.data_ptr()
+        hs.append(Act(None, hp))
+        qs.append(Act(None, qp))
+    flops = 2.0 * G * M * (D * D + D * N)
+    nbytes = G * ((3.0 * M * D + M * N) * 4 + (D * D + D * N) * 4)  # ctx + x in, h + q out (planes), weights once
+    with _timed("attn_block_kernel", flops, nbytes):
+        L.check(L.load().scatt_attn_out_q(probs, G, M, D, N, norms[0].eps, q_scale, prec.plane_fmt, max(prec.terms, 1), _stream()),
+                "scatt_attn_out_q")
+    return hs, qs
+
+
 ATTN_TC_MAX_T = 256  # longest key sequence the tcgen05 attention kernel takes (longer ones run on the fp32 kernel)
 
 

@@ -134,11 +134,17 @@ def _attn_tail(prec, attns, mlps, norms1, norms2, ctx: List[Act], residuals: Lis
 
 def coordinate_attention_forward(prec: Precision, mods: Sequence[CoordinateAttention], xs: List[Act], B: int, T: int,
                                  key_mask: Optional[torch.Tensor], additive: Optional[torch.Tensor] = None,
-                                 keep_f32: bool = True) -> List[Act]:
-    """reference ``model/keypoint_module.py:61-80`` for a group of streams."""
+                                 keep_f32: bool = True, q_for: Optional[Sequence["CoordinatesMerge"]] = None):
+    """reference ``model/keypoint_module.py:61-80`` for a group of streams.  ``q_for`` (causal layers on the plane
+    path): the merge layers that consume the result - their q projection is fused into this layer's tail and
+    ``(outputs, q)`` is returned."""
     kind = L.ATTN_SELF if mods[0].attn_type == "self_attn" else L.ATTN_CAUSAL
     is_self = mods[0].attn_type == "self_attn"
     ctx = attention_core(prec, [m.attn for m in mods], xs, None, B, T, T, kind, key_mask, additive)
+    if q_for is not None:
+        qa = [m.attn for m in q_for]
+        return F_.attn_out_q(prec, ctx, xs, [F_.pack_of(m.attn, "out", [m.attn.out_proj]) for m in mods],
+                             [m.attn_layer_norm for m in mods], [F_.pack_of(a, "q", [a.q_proj]) for a in qa], qa[0].scaling)
     if is_self:
         return _attn_tail(prec, [m.attn for m in mods], [m.mlp for m in mods], [m.attn_layer_norm for m in mods],
                           [m.last_layer_norm for m in mods], ctx, xs, keep_f32)
@@ -168,9 +174,10 @@ class CoordinatesMerge(nn.Module):
 
 def coordinates_merge_forward(prec: Precision, mods: Sequence[CoordinatesMerge], ys: List[Act], xs: Optional[List[Act]],
                               kv_views, B: int, Tq: int, Tk: int, key_mask: Optional[torch.Tensor],
-                              additive: Optional[torch.Tensor] = None, keep_f32: bool = True) -> List[Act]:
+                              additive: Optional[torch.Tensor] = None, keep_f32: bool = True,
+                              q_planes: Optional[List[Act]] = None) -> List[Act]:
     """reference ``model/keypoint_module.py:97-115`` for a group of streams."""
-    ctx = attention_core(prec, [m.attn for m in mods], ys, xs, B, Tq, Tk, L.ATTN_CROSS, key_mask, additive, kv_views)
+    ctx = attention_core(prec, [m.attn for m in mods], ys, xs, B, Tq, Tk, L.ATTN_CROSS, key_mask, additive, kv_views, q_planes)
     return _attn_tail(prec, [m.attn for m in mods], [m.mlp for m in mods], [m.attn_layer_norm for m in mods],
                       [m.last_layer_norm for m in mods], ctx, ys, keep_f32)
 
@@ -219,7 +226,13 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
     d = s[0].cols
     # The first causal layer only needs the causal-branch embedding: run it on a side stream while the
     # self branch works (inside a captured forward this becomes a parallel graph branch).
-    c_first, join = None, None
+    c_first, q_first, join = None, None, None
+    # causal layer i feeds merge layer i only: its out_proj + LayerNorm and the merge layer's q projection run as one launch
+    # (scatt_attn_out_q) where the fused-tail kernel is in use
+    fuse_q = (n > 0 and T <= F_.ATTN_PLANES_MAX_T and d // mods[0].causal_attn_layers[0].attn.num_heads == 16
+              and all(c_.planes is not None for c_ in c)
+              and all(l.bias is not None for m in mods for i in range(n) for l in (m.causal_attn_layers[i].attn.out_proj, m.coordinates_merge[i].attn.q_proj))
+              and F_.attn_out_q_supported(prec, c[0].rows, d, d, len(mods)))
     if OVERLAP_BRANCHES and n > 0:
         main = torch.cuda.current_stream()
         side = _side_stream(main.device)
@@ -227,10 +240,13 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
         fork.record(main)
         side.wait_event(fork)
         with torch.cuda.stream(side):
-            c_first = coordinate_attention_forward(prec, [m.causal_attn_layers[0] for m in mods], c, B, T, key_mask, keep_f32=False)
+            c_first = coordinate_attention_forward(prec, [m.causal_attn_layers[0] for m in mods], c, B, T, key_mask, keep_f32=False,
+                                                   q_for=[m.coordinates_merge[0] for m in mods] if fuse_q else None)
+            if fuse_q:
+                c_first, q_first = c_first
             join = torch.cuda.Event()
             join.record(side)
-        for a in list(c) + list(c_first):  # tensors that cross streams: keep the allocator honest in eager mode
+        for a in list(c) + list(c_first) + list(q_first or []):  # tensors that cross streams: keep the allocator honest in eager mode
             for t in (a.f32, a.planes):
                 if t is not None:
                     t.record_stream(side)
@@ -261,11 +277,15 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
     kv_first = F_.linear(prec, s, [kv_pack(m, "merge_kv_first" if split_kv else "merge_kv", range(1 if split_kv else n)) for m in mods],
                          F_.make_epilogue(), out_f32=not kv_planes, out_planes=kv_planes)
     for i in range(n):
+        q_pre = None
         if i == 0 and c_first is not None:
             torch.cuda.current_stream().wait_event(join)
-            c = c_first
+            c, q_pre = c_first, q_first
         else:
-            c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask, keep_f32=False)
+            c = coordinate_attention_forward(prec, [m.causal_attn_layers[i] for m in mods], c, B, T, key_mask, keep_f32=False,
+                                             q_for=[m.coordinates_merge[i] for m in mods] if fuse_q else None)
+            if fuse_q:
+                c, q_pre = c
         if split_kv and i == 1:
             kv_branch.join(kv_rest)
         kv_src, j = (kv_rest, i - 1) if (split_kv and i >= 1) else (kv_first, i)
@@ -274,7 +294,7 @@ def sca_forward(prec: Precision, mods: Sequence[SeparativeCoordinateAttention], 
         else:
             kv_views = [(kv.f32[:, 2 * j * d : (2 * j + 1) * d], kv.f32[:, (2 * j + 1) * d : (2 * j + 2) * d]) for kv in kv_src]
         c = coordinates_merge_forward(prec, [m.coordinates_merge[i] for m in mods], c, None, kv_views, B, T, T, key_mask,
-                                      keep_f32=i == n - 1)  # the ladder's result feeds the residual network in fp32
+                                      keep_f32=i == n - 1, q_planes=q_pre if kv_planes else None)  # the ladder's result feeds the residual network in fp32
     return c, s
 
 

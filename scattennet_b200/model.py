@@ -148,7 +148,7 @@ class MSCAEncoder(nn.Module):
         # a compact tensor (only the joints the three streams use, see forward_host) carries remapped indices
         idx = self._compact_idx(keypoints.device)[1] if compact else self._joint_idx(keypoints.device)
         # small batches: ~60 dependent launches each pay DRAM latency on their first weight tile when the step starts with
-        # a cold L2; one launch on a parallel branch hints all weight planes (~35 MB) into L2 (csrc/prefetch.cu).  Large
+        # a cold L2; one launch on a parallel branch hints all weight planes (~70 MB) into L2 (csrc/prefetch.cu).  Large
         # batches stream more activations through L2 than it holds - the hint would be evicted before use.
         pf = None
         if F_.L2_PREFETCH and prec.uses_planes and b * t <= 8192:

@@ -129,3 +129,58 @@ def test_attn_block_planes_only_output_and_repeatability():
     assert torch.equal(a.planes, b.planes)  # deterministic: no atomics, fixed accumulation order
     ref = ref_block(ctx, x, m)
     assert float(((a.planes[0].float() + a.planes[1].float()).double() - ref).abs().max()) <= 2e-4
+
+
+# ---- scatt_attn_out_q: the same kernel in its second mode (causal layer tail + the merge layer's q projection)
+
+
+def run_out_q(prec, ctxs, xs, layers, scale):
+    ctx_a = [Act(c).with_planes(prec) for c in ctxs]
+    x_a = [Act(x).with_planes(prec) for x in xs]
+    pk = lambda key: [F_.PackedLinear([m[key]], None, None) for m in layers]
+    return F_.attn_out_q(prec, ctx_a, x_a, pk("out"), [m["ln1"] for m in layers], pk("fc1"), scale)
+
+
+@pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
+@pytest.mark.parametrize("M,G", [(200, 1), (1600, 3), (333, 2), (77, 1), (129, 1)])
+def test_attn_out_q_vs_fp64(mode, M, G, schedule):
+    """h = LN(x + ctx Wo^T + bo) and q = (h Wq^T + bq) * scale, both as split planes, against fp64 torch - one CTA and a
+    2-CTA cluster per row tile, M tails, several streams."""
+    prec = F_.get_precision(mode)
+    D, scale = 256, 0.25
+    assert L.load().scatt_attn_out_q_supported(M, D, D)
+    layers = [make_layer(D, D, 23 + g) for g in range(G)]  # "fc1" plays q_proj (256 -> 256)
+    ctxs = [rnd(M, D, seed=70 + g) for g in range(G)]
+    xs = [rnd(M, D, seed=80 + g) for g in range(G)]
+    hs, qs = run_out_q(prec, ctxs, xs, layers, scale)
+    torch.cuda.synchronize()
+    f, d = torch.nn.functional, (lambda t: t.double())
+    for g in range(G):
+        m = layers[g]
+        h_ref = f.layer_norm(d(xs[g]) + d(ctxs[g]) @ d(m["out"].weight).t() + d(m["out"].bias), (D,), d(m["ln1"].weight), d(m["ln1"].bias), 1e-5)
+        q_ref = (h_ref @ d(m["fc1"].weight).t() + d(m["fc1"].bias)) * scale
+        h = hs[g].planes[0].double() + hs[g].planes[1].double()
+        q = qs[g].planes[0].double() + qs[g].planes[1].double()
+        assert hs[g].f32 is None and qs[g].f32 is None
+        assert float((h - h_ref).abs().max()) <= MODE_TOL[mode], (mode, M, g)
+        assert float((q - q_ref).abs().max()) <= MODE_TOL[mode], (mode, M, g)
+
+
+def test_attn_out_q_many_tiles_matches_two_launch_path():
+    """More row tiles than SMs (every CTA walks several tiles) and agreement with the launches it replaces
+    (scatt_linear with the LayerNorm epilogue, then scatt_linear with the q scaling)."""
+    prec = F_.get_precision("fp16x3")
+    D, G, scale = 256, 2, 0.25
+    M = 128 * 160 + 45
+    layers = [make_layer(D, D, 31 + g) for g in range(G)]
+    ctxs = [rnd(M, D, seed=90 + g) for g in range(G)]
+    xs = [rnd(M, D, seed=95 + g) for g in range(G)]
+    hs, qs = run_out_q(prec, ctxs, xs, layers, scale)
+    pk = lambda key: [F_.PackedLinear([m[key]], None, None) for m in layers]
+    h2 = F_.linear(prec, [Act(c).with_planes(prec) for c in ctxs], pk("out"), F_.make_epilogue(residual_mode=F_.L.RES_BEFORE_LN, layer_norm=True),
+                   residuals=[Act(x).with_planes(prec) for x in xs], lns=[m["ln1"] for m in layers])
+    q2 = F_.linear(prec, h2, pk("fc1"), F_.make_epilogue(scale_cols=D, scale=scale), out_f32=False)
+    torch.cuda.synchronize()
+    for g in range(G):
+        assert float(((hs[g].planes[0].float() + hs[g].planes[1].float()) - h2[g].f32).abs().max()) <= 2e-5
+        assert float(((qs[g].planes[0].float() + qs[g].planes[1].float()) - (q2[g].planes[0].float() + q2[g].planes[1].float())).abs().max()) <= 2e-5
