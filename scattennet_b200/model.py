@@ -141,7 +141,19 @@ class MSCAEncoder(nn.Module):
             self._idx_cache["max_joint"] = max(j for p in PARTS for j in self.cfg[p + "_idx"])
         return self._idx_cache["max_joint"]
 
-    def _run(self, keypoints: torch.Tensor, key_mask: torch.Tensor, with_heads: bool = True, compact: bool = False) -> Dict[str, torch.Tensor]:
+    def _prefetch_begin(self, prec, b: int, t: int):
+        """The weight prefetch branch (``scatt_l2_prefetch`` on the side stream); returns the branch to ``join()`` or None."""
+        if not (F_.L2_PREFETCH and prec.uses_planes and b * t <= 8192):
+            return None
+        planes = F_.weight_planes_of(self, prec)
+        if not planes:
+            return None
+        with F_.SideBranch([]) as pf:
+            F_.l2_prefetch(planes)
+        return pf
+
+    def _run(self, keypoints: torch.Tensor, key_mask: torch.Tensor, with_heads: bool = True, compact: bool = False,
+             prefetch: bool = True) -> Dict[str, torch.Tensor]:
         prec = F_.get_precision(self.precision)
         b, t = keypoints.shape[:2]
         mods = [self.body_encoder, self.left_encoder, self.right_encoder]
@@ -150,12 +162,7 @@ class MSCAEncoder(nn.Module):
         # small batches: ~60 dependent launches each pay DRAM latency on their first weight tile when the step starts with
         # a cold L2; one launch on a parallel branch hints all weight planes (~70 MB) into L2 (csrc/prefetch.cu).  Large
         # batches stream more activations through L2 than it holds - the hint would be evicted before use.
-        pf = None
-        if F_.L2_PREFETCH and prec.uses_planes and b * t <= 8192:
-            planes = F_.weight_planes_of(self, prec)
-            if planes:
-                with F_.SideBranch([]) as pf:
-                    F_.l2_prefetch(planes)
+        pf = self._prefetch_begin(prec, b, t) if prefetch else None
         blocks = streams_forward(prec, mods, keypoints, idx, key_mask, b, t)
         (body, left, right), tp = blocks[-1]
         lg, heads_branch = None, None
@@ -341,9 +348,16 @@ class MSCAEncoder(nn.Module):
             # the two slots' graphs replay in stream order, never concurrently: they share one memory pool
             pool = st.get("pool")
             with torch.cuda.graph(graph, pool=pool), torch.no_grad():
+                # the weight prefetch does not depend on the batch: it forks before the H2D copies and runs under them
+                b, t = st["kp_dev"].shape[:2]
+                pf = self._prefetch_begin(F_.get_precision(self.precision), b, t) if min(self.micro_batches, b) <= 1 else None
                 st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
                 st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
-                out = self._run_branches(st["kp_dev"], st["mask_dev"], True, True)
+                if pf is not None:
+                    out = self._run(st["kp_dev"], st["mask_dev"], True, True, prefetch=False)
+                    pf.join()
+                else:
+                    out = self._run_branches(st["kp_dev"], st["mask_dev"], True, True)
                 for k in heads:
                     pins[k].copy_(out[k], non_blocking=True)
             if pool is None:
