@@ -45,6 +45,9 @@ class LinearHeads(nn.Module):
             self.fuse_alignment_head = AlignmentModule(**cfg["alignment_module"], cls_num=vocab_size)
 
 
+BIND_INPUTS = os.environ.get("SCATT_BIND_INPUTS", "1") != "0"  # False: always copy the inputs into the captured graph's static buffers
+
+
 class MSCAEncoder(nn.Module):
     def __init__(self, cfg, vocab_size: int, precision: Optional[str] = None, use_graph: bool = False, micro_batches: int = 1,
                  alignment: bool = False):
@@ -369,6 +372,11 @@ class MSCAEncoder(nn.Module):
 
     # ------------------------------------------------------------------ CUDA graph replay
     def _run_graph(self, keypoints, mask, with_heads, compact=False):
+        """Replay the captured graph of this shape.  The first capture reads static copies of the inputs (any tensor may
+        be passed from call to call).  When the SAME input tensors come back (same storage, consecutive calls - a serving
+        loop that refills its input buffers in place, the benchmark's resident batch) a second graph is captured that
+        reads them where they are: no 6.9 MB device-to-device copy of the keypoints and no mask conversion launches in
+        front of the replay."""
         key = (tuple(keypoints.shape), str(keypoints.device), F_.get_precision(self.precision).name, with_heads, compact)
         ent = self._cache_get(self._graphs, key)
         if ent is None:
@@ -386,9 +394,22 @@ class MSCAEncoder(nn.Module):
             n0 = L.launch_count()
             with torch.cuda.graph(graph):
                 static_out = self._run_branches(static_kp, static_mask, with_heads, compact)
-            ent = (graph, static_kp, static_mask, static_out, L.launch_count() - n0)
+            ent = [graph, static_kp, static_mask, static_out, L.launch_count() - n0, None, None]  # [5] last inputs seen, [6] bound graph
             self._cache_put(self._graphs, key, ent)
-        graph, static_kp, static_mask, static_out, _ = ent
+        ptrs = (keypoints.data_ptr(), mask.data_ptr(), mask.dtype, tuple(mask.stride()))
+        bound = ent[6]
+        if bound is not None and bound[0] == ptrs:
+            bound[1].replay()
+            return bound[2]
+        if BIND_INPUTS and ent[5] == ptrs:  # the same tensors twice in a row: capture a graph that reads them in place
+            graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph2, pool=ent[0].pool()):  # never replayed concurrently with the static graph
+                out2 = self._run_branches(keypoints, F_.key_mask_u8(mask), with_heads, compact)
+            ent[6] = (ptrs, graph2, out2, keypoints, mask)  # the references keep the storage alive
+            graph2.replay()
+            return out2
+        ent[5] = ptrs
+        graph, static_kp, static_mask, static_out = ent[:4]
         static_kp.copy_(keypoints, non_blocking=True)
         static_mask.copy_(F_.key_mask_u8(mask), non_blocking=True)
         graph.replay()

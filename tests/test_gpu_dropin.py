@@ -139,6 +139,38 @@ def test_graphs_dropped_when_weights_change():
     assert len(m._graphs) <= m.max_cached_shapes
 
 
+def test_graph_reads_repeated_inputs_in_place():
+    """The same input tensors on consecutive calls: from the second call on a graph bound to them replays without the
+    device-to-device input copies; refilling them in place is seen by the next call, other tensors take the copying
+    graph, and every route returns what the eager path returns."""
+    cfg = model_config("phoenix-2014t")
+    m = S.MSCAEncoder(cfg, VOCAB_STUB, precision="fp16x3", use_graph=True).eval()
+    synth.load_synth_(m, 0)
+    m = m.to(DEV)
+    eager = S.MSCAEncoder(cfg, VOCAB_STUB, precision="fp16x3", use_graph=False).eval()
+    synth.load_synth_(eager, 0)
+    eager = eager.to(DEV)
+    batches = [synth.synth_batch(2, 48, seed=s, lengths=[48, 30 + s]) for s in (1, 2, 3)]
+    kp, mask = batches[0][0].to(DEV), batches[0][1].to(DEV)
+    with torch.no_grad():
+        for step, (kp_h, mask_h) in enumerate(batches + batches[:1]):
+            kp.copy_(kp_h.to(DEV))      # refill the SAME device tensors
+            mask.copy_(mask_h.to(DEV))
+            got = {k: v.clone() for k, v in m(kp, mask).items()}
+            want = eager(kp, mask)
+            torch.cuda.synchronize()
+            for k in want:
+                assert torch.equal(got[k], want[k]), (step, k)
+            bound = next(iter(m._graphs.values()))[6]
+            assert (bound is not None) == (step >= 1)
+        other_kp, other_mask = batches[1][0].to(DEV), batches[1][1].to(DEV)  # different storage: the copying graph
+        got = {k: v.clone() for k, v in m(other_kp, other_mask).items()}
+        want = eager(other_kp, other_mask)
+        torch.cuda.synchronize()
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+
+
 def test_input_validation():
     cfg = model_config("phoenix-2014t")
     m = S.MSCAEncoder(cfg, VOCAB_STUB).eval().to(DEV)
