@@ -264,12 +264,19 @@ class MSCAEncoder(nn.Module):
         key = ("host", b, t, str(dev))
         st = self._cache_get(self._host_staging, key)
         if st is None:
+            # keypoints and mask share ONE staging buffer per slot (and one on the device): a single H2D copy per step
+            n_kp = b * t * used.numel() * 2 * 4
+
+            def views(buf):
+                return buf[:n_kp].view(torch.float32).view(b, t, used.numel(), 2), buf[n_kp:].view(b, t)
+
             def make_slot():
-                return {"kp_pin": torch.empty(b, t, used.numel(), 2, dtype=torch.float32).pin_memory(),
-                        "mask_pin": torch.empty(b, t, dtype=torch.uint8).pin_memory(), "out_pin": {}, "busy": None}
-            st = {"slots": [make_slot(), make_slot()], "next": 0,
-                  "kp_dev": torch.empty(b, t, used.numel(), 2, dtype=torch.float32, device=dev),
-                  "mask_dev": torch.empty(b, t, dtype=torch.uint8, device=dev)}
+                pin = torch.empty(n_kp + b * t, dtype=torch.uint8).pin_memory()
+                kp_pin, mask_pin = views(pin)
+                return {"pin": pin, "kp_pin": kp_pin, "mask_pin": mask_pin, "out_pin": {}, "busy": None}
+            in_dev = torch.empty(n_kp + b * t, dtype=torch.uint8, device=dev)
+            kp_dev, mask_dev = views(in_dev)
+            st = {"slots": [make_slot(), make_slot()], "next": 0, "in_dev": in_dev, "kp_dev": kp_dev, "mask_dev": mask_dev}
             self._cache_put(self._host_staging, key, st)
         slot = st["slots"][st["next"]]
         st["next"] ^= 1
@@ -289,8 +296,7 @@ class MSCAEncoder(nn.Module):
 
                     res[heads[0] + "/gathered_dev"] = gather_logits_peer(out_dev[heads[0]])
                 return res
-            st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
-            st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
+            st["in_dev"].copy_(slot["pin"], non_blocking=True)
             out = self.forward(st["kp_dev"], st["mask_dev"], compact=True)
             extra = {}
             if gather:
@@ -341,8 +347,7 @@ class MSCAEncoder(nn.Module):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side), torch.no_grad():  # warm-up: packs weights, sets kernel attributes
-                st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
-                st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
+                st["in_dev"].copy_(slot["pin"], non_blocking=True)
                 for _ in range(2):
                     out = self._run(st["kp_dev"], st["mask_dev"], True, True)
                 pins = {k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in heads}
@@ -354,8 +359,7 @@ class MSCAEncoder(nn.Module):
                 # the weight prefetch does not depend on the batch: it forks before the H2D copies and runs under them
                 b, t = st["kp_dev"].shape[:2]
                 pf = self._prefetch_begin(F_.get_precision(self.precision), b, t) if min(self.micro_batches, b) <= 1 else None
-                st["kp_dev"].copy_(slot["kp_pin"], non_blocking=True)
-                st["mask_dev"].copy_(slot["mask_pin"], non_blocking=True)
+                st["in_dev"].copy_(slot["pin"], non_blocking=True)
                 if pf is not None:
                     out = self._run(st["kp_dev"], st["mask_dev"], True, True, prefetch=False)
                     pf.join()
