@@ -290,11 +290,20 @@ class MSCAEncoder(nn.Module):
                 # captured graph: a single launch instead of eight stream operations with the host in between.
                 # Sharded jobs add one launch behind it: the NVLink push of this rank's logits (the read-back of the own
                 # shard is already inside the graph and overlaps it).
-                res, out_dev = self._host_graph_step(st, slot, heads, dev)
+                res, out_dev = self._host_graph_step(st, slot, heads, dev, d2h_in_graph=not gather)
                 if gather:
+                    # the read-back of the own shard (PCIe) and the push of the logits to the peers (NVLink) both start
+                    # when the captured encoder has finished: the copy runs on a side stream beside the push kernel
                     from .distributed import gather_logits_peer
 
+                    main = torch.cuda.current_stream(dev)
+                    side = F_.side_stream(dev)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        for k in heads:
+                            res[k].copy_(out_dev[k], non_blocking=True)
                     res[heads[0] + "/gathered_dev"] = gather_logits_peer(out_dev[heads[0]])
+                    main.wait_stream(side)
                 return res
             st["in_dev"].copy_(slot["pin"], non_blocking=True)
             out = self.forward(st["kp_dev"], st["mask_dev"], compact=True)
@@ -340,8 +349,8 @@ class MSCAEncoder(nn.Module):
             busy.record(torch.cuda.current_stream(dev))
             slot["busy"] = busy
 
-    def _host_graph_step(self, st, slot, heads, dev):
-        key = ("hostgraph", tuple(heads), F_.get_precision(self.precision).name)
+    def _host_graph_step(self, st, slot, heads, dev, d2h_in_graph: bool = True):
+        key = ("hostgraph", tuple(heads), F_.get_precision(self.precision).name, d2h_in_graph)
         ent = slot.get(key)
         if ent is None:
             side = torch.cuda.Stream(device=dev)
@@ -365,8 +374,9 @@ class MSCAEncoder(nn.Module):
                     pf.join()
                 else:
                     out = self._run_branches(st["kp_dev"], st["mask_dev"], True, True)
-                for k in heads:
-                    pins[k].copy_(out[k], non_blocking=True)
+                if d2h_in_graph:
+                    for k in heads:
+                        pins[k].copy_(out[k], non_blocking=True)
             if pool is None:
                 st["pool"] = graph.pool()
             ent = slot[key] = (graph, pins, out)
