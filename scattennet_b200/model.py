@@ -208,7 +208,10 @@ class MSCAEncoder(nn.Module):
         streams use, in ascending joint order (what ``forward_host`` ships).
 
         With ``use_graph=True`` the returned tensors are the captured graph's static outputs: the next call with
-        the same shape overwrites them (clone what must survive).  Captured graphs are dropped by
+        the same shape overwrites them (clone what must survive).  When the same input tensors (same storage) are
+        passed on consecutive calls, a graph that reads them in place is captured and replayed from then on - refill
+        them in place on the calling stream; the model keeps a reference to them until the shape's cache entry is
+        evicted or ``invalidate_graphs()`` is called (``SCATT_BIND_INPUTS=0`` always copies instead).  Captured graphs are dropped by
         ``load_state_dict`` / ``.to()`` / ``.cuda()`` (``invalidate_graphs``); after modifying parameters in place
         call ``invalidate_graphs()`` yourself."""
         if self.training:
