@@ -277,7 +277,7 @@ int scatt_attention(const scatt_attention_problem* problems_host, int group, int
  * (`scatt_linear` with y_planes): planes[2][rows][ld], head h at columns
  * [col + hd*h, col + hd*(h+1)).  Tiles are fetched by TMA straight into tensor-core
  * layout - nothing is converted or transposed - so this is the fast path used by
- * SeparativeCoordinateAttention / Encoder.  Requires hd = 16 and Tk <= 672 (use
+ * SeparativeCoordinateAttention / Encoder.  Requires hd = 16 and Tk <= 1568 (use
  * scatt_attention otherwise); q must already carry the head_dim^-0.5 scaling. */
 typedef struct scatt_attn_operand {
   const void* planes;

@@ -17,8 +17,9 @@
 // Longer key sequences are walked in blocks of 224 keys with an exact two-pass softmax: pass A
 // recomputes S block by block for the row maxima, pass B recomputes it again, exponentiates and
 // accumulates O = sum_blocks P_blk V_blk (QK^T is one K=16 MMA per term, so recomputing it is free;
-// all K / V rows of the sequence stay resident in shared memory).  Up to 3 blocks (672 keys);
-// beyond that, and for dense additive masks, the fp32 CUDA-core kernel runs.
+// all K / V rows of the sequence stay resident in shared memory).  Up to 7 blocks (1568 keys: 214 KB of
+// shared memory, one CTA per SM from the fourth block on); beyond that, and for dense additive masks,
+// the fp32 CUDA-core kernel runs.
 #include <cfloat>
 #include <cstdlib>
 
@@ -34,7 +35,7 @@ using namespace tc;
 constexpr int HD = 16;
 constexpr int QT = 128;
 constexpr int KBLK = 224;  // keys per block: S/P columns [0, 224), O columns [224, 240)
-constexpr int kMaxBlocks = 3;
+constexpr int kMaxBlocks = 7;  // 7 x 224 keys x 4 planes of K / V rows = 196 KB: one CTA per SM beyond 3 blocks
 constexpr int KMAX = KBLK * kMaxBlocks;
 constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quadrant
 constexpr int kThreadsFa = 32 * kSoftmaxWarps + 32;  // + TMA / MMA warp

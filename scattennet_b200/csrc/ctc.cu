@@ -6,14 +6,27 @@
 // by the reference's own post-processing: blank = class 0, ids in the original numbering, consecutive
 // duplicates collapsed (itertools.groupby).
 //
-// One CTA per sequence.  A time step is: block-wide log-softmax of the V logits into shared memory;
-// one thread advances the <= W live prefixes (a W-entry problem); all threads score the W * (V - 1) one-label
-// extensions against the W-th best live prefix (an extension below it can never enter the beam), each warp
-// keeping its best W in registers (lane j holds the j-th; rare insertions are serialised by ballot); one warp
-// merges the 8 warp lists with the live prefixes into the next beam (order: probability, ties to the earlier
-// insertion - the sequential push / pop-bottom of the original reduces to exactly this top-W selection because
-// an extension can never beat the prefix it extends).  The prefix trie
-// (parent, label per node; at most 1 + W * T nodes) lives in shared memory, only token ids leave the chip.
+// One CTA per sequence, ONE block-wide barrier per time step.  The beam (<= W <= 16 live prefixes) lives in
+// registers, replicated in every warp: lane i holds prefix i (trie node, parent node, last label, parent's last
+// label, log-probabilities total / blank / label), and every warp advances and re-selects it redundantly with
+// warp shuffles - no thread-0 serial section, no hand-over of the beam through shared memory.  A step is:
+//   * the logits of frame t+1 are loaded into registers at the top of the step and staged (raw) into the other
+//     half of a double buffer at its end, together with per-warp (max, sum exp) partials of the frame's softmax
+//     normaliser - the normaliser of frame t is combined from the 8 partials after the barrier of step t-1,
+//     so the global loads and the softmax reduction of the next frame run under this frame's search;
+//   * advance: lane i finds its parent among the live prefixes by shuffles and updates (blank, label, total);
+//   * all threads score the W * (V - 1) one-label extensions against the W-th best live prefix (an extension
+//     below it can never enter the beam); a whole branch is skipped when its best possible extension (largest
+//     non-blank log-probability of the frame + the branch's probability) is below that bar - the usual case once
+//     the beam is full and the frame is a blank; each warp keeps its best W in registers (lane j holds the
+//     j-th; rare insertions are serialised by ballot);
+//   * barrier; every warp merges the 8 warp lists with the live prefixes into the next beam: W rounds of
+//     arg-max by redux.sync on an order-preserving integer image of the score, ties to the lower insertion code
+//     (order: probability, ties to the earlier insertion - the sequential push / pop-bottom of the original
+//     reduces to exactly this top-W selection because an extension can never beat the prefix it extends).
+//     Winners come out in descending order, so the beam stays sorted and the most probable prefix is lane 0.
+// The prefix trie (parent, label per node; at most 1 + W * T nodes) lives in shared memory, written by warp 0
+// and read only by the final back-walk; only token ids leave the chip.
 #include <cfloat>
 
 #include "common.cuh"
@@ -23,7 +36,10 @@ namespace scatt {
 namespace {
 
 constexpr int kCtcThreads = 256;
+constexpr int kCtcWarps = kCtcThreads / 32;
 constexpr int kMaxBeam = 16;
+constexpr int kRowRegs = 8;  // logits of the next frame held in registers per thread (V <= 2048; the rest is re-read)
+constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float lse2(float a, float b) {
   if (a == -INFINITY) return b;
@@ -34,33 +50,33 @@ __device__ __forceinline__ float lse2(float a, float b) {
 // (score, order): higher score first, then lower order (earlier insertion)
 __device__ __forceinline__ bool better(float s0, int o0, float s1, int o1) { return s0 > s1 || (s0 == s1 && o0 < o1); }
 
-struct Beam {
-  int n;
-  int node[kMaxBeam];
-  float old_total[kMaxBeam], old_blank[kMaxBeam];
-  float total[kMaxBeam], blank[kMaxBeam], label[kMaxBeam];
-  int next_node;
-  int forbidden[kMaxBeam];  // extension codes (branch * (V-1) + label) whose prefix is already live
-  float thr_score;          // W-th best live prefix (-inf while the beam is not full)
-  // selection result of the step: order code of each winner (negative: live prefix i = code + kMaxBeam)
-  int win_code[kMaxBeam];
-  float win_score[kMaxBeam];
-  int n_win;
-};
+// order-preserving map float -> uint32 (no NaNs here; -0 is folded into +0 first so that equal scores get equal keys)
+__device__ __forceinline__ uint32_t order_key(float s) {
+  const uint32_t b = __float_as_uint(s + 0.f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float order_key_inv(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k); }
+
+// softmax partials (m = max, s = sum exp(x - m)) of two disjoint sets
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  const float e1 = m == -INFINITY ? 0.f : expf(m - mm), e2 = m2 == -INFINITY ? 0.f : expf(m2 - mm);
+  s = s * e1 + s2 * e2;
+  m = mm;
+}
 
 __global__ void __launch_bounds__(kCtcThreads) ctc_beam_kernel(const float* __restrict__ logits, int T, int V,
                                                                const int* __restrict__ lengths, int W, int node_cap,
                                                                int* __restrict__ out_ids, int* __restrict__ out_len,
                                                                float* __restrict__ out_score) {
   extern __shared__ __align__(16) unsigned char ctc_smem[];
-  float* logp = reinterpret_cast<float*>(ctc_smem);                          // [V]
-  int* node_parent = reinterpret_cast<int*>(logp + ((V + 3) & ~3));          // [node_cap]
+  const int Vp = (V + 3) & ~3;
+  float* raw = reinterpret_cast<float*>(ctc_smem);                           // [2][Vp] logits of frame t / t+1
+  float* part = raw + 2 * Vp;                                                // [2][3][warps]: max, sum exp, non-blank max
+  int* node_parent = reinterpret_cast<int*>(part + 2 * 3 * kCtcWarps);       // [node_cap]
   int* node_label = node_parent + node_cap;                                  // [node_cap]
-  float* cand_score = reinterpret_cast<float*>(node_label + node_cap);       // [warps * W] per-warp best extensions
-  int* cand_code = reinterpret_cast<int*>(cand_score + (kCtcThreads / 32) * W);
-  Beam& bm = *reinterpret_cast<Beam*>(cand_code + (kCtcThreads / 32) * W);
-  __shared__ float red[kCtcThreads / 32];
-  __shared__ float s_norm;
+  float* cand_score = reinterpret_cast<float*>(node_label + node_cap);       // [2][warps * W] per-warp best extensions
+  int* cand_code = reinterpret_cast<int*>(cand_score + 2 * kCtcWarps * W);   // [2][warps * W]
 
   pdl_launch_dependents();
   pdl_wait();
@@ -69,198 +85,227 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_beam_kernel(const float* __re
   const float* x = logits + int64_t(b) * T * V;
   const int n_lab = V - 1;  // label k of the search = class k + 1 (class 0 is the blank)
 
-  if (tid == 0) {
-    bm.n = 1, bm.node[0] = 0, bm.total[0] = 0.f, bm.blank[0] = 0.f, bm.label[0] = -INFINITY, bm.next_node = 1;
-    node_parent[0] = -1, node_label[0] = -1;
+  // stage a frame held in registers (+ the tail past kRowRegs * 256 classes, re-read) and its softmax partials
+  auto stage = [&](const float (&nx)[kRowRegs], const float* row, int buf) {
+    float* dst = raw + buf * Vp;
+    float m = -INFINITY, mnb = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kRowRegs; ++r) {
+      const int i = tid + r * kCtcThreads;
+      if (i < V) {
+        dst[i] = nx[r];
+        m = fmaxf(m, nx[r]);
+        if (i > 0) mnb = fmaxf(mnb, nx[r]);
+      }
+    }
+    for (int i = tid + kRowRegs * kCtcThreads; i < V; i += kCtcThreads) {
+      const float v = row[i];
+      dst[i] = v;
+      m = fmaxf(m, v), mnb = fmaxf(mnb, v);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRowRegs; ++r)
+      if (tid + r * kCtcThreads < V) s += expf(nx[r] - m);
+    for (int i = tid + kRowRegs * kCtcThreads; i < V; i += kCtcThreads) s += expf(row[i] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float m2 = __shfl_xor_sync(kFull, m, o), s2 = __shfl_xor_sync(kFull, s, o);
+      lse_merge(m, s, m2, s2);
+      mnb = fmaxf(mnb, __shfl_xor_sync(kFull, mnb, o));
+    }
+    if (lane == 0) {
+      float* pp = part + buf * 3 * kCtcWarps;
+      pp[warp] = m, pp[kCtcWarps + warp] = s, pp[2 * kCtcWarps + warp] = mnb;
+    }
+  };
+  auto fetch = [&](float (&nx)[kRowRegs], const float* row) {
+#pragma unroll
+    for (int r = 0; r < kRowRegs; ++r) {
+      const int i = tid + r * kCtcThreads;
+      nx[r] = i < V ? __ldg(row + i) : 0.f;
+    }
+  };
+
+  // the beam, replicated per warp: lane i = live prefix i (sorted by descending probability)
+  int n = 1, next_node = 1;
+  int node = lane == 0 ? 0 : -2, par = -1, lab = -1, plab = -1;
+  float total = lane == 0 ? 0.f : -INFINITY, blank = total, label = -INFINITY;
+  if (tid == 0) node_parent[0] = -1, node_label[0] = -1;
+  if (len > 0) {
+    float nx[kRowRegs];
+    fetch(nx, x);
+    stage(nx, x, 0);
   }
   __syncthreads();
 
   for (int t = 0; t < len; ++t) {
-    // ---- log-softmax of the frame
-    const float* row = x + int64_t(t) * V;
-    float mx = -INFINITY;
-    for (int i = tid; i < V; i += kCtcThreads) mx = fmaxf(mx, row[i]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = red[0];
+    const int buf = t & 1;
+    const float* lraw = raw + buf * Vp;
+    const bool more = t + 1 < len;
+    const float* nrow = x + int64_t(t + 1) * V;
+    float nx[kRowRegs];
+    if (more) fetch(nx, nrow);
+
+    // ---- normaliser of the frame from the 8 per-warp partials (fixed order: every thread gets the same bits)
+    float norm, mlp;
+    {
+      const float* pp = part + buf * 3 * kCtcWarps;
+      float m = pp[0], s = pp[kCtcWarps], mnb = pp[2 * kCtcWarps];
 #pragma unroll
-    for (int w = 1; w < kCtcThreads / 32; ++w) mx = fmaxf(mx, red[w]);
-    float sum = 0.f;
-    for (int i = tid; i < V; i += kCtcThreads) sum += expf(row[i] - mx);
-    sum = warp_sum(sum);
-    __syncthreads();
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f;
-      for (int w = 0; w < kCtcThreads / 32; ++w) s += red[w];
-      s_norm = mx + logf(s);
+      for (int w = 1; w < kCtcWarps; ++w) {
+        lse_merge(m, s, pp[w], pp[kCtcWarps + w]);
+        mnb = fmaxf(mnb, pp[2 * kCtcWarps + w]);
+      }
+      norm = m + logf(s);
+      mlp = mnb - norm;  // largest log-probability of a label (rounding is monotonic: no logp below exceeds it)
     }
-    __syncthreads();
-    const float norm = s_norm;
-    for (int i = tid; i < V; i += kCtcThreads) logp[i] = row[i] - norm;
-    __syncthreads();
 
-    // ---- the live prefixes at t (one thread: W <= 16 entries)
-    if (tid == 0) {
-      const int n = bm.n;
-      // branches = live prefixes by descending probability (stable insertion sort)
-      for (int i = 1; i < n; ++i) {
-        const int nd = bm.node[i];
-        const float tt = bm.total[i], bb = bm.blank[i], ll = bm.label[i];
-        int j = i - 1;
-        while (j >= 0 && bm.total[j] < tt) {
-          bm.node[j + 1] = bm.node[j], bm.total[j + 1] = bm.total[j], bm.blank[j + 1] = bm.blank[j], bm.label[j + 1] = bm.label[j];
-          --j;
-        }
-        bm.node[j + 1] = nd, bm.total[j + 1] = tt, bm.blank[j + 1] = bb, bm.label[j + 1] = ll;
-      }
-      for (int i = 0; i < n; ++i) bm.old_total[i] = bm.total[i], bm.old_blank[i] = bm.blank[i];
-      const float lp_blank = logp[0];
-      for (int i = 0; i < n; ++i) {
-        const int nd = bm.node[i], par = node_parent[nd];
-        if (par >= 0) {
-          const int lab = node_label[nd];
-          float nl = bm.label[i];
-          for (int j = 0; j < n; ++j)
-            if (bm.node[j] == par) {  // the parent prefix is live: paths that reach this prefix from it at t
-              const float prev = (lab == node_label[par]) ? bm.old_blank[j] : bm.old_total[j];
-              nl = lse2(nl, prev);
-              break;
-            }
-          bm.label[i] = nl + logp[lab + 1];
-        }
-        bm.blank[i] = bm.old_total[i] + lp_blank;
-        bm.total[i] = lse2(bm.blank[i], bm.label[i]);
-      }
-      for (int i = 0; i < kMaxBeam; ++i) bm.forbidden[i] = -1;
-      float lowest = INFINITY;
-      for (int i = 0; i < n; ++i) {
-        lowest = fminf(lowest, bm.total[i]);
-        const int par = node_parent[bm.node[i]];
-        for (int j = 0; j < n && par >= 0; ++j)
-          if (bm.node[j] == par) bm.forbidden[i] = j * n_lab + node_label[bm.node[i]];
-      }
-      bm.thr_score = n == W ? lowest : -INFINITY;
+    // ---- the live prefixes at t: lane i looks its parent up among them
+    const float ot = total, ob = blank;
+    int fj = -1;
+    float prev = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+      const int nj = __shfl_sync(kFull, node, j);
+      const float otj = __shfl_sync(kFull, ot, j), obj = __shfl_sync(kFull, ob, j);
+      // the parent prefix is live: paths that reach this prefix from it at t
+      if (lane < n && par >= 0 && nj == par) fj = j, prev = (lab == plab) ? obj : otj;
     }
-    __syncthreads();
-
-    // ---- one-label extensions.  Warp-level top-W in registers: lane j holds the warp's j-th best (ls, lc).
-    const int n = bm.n;
+    if (lane < n) {
+      if (par >= 0) {
+        float nl = label;
+        if (fj >= 0) nl = lse2(nl, prev);
+        label = nl + (lraw[lab + 1] - norm);
+      }
+      blank = ot + (lraw[0] - norm);
+      total = lse2(blank, label);
+    }
+    // extension codes (branch * (V-1) + label) whose prefix is already live
+    const int forbidden = (lane < n && fj >= 0) ? fj * n_lab + lab : -1;
     int forb[kMaxBeam];
 #pragma unroll
-    for (int j = 0; j < kMaxBeam; ++j) forb[j] = bm.forbidden[j];
+    for (int j = 0; j < kMaxBeam; ++j) forb[j] = __shfl_sync(kFull, forbidden, j);
+    // an extension must beat the W-th best live prefix (ties lose: live prefixes were inserted first)
+    float thr_s = -INFINITY;
+    if (n == W) {
+      float lo = lane < n ? total : INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(kFull, lo, o));
+      thr_s = lo;
+    }
+    int thr_c = -1;
+
+    // ---- one-label extensions.  Warp-level top-W in registers: lane j holds the warp's j-th best (ls, lc).
     float ls = -INFINITY;
     int lc = 0x7fffffff;
-    // an extension must beat the W-th best live prefix (ties lose: live prefixes were inserted first)
-    float thr_s = bm.thr_score;
-    int thr_c = -1;
     for (int bi = 0; bi < n; ++bi) {
-      const int lab_b = node_label[bm.node[bi]];
-      const float ot = bm.old_total[bi], ob = bm.old_blank[bi];
+      const int lab_b = __shfl_sync(kFull, lab, bi);
+      const float otb = __shfl_sync(kFull, ot, bi), obb = __shfl_sync(kFull, ob, bi);
+      if (fmaxf(otb, obb) + mlp < thr_s) continue;  // no extension of this branch reaches the bar (warp-uniform)
       for (int k0 = 0; k0 < n_lab; k0 += kCtcThreads) {
         const int k = k0 + tid;
         float sc = -INFINITY;
         int cd = 0x7fffffff;
+        bool pending = false;
         if (k < n_lab) {
           cd = bi * n_lab + k;
-          sc = logp[k + 1] + (k == lab_b ? ob : ot);
-          bool live_child = false;
+          sc = (lraw[k + 1] - norm) + (k == lab_b ? obb : otb);
+          pending = sc != -INFINITY && better(sc, cd, thr_s, thr_c);
+          if (pending) {
+            bool live_child = false;
 #pragma unroll
-          for (int j = 0; j < kMaxBeam; ++j) live_child |= forb[j] == cd;
-          if (live_child) sc = -INFINITY;  // already advanced above
+            for (int j = 0; j < kMaxBeam; ++j) live_child |= forb[j] == cd;
+            if (live_child) pending = false, sc = -INFINITY;  // already advanced above
+          }
         }
-        bool pending = sc != -INFINITY && better(sc, cd, thr_s, thr_c);
-        unsigned mask = __ballot_sync(0xffffffffu, pending);
+        unsigned mask = __ballot_sync(kFull, pending);
         while (mask) {
           const int leader = __ffs(mask) - 1;
-          const float bsc = __shfl_sync(0xffffffffu, sc, leader);
-          const int bcd = __shfl_sync(0xffffffffu, cd, leader);
+          const float bsc = __shfl_sync(kFull, sc, leader);
+          const int bcd = __shfl_sync(kFull, cd, leader);
           // sorted insert: elements better than the newcomer form a prefix of the lanes
-          const int pos = __popc(__ballot_sync(0xffffffffu, better(ls, lc, bsc, bcd)));
-          const float up_s = __shfl_up_sync(0xffffffffu, ls, 1);
-          const int up_c = __shfl_up_sync(0xffffffffu, lc, 1);
+          const int pos = __popc(__ballot_sync(kFull, better(ls, lc, bsc, bcd)));
+          const float up_s = __shfl_up_sync(kFull, ls, 1);
+          const int up_c = __shfl_up_sync(kFull, lc, 1);
           if (lane == pos) ls = bsc, lc = bcd;
           else if (lane > pos) ls = up_s, lc = up_c;
           if (lane >= W) ls = -INFINITY, lc = 0x7fffffff;
-          const float ws = __shfl_sync(0xffffffffu, ls, W - 1);
-          const int wc = __shfl_sync(0xffffffffu, lc, W - 1);
+          const float ws = __shfl_sync(kFull, ls, W - 1);
+          const int wc = __shfl_sync(kFull, lc, W - 1);
           if (ws != -INFINITY && better(ws, wc, thr_s, thr_c)) thr_s = ws, thr_c = wc;  // list full: its tail is the bar
           if (lane == leader) pending = false;
           else pending = pending && better(sc, cd, thr_s, thr_c);
-          mask = __ballot_sync(0xffffffffu, pending);
+          mask = __ballot_sync(kFull, pending);
         }
       }
     }
-    if (lane < W) cand_score[warp * W + lane] = ls, cand_code[warp * W + lane] = lc;
+    const int n_items = kCtcWarps * W;
+    float* cs = cand_score + buf * n_items;
+    int* cc = cand_code + buf * n_items;
+    if (lane < W) cs[warp * W + lane] = ls, cc[warp * W + lane] = lc;
+    if (more) stage(nx, nrow, buf ^ 1);
     __syncthreads();
 
-    // ---- next beam: the best W of live prefixes + the warps' lists (warp 0; a handful of items per lane)
-    if (warp == 0) {
-      const int total_items = (kCtcThreads / 32) * W;
-      int n_win = 0;
-      for (int round = 0; round < W; ++round) {
-        float bs = -INFINITY;
-        int bc = 0x7fffffff, bpos = -1;
-        for (int i = lane; i < total_items + n; i += 32) {
-          float s;
-          int c;
-          if (i < n) s = bm.total[i], c = i - kMaxBeam;  // live prefixes were inserted first
-          else s = cand_score[i - n], c = cand_code[i - n];
-          if (s != -INFINITY && better(s, c, bs, bc)) bs = s, bc = c, bpos = i;
-        }
+    // ---- next beam: the best W of live prefixes + the warps' lists.  Lane-local items: its live prefix (code
+    // i - kMaxBeam: live prefixes were inserted first) and candidates lane, lane + 32, ... of the 8 W entries
+    float is[1 + kCtcWarps * kMaxBeam / 32];
+    int ic[1 + kCtcWarps * kMaxBeam / 32];
+    is[0] = lane < n ? total : -INFINITY, ic[0] = lane < n ? lane - kMaxBeam : 0x7fffffff;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-          const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-          if (os != -INFINITY && better(os, oc, bs, bc)) bs = os, bc = oc, bpos = op;
-        }
-        if (bpos < 0) break;  // fewer than W items exist
-        if (lane == 0) {
-          bm.win_code[n_win] = bc, bm.win_score[n_win] = bs;
-          if (bpos < n) bm.total[bpos] = -INFINITY;  // taken (its values are re-read from the saved copies below)
-          else cand_score[bpos - n] = -INFINITY;
-        }
-        ++n_win;
-        __syncwarp();
-      }
-      if (lane == 0) bm.n_win = n_win;
+    for (int r = 0; r < kCtcWarps * kMaxBeam / 32; ++r) {
+      const int i = lane + 32 * r;
+      is[r + 1] = i < n_items ? cs[i] : -INFINITY, ic[r + 1] = i < n_items ? cc[i] : 0x7fffffff;
     }
-    __syncthreads();
+    float win_s = -INFINITY;
+    int win_c = 0x7fffffff, n_win = 0;
+    for (int round = 0; round < W; ++round) {
+      float bs = is[0];
+      int bc = ic[0];
+#pragma unroll
+      for (int r = 1; r <= kCtcWarps * kMaxBeam / 32; ++r)
+        if (better(is[r], ic[r], bs, bc)) bs = is[r], bc = ic[r];
+      const uint32_t key = order_key(bs);
+      const uint32_t kmax = __reduce_max_sync(kFull, key);
+      if (kmax == order_key(-INFINITY)) break;  // fewer than W items exist
+      const int cmin = __reduce_min_sync(kFull, key == kmax ? bc : 0x7fffffff);
+#pragma unroll
+      for (int r = 0; r <= kCtcWarps * kMaxBeam / 32; ++r)
+        if (ic[r] == cmin) is[r] = -INFINITY;  // taken (codes of valid items are unique)
+      if (lane == n_win) win_s = order_key_inv(kmax), win_c = cmin;
+      ++n_win;
+    }
 
-    if (tid == 0) {
-      // rebuild the beam from the winners; live prefixes keep (blank, label), extensions become new trie nodes
-      int nn = 0;
-      int node2[kMaxBeam];
-      float t2[kMaxBeam], b2[kMaxBeam], l2[kMaxBeam];
-      for (int w = 0; w < bm.n_win; ++w) {
-        const int c = bm.win_code[w];
-        if (c < 0) {
-          const int i = c + kMaxBeam;
-          node2[nn] = bm.node[i], t2[nn] = bm.win_score[w], b2[nn] = bm.blank[i], l2[nn] = bm.label[i];
-        } else {
-          const int bi = c / n_lab, k = c - bi * n_lab;
-          const int nd = bm.next_node < node_cap ? bm.next_node++ : node_cap - 1;  // cap is 1 + W * T: never exceeded
-          node_parent[nd] = bm.node[bi], node_label[nd] = k;
-          node2[nn] = nd, t2[nn] = bm.win_score[w], b2[nn] = -INFINITY, l2[nn] = bm.win_score[w];
-        }
-        ++nn;
+    // ---- rebuild: lane w becomes winner w; live prefixes keep (blank, label), extensions become new trie nodes
+    {
+      const bool mine = lane < n_win;
+      const bool is_ext = mine && win_c >= 0;
+      int bi = 0, k = 0;
+      if (is_ext) bi = win_c / n_lab, k = win_c - bi * n_lab;
+      const int src = mine ? (win_c < 0 ? win_c + kMaxBeam : bi) : 0;
+      const int s_node = __shfl_sync(kFull, node, src), s_par = __shfl_sync(kFull, par, src);
+      const int s_lab = __shfl_sync(kFull, lab, src), s_plab = __shfl_sync(kFull, plab, src);
+      const float s_blank = __shfl_sync(kFull, blank, src), s_label = __shfl_sync(kFull, label, src);
+      const unsigned ext_mask = __ballot_sync(kFull, is_ext);
+      if (is_ext) {
+        const int nd = min(next_node + __popc(ext_mask & ((1u << lane) - 1u)), node_cap - 1);  // cap is 1 + W * T: never exceeded
+        node = nd, par = s_node, plab = s_lab, lab = k, blank = -INFINITY, label = win_s;
+        if (warp == 0) node_parent[nd] = s_node, node_label[nd] = k;
+      } else if (mine) {
+        node = s_node, par = s_par, lab = s_lab, plab = s_plab, blank = s_blank, label = s_label;
+      } else {
+        node = -2, par = -1, lab = -1, plab = -1, blank = -INFINITY, label = -INFINITY;
       }
-      for (int i = 0; i < nn; ++i) bm.node[i] = node2[i], bm.total[i] = t2[i], bm.blank[i] = b2[i], bm.label[i] = l2[i];
-      bm.n = nn;
+      total = mine ? win_s : -INFINITY;
+      next_node += __popc(ext_mask);
+      n = n_win;
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- top path: walk the trie back from the most probable live prefix, then emit forward with the
   // reference's groupby (consecutive duplicates collapse)
   if (tid == 0) {
-    int best = 0;
-    for (int i = 1; i < bm.n; ++i)
-      if (bm.total[i] > bm.total[best]) best = i;
-    int nd = bm.node[best], depth = 0;
+    int nd = node, depth = 0;  // the beam is sorted: the most probable live prefix is lane 0
     for (int p = nd; node_parent[p] >= 0; p = node_parent[p]) ++depth;
     int* ids = out_ids + int64_t(b) * T;
     // raw labels are written back to front into ids[0..depth), then compacted in place
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(kCtcThreads) ctc_beam_kernel(const float* __re
       if (i == 0 || ids[i] != ids[i - 1]) ids[m++] = ids[i];  // in place: m <= i always
     for (int i = m; i < T; ++i) ids[i] = -1;
     out_len[b] = m;
-    if (out_score) out_score[b] = len > 0 ? bm.total[best] : 0.f;
+    if (out_score) out_score[b] = len > 0 ? total : 0.f;
   }
 }
 
@@ -284,7 +329,7 @@ int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths
   SCATT_REQUIRE(V >= 2 && T >= 0 && B >= 0, "ctc_beam_decode: bad shape");
   if (B == 0) return SCATT_OK;
   const int node_cap = 1 + beam * (T > 0 ? T : 1);
-  const size_t smem = size_t((V + 3) & ~3) * 4 + size_t(node_cap) * 8 + size_t(kCtcThreads / 32) * beam * 8 + sizeof(Beam) + 16;
+  const size_t smem = size_t((V + 3) & ~3) * 8 + size_t(2 * 3 * kCtcWarps) * 4 + size_t(node_cap) * 8 + size_t(2 * kCtcWarps) * beam * 8 + 16;
   SCATT_REQUIRE(smem <= 200 * 1024, "ctc_beam_decode: T=%d, V=%d, beam=%d need %zu bytes of shared memory (limit 200 KB)", T, V,
                 beam, smem);
   static PerDeviceFlag configured;  // the attribute belongs to the device's context: once per device, to the limit

@@ -511,7 +511,7 @@ def stream_attention(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: i
     return outs
 
 
-ATTN_PLANES_MAX_T = 672  # longest key sequence of the TMA-fed tcgen05 attention kernel (3 blocks of 224 keys)
+ATTN_PLANES_MAX_T = 1568  # longest key sequence of the TMA-fed tcgen05 attention kernel (7 blocks of 224 keys)
 
 
 def stream_attention_planes(prec: Precision, qs, ks, vs, B: int, Tq: int, Tk: int, H: int, kind: int,

@@ -355,7 +355,7 @@ def test_stream_attention_key_mask(kind, B, T, mode):
 
 @pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
 @pytest.mark.parametrize("kind", ["self", "causal", "cross"])
-@pytest.mark.parametrize("B,T", [(2, 24), (3, 37), (8, 200), (1, 130), (2, 224), (5, 16), (2, 225), (3, 400), (2, 512), (1, 672), (24, 200), (40, 100), (12, 450)])
+@pytest.mark.parametrize("B,T", [(2, 24), (3, 37), (8, 200), (1, 130), (2, 224), (5, 16), (2, 225), (3, 400), (2, 512), (1, 672), (24, 200), (40, 100), (12, 450), (2, 673), (3, 1000), (1, 1568)])
 def test_stream_attention_planes(kind, B, T, mode):
     """TMA-fed tcgen05 kernel: operands are split planes inside a wider [rows, 768] buffer, like the QKV GEMM writes them."""
     H, D = 16, 256
