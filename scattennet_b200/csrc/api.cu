@@ -71,7 +71,9 @@ int scatt_debug_set_trace(void* dev_buf) {
   const int rc2 = debug_set_trace_attention(dev_buf);
   if (rc2 != SCATT_OK) return rc2;
   const int rc3 = debug_set_trace_fa(dev_buf);
-  return rc3 != SCATT_OK ? rc3 : debug_set_trace_block(dev_buf);
+  if (rc3 != SCATT_OK) return rc3;
+  const int rc4 = debug_set_trace_ctc(dev_buf);
+  return rc4 != SCATT_OK ? rc4 : debug_set_trace_block(dev_buf);
 }
 
 int scatt_split_planes(const float* x, int64_t rows, int64_t cols, int64_t ldx, float scale, void* planes, int plane_fmt,

@@ -239,6 +239,7 @@ int debug_set_block_cluster(int cl);
 int debug_set_trace(void* dev_buf);
 int debug_set_trace_attention(void* dev_buf);
 int debug_set_trace_fa(void* dev_buf);
+int debug_set_trace_ctc(void* dev_buf);
 int launch_attention(const scatt_attention_problem* p, int group, int B, int Tq, int Tk, int H, int hd, int64_t ldq,
                      int64_t ldk, int64_t ldv, int kind, int fmt, cudaStream_t s);
 bool attention_tc_supported(int Tq, int Tk, int hd, const scatt_attention_problem* p, int group);

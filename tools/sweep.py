@@ -65,7 +65,7 @@ def kernel_sweep(args):
     print(f"### stream attention, B*3 streams grouped, H=16, hd=16 (us per grouped launch, back-to-back in a CUDA graph)\n")
     print("| T | B | kind | engine | us | TFLOP/s (4BT^2D, causal half) | % bf16 peak | exp/s (1e12) |")
     print("|---|---|---|---|---|---|---|---|")
-    for T in (() if args.only == "linear" else (64, 128, 192, 200, 256, 320, 384, 448, 512)):
+    for T in (() if args.only == "linear" else tuple(int(v) for v in args.attn_T.split(","))):
         B = max(1, 12800 // T)
         qkv = [torch.randn(B * T, 3 * D, generator=gen).to(dev) for _ in range(3)]
         km = torch.ones(B, T, dtype=torch.uint8, device=dev)
@@ -82,6 +82,8 @@ def kernel_sweep(args):
                 ex = 3 * B * H * (T * (T + 1) / 2 if kind == 1 else T * T)
                 eng = "tcgen05 (TMA-fed)" if (prec.uses_planes and T <= F_.ATTN_PLANES_MAX_T) else "cuda-core fp32"
                 print(f"| {T} | {B} | {kn} | {mode} {eng} | {us:.1f} | {fl / us / 1e6:.1f} | {100 * fl / us / 1e6 / PEAK_TF:.2f} | {ex / us / 1e6:.2f} |", flush=True)
+    if args.only == "attention":
+        return
     print(f"\n### linear (tcgen05), 3 streams grouped (us per launch, back-to-back in a CUDA graph)\n")
     print("| M | N | K | epilogue | mode | us | TFLOP/s (2MNK) | % bf16 peak | GB/s (operands+outputs) |")
     print("|---|---|---|---|---|---|---|---|---|")
@@ -195,7 +197,8 @@ if __name__ == "__main__":
     ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512,1024")
     ap.add_argument("--T", type=int, default=200)
     ap.add_argument("--config", default="phoenix-2014t")
-    ap.add_argument("--only", default="", help="kernels: 'linear' skips the attention section")
+    ap.add_argument("--only", default="", help="kernels: 'linear' skips the attention section, 'attention' the linear one")
+    ap.add_argument("--attn-T", default="64,128,192,200,256,320,384,448,512", help="kernels: sequence lengths of the attention section")
     ap.add_argument("--schedules", default="", help="fusion: extra ncols:spc overrides, e.g. 128:1,256:1,256:4")
     a = ap.parse_args()
     {"batch": batch_sweep, "kernels": kernel_sweep, "membound": membound_sweep, "fusion": fusion_sweep}[a.what](a)
