@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) fusion_attention_kernel(const float* __re
   float* inv = sc + size_t(FQ) * T;    // [FQ] 1 / row sum
   pdl_launch_dependents();
   pdl_wait();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = scatt_warp_idx();
   const int b = blockIdx.y, i0 = blockIdx.x * FQ;
   const int nq = min(FQ, T - i0);
   const int nv = D >> 7;  // float4 chunks per lane

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(kThreadsFa, 2) stream_attention_fa_kernel(cons
   auto bar_pk = [&](int it) -> uint32_t { return it == 0 ? bar_p : bar_qk + 48 + 8 * it; };
   float* cls = reinterpret_cast<float*>(sm + L.cls);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int g = blockIdx.z / P.B, b = blockIdx.z % P.B, h = blockIdx.y;
   const FaProblem& A = P.p[g];
   const int m0 = blockIdx.x * QT;
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kThreadsFa2, 1) stream_attention_fa2_kernel(co
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base0 = (raw + 1023u) & ~1023u;
   const Fa2Smem L = fa2_smem_map(P.nblk, P.kbox);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int grp = warp / kGroupWarps, wl = warp % kGroupWarps;
   const uint32_t base = base0 + uint32_t(grp) * L.group_bytes;
   uint8_t* sm = smem_raw + (base - raw);

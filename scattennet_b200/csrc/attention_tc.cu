@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreadsAtt, 2) stream_attention_tc_kernel(con
   const uint32_t bar_s = base + kBarOff, bar_p = bar_s + 8, bar_o = bar_s + 16, tmem_ptr_addr = bar_s + 24;
   float* pad = reinterpret_cast<float*>(sm + kPadOff);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int g = blockIdx.z / P.B, b = blockIdx.z % P.B, h = blockIdx.y;
   const scatt_attention_problem& A = P.p[g];
   const int m0 = blockIdx.x * QT;

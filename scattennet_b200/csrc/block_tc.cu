@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_block_kernel(const __grid_co
   const bool tracing = SCATT_BLOCK_TRACE && g_trace_blk != nullptr && blockIdx.x == 0;
   (void)trp, (void)tracing;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.groups;
   // CL = 2: the CTAs of a cluster walk the same tiles; CTA `rank` owns the hidden chunks rank, rank + 2, ...
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;

@@ -109,6 +109,21 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
 #ifdef __CUDACC__
 
 // Blocks until the preceding kernel of the stream has completed (no-op without the launch attribute).
+// Warp index for role dispatch, taken through a shuffle so that the compiler treats it - and every branch on it - as
+// warp-uniform (CUTLASS's canonical_warp_idx_sync idiom).  With threadIdx.x >> 5 the role bodies count as divergent code:
+// every shuffle / vote / elect gets a divergence guard, uniform registers go unused and the attention kernel needs 95
+// instead of 76 registers; measured -4.4 % on the B=8 step in an A/B pair (SCATT_UNIFORM_WARP=0 is the old form).
+#ifndef SCATT_UNIFORM_WARP
+#define SCATT_UNIFORM_WARP 1
+#endif
+__device__ __forceinline__ int scatt_warp_idx() {
+#if SCATT_UNIFORM_WARP
+  return __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);
+#else
+  return int(threadIdx.x >> 5);
+#endif
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Lets the next kernel of the stream start its prologue.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kFtThreads, 1) frontend_tc_kernel(const __grid
   const uint32_t tmem_ptr_addr = bar0 + 64u;
   auto pos_full = [&](uint32_t w, uint32_t s) { return bar0 + 80u + 16u * w + 8u * s; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int pi = int(blockIdx.x) / P.ctas_per_pair, slot = int(blockIdx.x) % P.ctas_per_pair;
   const FtPair& Q = P.pair[pi];
   const int nj = Q.n_joints, nks = nj >= 16 ? 2 : 1;  // + 1 column for the bias

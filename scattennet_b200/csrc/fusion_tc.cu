@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) fusion_attention_tc_kernel(cons
   float* xch = reinterpret_cast<float*>(sm + 1024);  // [2][128] row max, [2][128] row sum
   const uint32_t ring = base + kFuCtrlBytes;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int b = blockIdx.z, m0 = blockIdx.y * kFuQT, slice0 = blockIdx.x * P.spc;
   const int T = P.T, D = P.D, tkp = P.tkp, kch = P.kch, qr = P.qr, ncols = P.ncols, stages = P.stages;
   const bool lo_q = P.terms >= 2, lo_k = P.terms >= 3;  // product terms: q_hi k_lo (3), q_lo k_hi (2), q_hi k_hi

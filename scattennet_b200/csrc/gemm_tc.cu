@@ -546,7 +546,7 @@ __device__ __forceinline__ void linear_tc_body(const TcParams& P) {
   auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int g = blockIdx.z;
   const int n0 = blockIdx.x * CW;
   const int64_t m0 = int64_t(blockIdx.y) * BM;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1) linear_tc_persist_kern
   auto gen = [&](uint32_t a) { return smem_raw + (a - raw); };
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen(tmem_ptr_addr));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = scatt_warp_idx(), lane = threadIdx.x & 31;
   const int num_kb = (P.K + BK - 1) / BK;
   const int tiles_n = (P.N + BN - 1) / BN, tiles_m = int((P.M + BM - 1) / BM);
   const int tiles_per_group = tiles_n * tiles_m, total_tiles = tiles_per_group * int(P.groups);

@@ -12,7 +12,7 @@ namespace {
 constexpr int kLsThreads = 256;
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = scatt_warp_idx();
   v = is_max ? warp_max(v) : warp_sum(v);
   __syncthreads();  // red may still be read from the previous reduction
   if (lane == 0) red[warp] = v;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) log_softmax_warp_kernel(const float* __re
   const int lane = threadIdx.x & 31;
   const int64_t M = int64_t(B) * T, warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int nvec = V >> 2;
-  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+  for (int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + scatt_warp_idx(); row < M; row += warps) {  // warp-uniform
     const float* xr = x + row * ldx;
     float4 v[kLsVec];
     float mx = -INFINITY;

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   LstmSmem& S = *reinterpret_cast<LstmSmem*>(lstm_smem_raw);
   float* cell = reinterpret_cast<float*>(lstm_smem_raw + sizeof(LstmSmem));  // [B][kUnits]
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = scatt_warp_idx();
   const int dir = blockIdx.y, slice = blockIdx.x, j0 = slice * kUnits;
 
   // resident weights: local row r = gate*8 + unit  <-  W_hh[dir][gate*H + j0 + unit][:]

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) rowwise_kernel(RowwiseGroup grp, int64_t 
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int nvec_row = N >> 2;
-  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+  for (int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + scatt_warp_idx(); row < M; row += warps) {  // warp-uniform
     float4 v[kMaxVec];
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i)
@@ -121,7 +121,7 @@ struct SplitKArgs {
 // 17 us per launch.  LayerNorm statistics: two-pass (mean, then centred squares) through warp shuffles + shared memory.
 __device__ __forceinline__ float block_sum(float v, float* red, int nwarps) {
   v = warp_sum(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = scatt_warp_idx();
   __syncthreads();  // red may still be read from the previous reduction
   if (lane == 0) red[warp] = v;
   __syncthreads();
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256) posembed_ln_kernel(const float* __restric
   const int64_t M = int64_t(B) * T;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int nvec_row = D >> 2;
-  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < M; row += warps) {
+  for (int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + scatt_warp_idx(); row < M; row += warps) {  // warp-uniform
     const int t = int(row % T);
     float4 v[kMaxVec];
 #pragma unroll
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(32 * kFeWarps, 2) frontend_kernel(const float*
   for (int br = 0; br < 2; ++br)  // the host passes W^T [nj][D]: a straight, coalesced copy
     for (int i = threadIdx.x * 4; i < nj * D; i += blockDim.x * 4)
       *reinterpret_cast<float4*>(wt[br] + i) = *reinterpret_cast<const float4*>(S.map_wt[br] + i);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = scatt_warp_idx();
   uint8_t* stage = reinterpret_cast<uint8_t*>(smem + 2 * wt_stride) + warp * 2 * kFeBufBytes;
   const uint32_t stage_addr = uint32_t(__cvta_generic_to_shared(stage));
   const int my_joint = lane < nj ? S.joint_idx[lane] : 0;
