@@ -296,6 +296,10 @@ typedef struct scatt_attention_planes_problem {
 
 int scatt_attention_planes(const scatt_attention_planes_problem* problems_host, int group, int B, int Tq, int Tk, int H,
                            int hd, int kind, int plane_fmt, int terms, void* stream);
+/* Developer aid: the schedule of scatt_attention_planes - 0 by item count (one (batch, head, query tile) item per CTA
+ * below 4096 items, the persistent two-group kernel from there on), 1 forces the persistent kernel (where its
+ * shared-memory map fits: Tk <= 672), 2 one item per CTA. */
+int scatt_debug_set_attn_persist(int mode);
 
 /* ------------------------------------------------------------------ K5: fusion attention */
 

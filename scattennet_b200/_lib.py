@@ -27,7 +27,7 @@ ATTN_SELF, ATTN_CAUSAL, ATTN_CROSS = 0, 1, 2
 SYMBOLS = (
     "scatt_abi_version", "scatt_version", "scatt_last_error", "scatt_last_kernel", "scatt_launch_count", "scatt_device_check",
     "scatt_debug_set_trace",
-    "scatt_split_planes", "scatt_l2_prefetch", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_attn_out_q", "scatt_attn_out_q_supported", "scatt_debug_set_block_cluster",
+    "scatt_split_planes", "scatt_l2_prefetch", "scatt_frontend", "scatt_posembed_layernorm", "scatt_linear", "scatt_linear_ws", "scatt_linear_workspace_bytes", "scatt_linear_ln_fused", "scatt_attn_block", "scatt_attn_block_supported", "scatt_attn_out_q", "scatt_attn_out_q_supported", "scatt_debug_set_block_cluster", "scatt_debug_set_attn_persist",
     "scatt_rowwise", "scatt_attention", "scatt_attention_planes", "scatt_fusion_attention", "scatt_fusion_attention_planes",
     "scatt_fusion_attention_planes_supported", "scatt_pool_pairs", "scatt_pool_pairs_group",
     "scatt_lstm_workspace_bytes", "scatt_lstm_bidir", "scatt_log_softmax", "scatt_finite_check",
@@ -121,6 +121,8 @@ def _declare(lib):
     lib.scatt_attn_block_supported.restype = i32
     lib.scatt_debug_set_block_cluster.argtypes = [i32]
     lib.scatt_debug_set_block_cluster.restype = i32
+    lib.scatt_debug_set_attn_persist.argtypes = [i32]
+    lib.scatt_debug_set_attn_persist.restype = i32
     lib.scatt_linear_ln_fused.argtypes = [i64, i32, i32, i32]
     lib.scatt_linear_ln_fused.restype = i32
     lib.scatt_rowwise.argtypes = [vp, i64, i32, i64, vp, i64, vp, vp, C.POINTER(Epilogue), vp, i64, vp, i32, vp]

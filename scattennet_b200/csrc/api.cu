@@ -144,6 +144,7 @@ int scatt_attn_out_q(const scatt_outq_problem* problems_host, int group, int64_t
 int scatt_attn_out_q_supported(int64_t M, int D, int N) { return attn_out_q_supported(M, D, N) ? 1 : 0; }
 
 int scatt_debug_set_block_cluster(int cluster) { return debug_set_block_cluster(cluster); }
+int scatt_debug_set_attn_persist(int mode) { return debug_set_attn_persist(mode); }
 
 int scatt_attn_block_supported(int64_t M, int D, int F) { return attn_block_supported(M, D, F) ? 1 : 0; }
 

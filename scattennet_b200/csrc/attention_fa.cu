@@ -20,6 +20,7 @@
 // all K / V rows of the sequence stay resident in shared memory).  Up to 7 blocks (1568 keys: 214 KB of
 // shared memory, one CTA per SM from the fourth block on); beyond that, and for dense additive masks,
 // the fp32 CUDA-core kernel runs.
+#include <atomic>
 #include <cfloat>
 #include <cstdlib>
 
@@ -908,6 +909,17 @@ int debug_set_trace_fa(void* dev_buf) {
   return SCATT_OK;
 }
 
+constexpr int kPersistMinItems = 4096;
+static std::atomic<int> g_attn_persist{[] {
+  const char* e = std::getenv("SCATT_ATTN_PERSIST");
+  return e ? (e[0] == '1' ? 1 : 2) : 0;
+}()};
+int debug_set_attn_persist(int mode) {
+  SCATT_REQUIRE(mode >= 0 && mode <= 2, "debug_set_attn_persist: 0 (by item count), 1 (persistent) or 2 (one item per CTA)");
+  g_attn_persist.store(mode, std::memory_order_relaxed);
+  return SCATT_OK;
+}
+
 bool attention_planes_supported(int Tq, int Tk, int hd) { return hd == HD && Tk >= 1 && Tk <= KMAX; }
 int attention_planes_max_keys() { return KMAX; }
 
@@ -940,12 +952,13 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
     const char* e = std::getenv("SCATT_FA2_STAGE");
     P.debug_stage = e ? std::atoi(e) : 0;
   }
-  // Opt-in (SCATT_ATTN_PERSIST=1): measured SLOWER than one item per CTA at every batch size tried
-  // (B = 8: 27.0 vs 24.1 us per grouped launch; B = 256: -1 %), see DESIGN.md section 7 - kept for the next iteration.
-  static const bool persist = [] {
-    const char* e = std::getenv("SCATT_ATTN_PERSIST");
-    return e && e[0] == '1';
-  }();
+  // Schedule: one item per CTA, or the persistent two-group kernel.  Measured with the warp-uniform role dispatch
+  // (profiles/r02_toggles.txt): B = 8 (768 items per launch) 0.886 vs 0.917 ms per step - the one-item kernel wins
+  // while the grid is a few waves; B = 64 / 256 (6 k / 25 k items) +1.6 % / +2.7 % frames/s for the persistent one.
+  // 0 = by item count, 1 / 2 = force persistent / one-item (SCATT_ATTN_PERSIST=1|0, scatt_debug_set_attn_persist).
+  const int items = group * B * H * ((Tq + QT - 1) / QT);
+  const int mode = g_attn_persist.load(std::memory_order_relaxed);
+  const bool persist = fa2_smem_map(P.nblk, P.kbox).total <= 227u * 1024u && (mode == 1 || (mode == 0 && items >= kPersistMinItems));
   if (persist) {
     const Fa2Smem L2 = fa2_smem_map(P.nblk, P.kbox);
     static PerDeviceFlag attr2_done;
@@ -955,7 +968,6 @@ int launch_attention_planes(const scatt_attention_planes_problem* p, int group, 
       attr2_done.store(true);
     }
     SCATT_REQUIRE(L2.total <= 227u * 1024u, "attention(planes): shared memory map of the persistent kernel exceeds 227 KB");
-    const int items = group * B * H * ((Tq + QT - 1) / QT);
     dim3 grid2(unsigned(min(148, (items + 1) / 2)));
     if (fmt == SCATT_PLANE_F16)
       (void)launch_kernel(stream_attention_fa2_kernel<SCATT_PLANE_F16>, grid2, dim3(kThreadsFa2), L2.total, s, P);

@@ -251,6 +251,7 @@ int launch_attn_block(const scatt_block_problem* p, int group, int64_t M, int D,
                       cudaStream_t s);
 int debug_set_trace_block(void* dev_buf);
 int debug_set_block_cluster(int cl);
+int debug_set_attn_persist(int mode);
 int debug_set_trace(void* dev_buf);
 int debug_set_trace_attention(void* dev_buf);
 int debug_set_trace_fa(void* dev_buf);

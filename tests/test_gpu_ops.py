@@ -353,10 +353,19 @@ def test_stream_attention_key_mask(kind, B, T, mode):
     assert float((out.cpu() - ref).abs().max()) <= ATT_TOL[mode]
 
 
+@pytest.fixture(params=[2, 1], ids=["one_item_per_cta", "persistent"])
+def attn_schedule(request):
+    """Both schedules of scatt_attention_planes on every shape (the library picks by item count: >= 4096 items run the
+    persistent two-group kernel, which the small test shapes would never reach)."""
+    L.check(L.load().scatt_debug_set_attn_persist(request.param), "set_attn_persist")
+    yield request.param
+    L.check(L.load().scatt_debug_set_attn_persist(0), "set_attn_persist")
+
+
 @pytest.mark.parametrize("mode", ["fp16x3", "bf16x3", "fp16x1"])
 @pytest.mark.parametrize("kind", ["self", "causal", "cross"])
 @pytest.mark.parametrize("B,T", [(2, 24), (3, 37), (8, 200), (1, 130), (2, 224), (5, 16), (2, 225), (3, 400), (2, 512), (1, 672), (24, 200), (40, 100), (12, 450), (2, 673), (3, 1000), (1, 1568)])
-def test_stream_attention_planes(kind, B, T, mode):
+def test_stream_attention_planes(kind, B, T, mode, attn_schedule):
     """TMA-fed tcgen05 kernel: operands are split planes inside a wider [rows, 768] buffer, like the QKV GEMM writes them."""
     H, D = 16, 256
     prec = F_.get_precision(mode)
@@ -564,3 +573,22 @@ def test_frontend_gather_exact_and_embeddings():
     with pytest.raises(IndexError):
         big, _ = synth.synth_batch(1, 257, seed=2)
         frontend_forward(prec, mods, big.to(DEV), idxs, 1, 257)
+
+
+def test_stream_attention_planes_automatic_schedule():
+    """4160 items (>= 4096): the automatic choice is the persistent kernel; same result as the one-item schedule bit for bit."""
+    B, T, H, D = 130, 200, 16, 256
+    prec = F_.get_precision("fp16x3")
+    planes = F_.split_planes(rnd(B * T, 3 * D, seed=11), prec)
+    mask = (torch.arange(T)[None] < torch.tensor(synth.parity_lengths(B, T))[:, None]).long()
+    km = F_.key_mask_u8(mask.to(DEV))
+    run = lambda: F_.stream_attention_planes(prec, [(planes, 0)], [(planes, D)], [(planes, 2 * D)], B, T, T, H, 1, key_mask=km)[0]
+    auto = run()
+    assert L.load().scatt_last_kernel().decode().startswith("stream_attention_fa2_kernel")
+    L.check(L.load().scatt_debug_set_attn_persist(2), "set_attn_persist")
+    try:
+        one = run()
+        assert L.load().scatt_last_kernel().decode().startswith("stream_attention_fa_kernel")
+    finally:
+        L.check(L.load().scatt_debug_set_attn_persist(0), "set_attn_persist")
+    assert torch.equal(auto.planes, one.planes)
