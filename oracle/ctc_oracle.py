@@ -22,6 +22,8 @@ vectors for this path).  What pins this file instead (``tests/test_oracle_ctc.py
   * with a beam wide enough to hold every prefix, prefix beam search is exact: its best labelling and
     score must equal a brute-force enumeration of all alignments (known-answer check of the recursion);
   * hand-computed 2-step cases; invariance of the result under the reference's rotation + ``+1``;
+  * ``beam_search_set_form`` - the heap-free restatement the device kernel implements - returns the same ``W`` paths
+    and scores as the sequential restatement on random logits of every sharpness;
   * the input of TensorFlow's own op test (``ctc_decoder_ops_test.py::testCTCDecoderBeamSearch``: 5 x 6 probability
     matrix, beam_width 2, top_paths 2) with the two decoded label sequences that test expects - REPRODUCED FROM
     MEMORY (the file cannot be fetched offline), labels only, so it is supporting evidence, not a pin.
@@ -137,6 +139,127 @@ def beam_search_top_paths(logits: np.ndarray, beam_width: int, top_paths: int) -
                     c.newp = [LOG_ZERO, LOG_ZERO, LOG_ZERO]
     ranked = sorted(leaves, key=lambda e: -e.newp[0])  # stable, like the single-best max() over the same order
     return [(e.labels(), e.newp[0]) for e in ranked[:top_paths]]
+
+
+# ----------------------------------------------------------------------------- set formulation (what csrc/ctc.cu computes)
+
+
+def _f32_lse(a, b):
+    a, b = np.float32(a), np.float32(b)
+    if a == LOG_ZERO:
+        return b
+    if b == LOG_ZERO:
+        return a
+    return np.float32(max(a, b) + np.float32(np.log1p(np.float32(np.exp(np.float32(-abs(np.float32(a - b))))))))
+
+
+class _Live:
+    __slots__ = ("labels", "par", "lab", "plab", "total", "blank", "label")
+
+
+def beam_search_set_form(logits: np.ndarray, beam_width: int, labels_per_frame: Optional[int] = None,
+                         stats: Optional[dict] = None) -> List[Tuple[List[int], float]]:
+    """The same search as ``beam_search_top_paths(logits, W, W)`` restated without the sequential heap, in fp32 - the
+    algorithm of the device kernel (``csrc/ctc.cu``), kept here so that it can be checked against the sequential
+    restatement on the CPU (``tests/test_oracle_ctc.py``).
+
+    A step of the original is: advance the live prefixes; then, branches in beam order and labels in ascending
+    order, push every extension that beats the current worst leaf (popping that leaf).  Two facts reduce it to sets:
+      * the leaves at the end are the best ``W`` of (live prefixes + generated extensions), ties to the earlier insertion;
+      * an extension is generated unless its branch is skipped, and a branch ``p`` is skipped when ``is_candidate(oldp)``
+        fails - harmless, none of its extensions (nor those of its later children) could enter - or when ``p`` was DEACTIVATED: ``p`` had been popped before
+        the label loop of its (live, earlier) parent reached ``label(p)``; the parent then finds the child inactive,
+        scores it as a fresh extension, fails, and resets its probabilities including ``oldp``.
+    So only the set of grown branches has to be reproduced, by counting, in branch order, how many items beat a total.
+    Counts over a whole branch need only the frame's ``2 W`` best labels (``labels_per_frame``; ``None`` = all): a prefix
+    places at most ``W`` extensions, at most ``W - 1`` labels are live children of it, one label (its own last label) is
+    scored from the blank-ending mass and may sink - and a count that covers every listed label is >= ``W`` anyway.  The
+    one count that depends on label ORDER (extensions ``(m, k)`` with ``k < label(p)``) scans all labels."""
+    t_len, v = logits.shape
+    n_lab = v - 1
+    root = _Live()
+    root.labels, root.par, root.lab, root.plab = [], None, -1, -1
+    root.total, root.blank, root.label = np.float32(0), np.float32(0), np.float32(LOG_ZERO)
+    live = [root]
+    w = beam_width
+    for t in range(t_len):
+        row = logits[t].astype(np.float32)
+        mx = np.float32(row.max())
+        norm = np.float32(mx + np.log(np.exp(row - mx, dtype=np.float32).sum(dtype=np.float32)))
+        logp = (row - norm).astype(np.float32)
+        n = len(live)
+        ot, ob = [p.total for p in live], [p.blank for p in live]
+        fj = [-1] * n
+        for i, p in enumerate(live):
+            if p.par is not None:
+                for j, q in enumerate(live):
+                    if q is p.par:
+                        fj[i] = j
+                nl = p.label
+                if fj[i] >= 0:
+                    nl = _f32_lse(nl, ob[fj[i]] if p.lab == p.plab else ot[fj[i]])
+                p.label = np.float32(nl + logp[p.lab])
+            p.blank = np.float32(ot[i] + logp[n_lab])
+            p.total = _f32_lse(p.blank, p.label)
+        a = [p.total for p in live]
+        forb = [set() for _ in range(n)]
+        for j in range(n):
+            if fj[j] >= 0:
+                forb[fj[j]].add(live[j].lab)
+        order = sorted(range(n_lab), key=lambda k: (-float(logp[k]), k))
+        top = order if labels_per_frame is None else order[:labels_per_frame]
+
+        def score(i, k):
+            return np.float32(logp[k] + (ob[i] if k == live[i].lab else ot[i]))
+
+        def count_listed(i, tau, ge):
+            c = 0
+            for k in top:
+                if k not in forb[i]:
+                    s = score(i, k)
+                    c += s != LOG_ZERO and ((s >= tau) if ge else (s > tau))
+            return c
+
+        grown, dead = [False] * n, [False] * n
+        for m in range(n):
+            # (the original also skips a branch whose old total does not beat the current worst leaf; none of its extensions
+            # could enter, and neither could those of its later children, so that skip needs no reproduction)
+            grown[m] = (not dead[m]) and ot[m] != LOG_ZERO
+            if not grown[m]:
+                continue
+            for j in range(m + 1, n):
+                if fj[j] != m:
+                    continue
+                base = sum(1 for l in range(n) if l != j and (a[l] > a[j] or (a[l] == a[j] and l > j)))
+                base += sum(count_listed(i, a[j], False) for i in range(m) if grown[i])
+                if base >= w:
+                    dead[j] = True
+                elif base + count_listed(m, a[j], False) >= w:
+                    if stats is not None:
+                        stats["scans"] = stats.get("scans", 0) + 1
+                    part = sum(1 for k in range(live[j].lab) if k not in forb[m] and score(m, k) != LOG_ZERO and score(m, k) > a[j])
+                    dead[j] = base + part >= w
+        if stats is not None:
+            stats["steps"] = stats.get("steps", 0) + 1
+            stats["deactivated"] = stats.get("deactivated", 0) + sum(dead)
+        items = [(-float(a[i]), 0, i, -1) for i in range(n)]
+        for i in range(n):
+            if grown[i]:
+                for k in top:
+                    if k not in forb[i] and score(i, k) != LOG_ZERO:
+                        items.append((-float(score(i, k)), 1, i, k))
+        items.sort()
+        nxt = []
+        for neg, kind, i, k in items[:w]:
+            if kind == 0:
+                nxt.append(live[i])
+            else:
+                q = _Live()
+                q.labels, q.par, q.lab, q.plab = live[i].labels + [k], live[i], k, live[i].lab
+                q.total, q.blank, q.label = np.float32(-neg), np.float32(LOG_ZERO), np.float32(-neg)
+                nxt.append(q)
+        live = nxt
+    return [(p.labels, float(p.total)) for p in live]
 
 
 def ctc_decode(gloss_logits: np.ndarray, beam_size: int, input_lengths: Sequence[int]) -> List[List[int]]:

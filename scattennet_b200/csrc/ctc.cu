@@ -9,28 +9,31 @@
 // One CTA per sequence: seven PRODUCER warps and one SEARCH warp, no block-wide barrier inside the time loop.
 //
 // Producers (warps 1..7, one frame each, round-robin): everything about a frame that does not depend on the beam -
-// the softmax normaliser, the blank logit, and the frame's L = min(V - 1, 2 W - 1) best labels in the order
+// the softmax normaliser, the blank logit, and the frame's L = min(V - 1, 2 W) best labels in the order
 // (logit descending, label ascending), found by L rounds of a warp arg-max (lane-local scan of <= 36 registers,
 // redux.sync on an order-preserving integer image of the value, redux.sync min on the class index among the
-// equals).  A record of 2 + 2 L words per frame goes to shared memory behind a ready flag.  Why 2 W - 1 labels are
+// equals).  A record of 2 + 2 L words per frame goes to shared memory behind a ready flag.  Why 2 W labels are
 // enough: a prefix can put at most W extensions into the next beam, they are its W best labels that are not
-// already live children of it, and at most W - 1 labels are (every other live prefix); the one label scored from
-// the prefix's blank-ending mass instead of its total only sinks in that order.
+// already live children of it, at most W - 1 labels are (every other live prefix), and one label - the prefix's own
+// last label - is scored from the blank-ending mass instead of the total and can sink out of that order.
 // Search (warp 0): the beam (<= W <= 16 live prefixes) lives in registers, lane i = prefix i (trie node, parent,
 // last label, parent's last label, log-probabilities total / blank / label), always sorted by descending total.
 // A time step is: wait for the frame's record; advance the live prefixes (lane i finds its parent among them by
-// shuffles); score the <= n * L candidate extensions (branch, label) - MAXR registers per lane - dropping those
-// below the W-th best live prefix and the live children; W rounds of the same redux arg-max over live prefixes +
-// candidates (order: probability, ties to the earlier insertion code - the sequential push / pop-bottom of the
-// original reduces to exactly this top-W selection because an extension can never beat the prefix it extends);
-// lane w becomes winner w.  The only global loads on the serial path - the next frame's logits of the labels that
-// can be live then (own last labels + the L candidates) - are issued at the top of the step and consumed by the next.
+// shuffles); score the <= n * L candidate extensions (branch, label) - MAXR registers per lane; decide which
+// branches the sequential original actually grows (see the comment at that pass: a popped prefix can be
+// deactivated before its turn); W rounds of the same redux arg-max over live prefixes + candidates of the grown
+// branches (order: probability, ties to the earlier insertion code - the sequential push / pop-bottom of the original
+// reduces to exactly this top-W selection over what it generates); lane w becomes winner w.  The only global loads
+// on the serial path - the next frame's logits of the labels that can be live then (own last labels + the L
+// candidates) - are issued at the top of the step and consumed by the next.
 // The prefix trie (parent, label per node; at most 1 + W * T nodes) lives in shared memory, written and walked back by
 // the search warp; only token ids leave the chip.
+// oracle/ctc_oracle.py::beam_search_set_form is this algorithm on the CPU; tests/test_oracle_ctc.py checks it against
+// the sequential restatement (all W paths and scores).
 //
 // Rounding note: candidates are ranked per frame by logit, the search ranks extensions by fl(logp + prefix mass);
 // two labels whose logits differ can collide in that sum, and the tie then goes to the lower label.  The two orders
-// can only disagree about the (2 W - 1)-th label of a frame, which matters only if one prefix both owns all other
+// can only disagree about the 2W-th label of a frame, which matters only if one prefix both owns all other
 // live prefixes as children and wins every slot of the next beam - and the host oracle (double precision) has no
 // defined answer for such collisions either.
 #include <cfloat>
@@ -259,9 +262,6 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_beam_kernel(const float* _
     int forb[FW];
 #pragma unroll
     for (int j = 0; j < FW; ++j) forb[j] = __shfl_sync(kFull, forbidden, j);
-    // an extension must beat the W-th best live prefix (ties lose: live prefixes were inserted first)
-    float thr_s = -INFINITY;
-    if (n == W) thr_s = order_key_inv(__reduce_min_sync(kFull, lane < n ? order_key(total) : 0xffffffffu));
 
     const long long c2 = clock64();
     // ---- items of the selection: this lane's live prefix (code i - kMaxBeam: live prefixes were inserted first)
@@ -281,13 +281,78 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_beam_kernel(const float* _
         const float otb = __shfl_sync(kFull, ot, bi), obb = __shfl_sync(kFull, ob, bi);
         const float sc = lpk + (k == lab_b ? obb : otb);
         const int cd = bi * n_lab + k;
-        bool ok = lane + 32 * r < n_cand && sc != -INFINITY && better(sc, cd, thr_s, -1);
+        bool ok = lane + 32 * r < n_cand && sc != -INFINITY;
         if (ok) {
 #pragma unroll
           for (int j = 0; j < FW; ++j) ok = ok && forb[j] != cd;  // a live child was advanced above
         }
         if (ok) is[r + 1] = sc, ic[r + 1] = cd;
       }
+    }
+
+    // ---- which branches the original actually grows.  Its step is sequential - branches in beam order, labels in
+    // ascending order, every candidate better than the current worst leaf pops that leaf - and a live prefix p that was
+    // popped before its parent's label loop reaches label(p) is deactivated there INCLUDING the old probabilities its own
+    // turn as a branch would grow from (ctc_beam_search.h: "Deactivate child"): the extensions of p are then never
+    // generated.  Everything else of the sequence reduces to "best W of live prefixes + generated extensions", so only
+    // the set of grown branches has to be reproduced, in branch order m = 0 .. n-1:
+    //   grown(m)  = p_m not deactivated;
+    //   for every live child p_j (j > m) of a grown p_m: p_j is deactivated iff at least W items generated before the
+    //   loop of m reaches label(p_j) beat its total: live prefixes, extensions of grown branches < m, and extensions
+    //   (m, k) with k < label(p_j).
+    // Counts over a whole branch come from the 2 W labels in registers and saturate correctly: if every listed label of a
+    // branch beats a total there are >= W of them.  Only the count over k < label(p_j) depends on label ORDER and scans
+    // the frame's logits (every tenth step or so).
+    // (The original also skips a branch whose old total does not beat the current worst leaf - none of its extensions, nor
+    // those of its later children, could enter: that skip needs no reproduction.  And a step without a live child ordered
+    // after its live parent has nothing to deactivate.)
+    unsigned grown = 0, dead = 0;
+    const unsigned pairs = __ballot_sync(kFull, lane < n && fj >= 0 && fj < lane);
+    for (int m = 0; m < n; ++m) {
+      const float o_m = __shfl_sync(kFull, ot, m);
+      if (((dead >> m) & 1u) || o_m == -INFINITY) continue;
+      grown |= 1u << m;
+      if (!pairs) continue;
+      unsigned kids = __ballot_sync(kFull, lane < n && fj == m && lane > m);
+      while (kids) {
+        const int j = __ffs(kids) - 1;
+        kids &= kids - 1;
+        const float a_j = __shfl_sync(kFull, total, j);
+        const int lab_j = __shfl_sync(kFull, lab, j);
+        int c1 = lane < n && lane != j && (total > a_j || (total == a_j && lane > j));
+        int cm = 0;
+#pragma unroll
+        for (int r = 0; r < MAXR; ++r) {
+          const int bi = cand_at[r] >> 8;
+          c1 += bi < m && ((grown >> bi) & 1u) && is[r + 1] > a_j;
+          cm += bi == m && is[r + 1] > a_j;
+        }
+        const int base = __reduce_add_sync(kFull, c1);
+        bool out = base >= W;
+        if (!out && base + __reduce_add_sync(kFull, cm) >= W) {
+          // ambiguous: count the extensions (m, k), k < label(p_j), that beat p_j - over all labels, in label order
+          const float ot_m = o_m, ob_m = __shfl_sync(kFull, ob, m);
+          const int lab_m = __shfl_sync(kFull, lab, m);
+          const float* row = x + int64_t(t) * V;
+          int cp = 0;
+#pragma unroll 4
+          for (int k = lane; k < lab_j; k += 32) {
+            const float sc = (__ldg(row + k + 1) - norm) + (k == lab_m ? ob_m : ot_m);
+            bool hit = sc > a_j;
+            const int cd = m * n_lab + k;
+#pragma unroll
+            for (int q = 0; q < FW; ++q) hit = hit && forb[q] != cd;
+            cp += hit;
+          }
+          out = base + __reduce_add_sync(kFull, cp) >= W;
+        }
+        if (out) dead |= 1u << j;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) {
+      const int bi = cand_at[r] >> 8;  // slots past n * L carry branch numbers >= n
+      if (bi >= kMaxBeam || !((grown >> bi) & 1u)) is[r + 1] = -INFINITY, ic[r + 1] = kNone;
     }
 
     const long long c3 = clock64();
@@ -380,7 +445,7 @@ int launch_ctc_beam(const float* logits, int B, int T, int V, const int* lengths
   SCATT_REQUIRE(V >= 2 && T >= 0 && B >= 0, "ctc_beam_decode: bad shape");
   if (B == 0) return SCATT_OK;
   const int node_cap = 1 + beam * (T > 0 ? T : 1);
-  const int L = std::min(V - 1, 2 * beam - 1);  // labels of a frame that can enter the beam (see the header)
+  const int L = std::min(V - 1, 2 * beam);  // labels of a frame that can enter the beam (see the header)
   const size_t smem = ctc_smem_bytes(T, L, node_cap);
   SCATT_REQUIRE(smem <= 200 * 1024, "ctc_beam_decode: T=%d, V=%d, beam=%d need %zu bytes of shared memory (limit 200 KB)", T, V,
                 beam, smem);

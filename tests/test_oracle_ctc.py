@@ -78,3 +78,45 @@ def test_tensorflow_op_test_vector_labels():
     (lab0, lp0), (lab1, lp1) = C.beam_search_top_paths(logits, beam_width=2, top_paths=2)
     assert lab0 == [1, 0] and lab1 == [0, 1, 0]
     assert lp0 > lp1
+
+
+def _logits(kind, rng, t_len, v):
+    x = rng.standard_normal((t_len, v)).astype(np.float32)
+    if kind in ("peaky", "mild"):
+        hot = np.where(rng.random(t_len) < 0.6, v - 1, rng.integers(0, v - 1, size=t_len))  # blank = last class here
+        x[np.arange(t_len), hot] += ((6.0 + 8.0 * rng.random(t_len)) if kind == "peaky" else 6.0 * rng.random(t_len)).astype(np.float32)
+    elif kind == "flat":
+        x *= np.float32(0.05)
+    return x
+
+
+@pytest.mark.parametrize("kind", ["peaky", "mild", "normal", "flat"])
+@pytest.mark.parametrize("beam", [1, 2, 3, 5, 8])
+def test_set_form_equals_sequential_search(kind, beam):
+    """The heap-free formulation the device kernel computes (best W of live prefixes + extensions of the branches the
+    sequential original actually grows, from each frame's 2W best labels) returns the same W paths and scores as the
+    sequential restatement - including the steps where the original deactivates a popped prefix and so never
+    generates its extensions (about every tenth step)."""
+    rng = np.random.default_rng(1000 * beam + len(kind))
+    stats = {}
+    for _ in range(10):
+        x = _logits(kind, rng, 20, 40)
+        want = C.beam_search_top_paths(x, beam, beam)
+        for lpf in (None, 2 * beam):
+            got = C.beam_search_set_form(x, beam, labels_per_frame=lpf, stats=stats)
+            assert [p[0] for p in got] == [p[0] for p in want], (kind, beam, lpf)
+            assert all(abs(g[1] - w[1]) <= 1e-4 * max(1.0, abs(w[1])) for g, w in zip(got, want))
+    if kind == "peaky" and beam >= 2:
+        assert stats["deactivated"] > 0  # the order-dependent case does occur in these inputs
+
+
+def test_fewer_than_2w_labels_are_not_enough():
+    """Beam 1 with one label per frame: the frame's best label repeats the prefix's last label right after it was appended
+    (its extension is scored from the blank-ending mass, -inf), and the second-best label is the one that extends."""
+    rng = np.random.default_rng(106)
+    differs = 0
+    for _ in range(6):
+        x = rng.standard_normal((14, 40)).astype(np.float32)
+        differs += C.beam_search_set_form(x, 1, labels_per_frame=1) != C.beam_search_set_form(x, 1, labels_per_frame=2)
+        assert [p[0] for p in C.beam_search_set_form(x, 1, labels_per_frame=2)] == [p[0] for p in C.beam_search_top_paths(x, 1, 1)]
+    assert differs > 0
