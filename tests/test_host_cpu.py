@@ -44,6 +44,16 @@ def test_linear_ln_fused_query_is_host_logic():
     assert lib.scatt_linear_ln_fused(400, 256, 1, simt) == 0
 
 
+def test_debug_setters_validate_their_argument():
+    """Host logic of the schedule overrides (no device needed): out-of-range modes are refused with an error string."""
+    lib = _lib.load()
+    assert lib.scatt_debug_set_attn_persist(0) == 0 and lib.scatt_debug_set_attn_persist(2) == 0
+    assert lib.scatt_debug_set_attn_persist(3) != 0 and b"debug_set_attn_persist" in lib.scatt_last_error()
+    assert lib.scatt_debug_set_attn_persist(0) == 0
+    assert lib.scatt_debug_set_block_cluster(3) != 0
+    assert lib.scatt_debug_set_block_cluster(0) == 0
+
+
 def test_ctypes_structs_match_header_sizes():
     import ctypes as C
 
